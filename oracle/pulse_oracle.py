@@ -1,0 +1,575 @@
+"""CPU oracle for the PULSE hot path (TEST INFRASTRUCTURE -- never imported by pulse_b200/).
+
+A standalone fp32 PyTorch-CPU restatement of the arithmetic of the reference's per-step rollout and
+update path, written from the behaviour of the reference functions cited beside each routine
+(paths relative to the reference tree).  It exists so that the CUDA path can be checked on a GPU box
+where the reference itself is not present, and so `bench.py` has a CPU arm (`cpu_baseline`,
+`--impl reference`, kind "port") that does the same work the reference's PyTorch path does.
+
+Pinning: `tests/test_oracle_vs_golden.py` checks every routine here against `tests/golden/*.npz`,
+which `tests/golden/make_golden.py` produced by running the reference's own functions (imported
+unmodified from /root/reference under `oracle/refshim`).  When /root/reference is present the
+same test also re-runs the reference live.  Integer outputs (frame indices, reset / terminate
+masks) must be identical; float outputs agree to 1e-6 or better (same op order, same library).
+
+Third-party arithmetic absent from the reference tree and restated here [3P-memory]:
+  * isaacgym.torch_utils (Isaac Gym Preview 4, unpinned): quat_mul (8-product form), quat_conjugate,
+    quat_from_angle_axis, normalize, normalize_angle.
+  * rl_games 1.1.4 (requirement.txt:27): ModelA2CContinuousLogStd neglogp / entropy,
+    torch_ext.policy_kl, swap_and_flatten01.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU arms may import this module.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import torch
+
+F32 = torch.float32
+NUM_BODIES = 24
+NUM_DOF = 69
+SELF_OBS = 358
+TASK_OBS_V6 = 576
+AMP_OBS = 196
+# dof columns dropped by the AMP "dof_subset" (L_Toe, R_Toe, L_Hand, R_Hand) -- humanoid.py:397,417-421
+AMP_DROPPED_JOINTS = (3, 7, 17, 22)  # joint index = body index - 1
+KEY_BODY_IDS = (7, 3, 22, 17)  # R_Ankle, L_Ankle, R_Wrist, L_Wrist -- env_im.yaml:36
+RESET_BODY_IDS = tuple(j for j in range(24) if j not in (3, 4, 7, 8))  # env_im.yaml:38
+# dt = control_freq_inv * sim dt = 2 * fp32(1/60) -> fp32(1/30)  (humanoid.py:122, config.py:47)
+STEP_DT = float(torch.tensor(1.0 / 60.0, dtype=F32) * 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# quaternion primitives (xyzw)
+# ------------------------------------------------------------------------------------------------
+def quat_mul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """isaacgym.torch_utils.quat_mul [3P-memory]: Hamilton product, 8-multiplication form."""
+    x1, y1, z1, w1 = a.unbind(-1)
+    x2, y2, z2, w2 = b.unbind(-1)
+    ww = (z1 + x1) * (x2 + y2)
+    yy = (w1 - y1) * (w2 + z2)
+    zz = (w1 + y1) * (w2 - z2)
+    xx = ww + yy + zz
+    qq = 0.5 * (xx + (z1 - x1) * (x2 - y2))
+    w = qq - ww + (z1 - y1) * (y2 - z2)
+    x = qq - xx + (x1 + w1) * (x2 + w2)
+    y = qq - yy + (w1 - x1) * (y2 + z2)
+    z = qq - zz + (z1 + y1) * (w2 - x2)
+    return torch.stack([x, y, z, w], dim=-1)
+
+
+def quat_conj(q: torch.Tensor) -> torch.Tensor:
+    """isaacgym.torch_utils.quat_conjugate [3P-memory]."""
+    return torch.cat([-q[..., :3], q[..., 3:]], dim=-1)
+
+
+def _unit(x: torch.Tensor, eps: float = 1e-9) -> torch.Tensor:
+    """isaacgym.torch_utils.normalize [3P-memory]: x / max(|x|, eps)."""
+    return x / x.norm(p=2, dim=-1).clamp(min=eps).unsqueeze(-1)
+
+
+def quat_rotate(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:45-55 (my_quat_rotate), any leading shape."""
+    w = q[..., 3:4]
+    u = q[..., :3]
+    a = v * (2.0 * w ** 2 - 1.0)
+    b = torch.cross(u, v, dim=-1) * w * 2.0
+    c = u * (u * v).sum(-1, keepdim=True) * 2.0
+    return a + b + c
+
+
+def wrap_angle(x: torch.Tensor) -> torch.Tensor:
+    """isaacgym.torch_utils.normalize_angle [3P-memory]."""
+    return torch.atan2(torch.sin(x), torch.cos(x))
+
+
+def quat_from_angle_axis(angle: torch.Tensor, axis: torch.Tensor) -> torch.Tensor:
+    """isaacgym.torch_utils.quat_from_angle_axis [3P-memory]."""
+    half = (angle / 2).unsqueeze(-1)
+    return _unit(torch.cat([_unit(axis) * half.sin(), half.cos()], dim=-1))
+
+
+def quat_to_angle_axis(q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """phc/utils/torch_utils.py:57-78."""
+    w = q[..., 3]
+    s = torch.sqrt(1 - w * w)
+    ang = wrap_angle(2 * torch.acos(w))
+    axis = q[..., :3] / s.unsqueeze(-1)
+    ok = s.abs() > 1e-5
+    z_axis = torch.zeros_like(axis)
+    z_axis[..., 2] = 1
+    ang = torch.where(ok, ang, torch.zeros_like(ang))
+    axis = torch.where(ok.unsqueeze(-1), axis, z_axis)
+    return ang, axis
+
+
+def quat_to_exp_map(q: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:81-97."""
+    ang, axis = quat_to_angle_axis(q)
+    return ang.unsqueeze(-1) * axis
+
+
+def exp_map_to_quat(e: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:148-172."""
+    ang = e.norm(dim=-1)
+    axis = e / ang.unsqueeze(-1)
+    ang = wrap_angle(ang)
+    ok = ang.abs() > 1e-5
+    z_axis = torch.zeros_like(e)
+    z_axis[..., 2] = 1
+    ang = torch.where(ok, ang, torch.zeros_like(ang))
+    axis = torch.where(ok.unsqueeze(-1), axis, z_axis)
+    return quat_from_angle_axis(ang, axis)
+
+
+def quat_to_six(q: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:100-113 (quat_to_tan_norm): rotated x-axis then rotated z-axis."""
+    ex = torch.zeros_like(q[..., :3])
+    ex[..., 0] = 1
+    ez = torch.zeros_like(q[..., :3])
+    ez[..., 2] = 1
+    return torch.cat([quat_rotate(q, ex), quat_rotate(q, ez)], dim=-1)
+
+
+def slerp(q0: torch.Tensor, q1: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:175-197.  `t` broadcasts against [...,1]; result not renormalised."""
+    c = (q0 * q1).sum(-1)
+    q1 = torch.where((c < 0).unsqueeze(-1), -q1, q1)
+    c = c.abs().unsqueeze(-1)
+    half = torch.acos(c)
+    s = torch.sqrt(1.0 - c * c)
+    ra = torch.sin((1 - t) * half) / s
+    rb = torch.sin(t * half) / s
+    out = ra * q0 + rb * q1
+    out = torch.where(s.abs() < 0.001, 0.5 * q0 + 0.5 * q1, out)
+    out = torch.where(c.abs() >= 1, q0, out)
+    return out
+
+
+def heading_angle(q: torch.Tensor) -> torch.Tensor:
+    """phc/utils/torch_utils.py:200-212."""
+    ex = torch.zeros_like(q[..., :3])
+    ex[..., 0] = 1
+    r = quat_rotate(q, ex)
+    return torch.atan2(r[..., 1], r[..., 0])
+
+
+def heading_quat(q: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """phc/utils/torch_utils.py:215-240 (calc_heading_quat / calc_heading_quat_inv)."""
+    h = heading_angle(q)
+    ez = torch.zeros_like(q[..., :3])
+    ez[..., 2] = 1
+    return quat_from_angle_axis(-h if inverse else h, ez)
+
+
+# ------------------------------------------------------------------------------------------------
+# MotionLib tables and queries
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class MotionTables:
+    """The flat per-frame buffers MotionLibBase.load_motions builds (motion_lib_base.py:287-316)."""
+    gts: torch.Tensor            # [F,24,3] global body translation
+    grs: torch.Tensor            # [F,24,4] global body rotation
+    lrs: torch.Tensor            # [F,24,4] local joint rotation
+    gvs: torch.Tensor            # [F,24,3] global linear velocity
+    gavs: torch.Tensor           # [F,24,3] global angular velocity
+    dvs: torch.Tensor            # [F,23,3] dof velocity
+    motion_aa: torch.Tensor      # [F,72]
+    lengths: torch.Tensor        # [M] f32 seconds
+    num_frames: torch.Tensor     # [M] i64
+    dt: torch.Tensor             # [M] f32
+    length_starts: torch.Tensor  # [M] i64 (exclusive cumsum of num_frames)
+    fps: Optional[torch.Tensor] = None
+    motion_bodies: Optional[torch.Tensor] = None        # [M,17]
+    motion_limb_weights: Optional[torch.Tensor] = None  # [M,10]
+
+    @property
+    def num_motions(self) -> int:
+        return int(self.lengths.shape[0])
+
+
+def frame_blend(time: torch.Tensor, length: torch.Tensor, num_frames: torch.Tensor,
+                dt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """motion_lib_base.py:546-556 (_calc_frame_blend).  Index results are int64 and exact."""
+    phase = torch.clip(time / length, 0.0, 1.0)
+    time = torch.where(time < 0, torch.zeros_like(time), time)
+    i0 = (phase * (num_frames - 1)).long()
+    i1 = torch.min(i0 + 1, num_frames - 1)
+    blend = torch.clip((time - i0 * dt) / dt, 0.0, 1.0)
+    return i0, i1, blend
+
+
+def motion_state(tb: MotionTables, motion_ids: torch.Tensor, motion_times: torch.Tensor,
+                 offset: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """motion_lib_base.py:434-517 (get_motion_state): gather two frames, lerp / slerp."""
+    i0, i1, blend = frame_blend(motion_times, tb.lengths[motion_ids], tb.num_frames[motion_ids], tb.dt[motion_ids])
+    f0 = i0 + tb.length_starts[motion_ids]
+    f1 = i1 + tb.length_starts[motion_ids]
+    b = blend.unsqueeze(-1).unsqueeze(-1)
+
+    pos = (1.0 - b) * tb.gts[f0] + b * tb.gts[f1]
+    if offset is not None:
+        pos = pos + offset[..., None, :]
+    vel = (1.0 - b) * tb.gvs[f0] + b * tb.gvs[f1]
+    ang_vel = (1.0 - b) * tb.gavs[f0] + b * tb.gavs[f1]
+    dof_vel = (1.0 - b) * tb.dvs[f0] + b * tb.dvs[f1]
+    local_rot = slerp(tb.lrs[f0], tb.lrs[f1], b)
+    dof_pos = quat_to_exp_map(local_rot[:, 1:]).reshape(local_rot.shape[0], -1)  # :561-564
+    rot = slerp(tb.grs[f0], tb.grs[f1], b)
+    out = {
+        "root_pos": pos[:, 0].clone(), "root_rot": rot[:, 0].clone(), "dof_pos": dof_pos,
+        "root_vel": vel[:, 0].clone(), "root_ang_vel": ang_vel[:, 0].clone(),
+        "dof_vel": dof_vel.reshape(dof_vel.shape[0], -1), "motion_aa": tb.motion_aa[f0],
+        "rg_pos": pos, "rb_rot": rot, "body_vel": vel, "body_ang_vel": ang_vel,
+        "frame_idx0": i0, "frame_idx1": i1, "blend": blend,
+    }
+    if tb.motion_bodies is not None:
+        out["motion_bodies"] = tb.motion_bodies[motion_ids]
+    if tb.motion_limb_weights is not None:
+        out["motion_limb_weights"] = tb.motion_limb_weights[motion_ids]
+    return out
+
+
+def root_pos_smpl(tb: MotionTables, motion_ids: torch.Tensor, motion_times: torch.Tensor) -> torch.Tensor:
+    """motion_lib_base.py:519-544 (get_root_pos_smpl)."""
+    i0, i1, blend = frame_blend(motion_times, tb.lengths[motion_ids], tb.num_frames[motion_ids], tb.dt[motion_ids])
+    f0 = i0 + tb.length_starts[motion_ids]
+    f1 = i1 + tb.length_starts[motion_ids]
+    b = blend.unsqueeze(-1).unsqueeze(-1)
+    return ((1.0 - b) * tb.gts[f0] + b * tb.gts[f1])[:, 0].clone()
+
+
+def sample_time_interval(tb: MotionTables, motion_ids: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
+    """motion_lib_base.py:411-420 with the uniform draw `phase` supplied by the caller.
+
+    `curr_fps = 1/30` is a python double; tensor/python-scalar on CPU divides in fp32 by fp32(1/30).
+    """
+    step = 1 / 30
+    return ((phase * tb.lengths[motion_ids]) / step).long() * step
+
+
+# ------------------------------------------------------------------------------------------------
+# observation / reward / reset
+# ------------------------------------------------------------------------------------------------
+def self_obs_smpl_max(body_pos, body_rot, body_vel, body_ang_vel, local_root_obs: bool = True,
+                      root_height_obs: bool = True) -> torch.Tensor:
+    """humanoid.py:1675-1731 (compute_humanoid_observations_smpl_max), upright start, no shape obs.
+
+    Layout: [h | R(p_j-p_0) j=1..23 | six(hinv*q_j) j=0..23 | R v_j | R w_j]  = 1+69+144+72+72.
+    """
+    n, nb, _ = body_pos.shape
+    hinv = heading_quat(body_rot[:, 0], inverse=True).unsqueeze(1).expand(n, nb, 4)
+    rel = quat_rotate(hinv, body_pos - body_pos[:, :1]).reshape(n, -1)[:, 3:]
+    rot6 = quat_to_six(quat_mul(hinv, body_rot)).reshape(n, -1)
+    if not local_root_obs:
+        rot6 = rot6.clone()
+        rot6[:, :6] = quat_to_six(body_rot[:, 0])
+    vel = quat_rotate(hinv, body_vel).reshape(n, -1)
+    ang = quat_rotate(hinv, body_ang_vel).reshape(n, -1)
+    parts = [rel, rot6, vel, ang]
+    if root_height_obs:
+        parts.insert(0, body_pos[:, 0, 2:3])
+    return torch.cat(parts, dim=-1)
+
+
+def imitation_obs_v6(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel,
+                     ref_pos, ref_rot, ref_vel, ref_ang_vel) -> torch.Tensor:
+    """humanoid_im.py:1328-1378 (compute_imitation_observations_v6), time_steps=1, upright.
+
+    Block-major layout over the J tracked bodies:
+    [R dp | six(hinv*(qref*conj q)*h) | R dv | R dw | R (pref-root) | six(hinv*qref)] = J*(3+6+3+3+3+6).
+    """
+    n, nb, _ = body_pos.shape
+    hinv = heading_quat(root_rot, inverse=True).unsqueeze(1).expand(n, nb, 4)
+    hfwd = heading_quat(root_rot, inverse=False).unsqueeze(1).expand(n, nb, 4)
+    d_pos = quat_rotate(hinv, ref_pos - body_pos)
+    d_rot = quat_mul(quat_mul(hinv, quat_mul(ref_rot, quat_conj(body_rot))), hfwd)
+    d_vel = quat_rotate(hinv, ref_vel - body_vel)
+    d_ang = quat_rotate(hinv, ref_ang_vel - body_ang_vel)
+    loc_pos = quat_rotate(hinv, ref_pos - root_pos[:, None, :])
+    loc_rot = quat_to_six(quat_mul(hinv, ref_rot))
+    blocks = [d_pos, quat_to_six(d_rot), d_vel, d_ang, loc_pos, loc_rot]
+    return torch.cat([x.reshape(n, -1) for x in blocks], dim=-1)
+
+
+def imitation_obs_v7(root_pos, root_rot, body_pos, body_vel, ref_pos, ref_vel) -> torch.Tensor:
+    """humanoid_im.py:1381-1413 (compute_imitation_observations_v7): [R dp | R dv | R (pref-root)]."""
+    n, nb, _ = body_pos.shape
+    hinv = heading_quat(root_rot, inverse=True).unsqueeze(1).expand(n, nb, 4)
+    blocks = [quat_rotate(hinv, ref_pos - body_pos), quat_rotate(hinv, ref_vel - body_vel),
+              quat_rotate(hinv, ref_pos - root_pos[:, None, :])]
+    return torch.cat([x.reshape(n, -1) for x in blocks], dim=-1)
+
+
+REWARD_SPECS = {"k_pos": 100.0, "k_rot": 10.0, "k_vel": 0.1, "k_ang_vel": 0.1,
+                "w_pos": 0.5, "w_rot": 0.3, "w_vel": 0.1, "w_ang_vel": 0.1}  # humanoid_im.py:55
+
+
+def imitation_reward(body_pos, body_rot, body_vel, body_ang_vel, ref_pos, ref_rot, ref_vel, ref_ang_vel,
+                     specs: Dict[str, float] = REWARD_SPECS) -> Tuple[torch.Tensor, torch.Tensor]:
+    """humanoid_im.py:1543-1574 (compute_imitation_reward)."""
+    e_pos = ((ref_pos - body_pos) ** 2).mean(dim=-1).mean(dim=-1)
+    ang = quat_to_angle_axis(quat_mul(ref_rot, quat_conj(body_rot)))[0]
+    e_rot = (ang ** 2).mean(dim=-1)
+    e_vel = ((ref_vel - body_vel) ** 2).mean(dim=-1).mean(dim=-1)
+    e_ang = ((ref_ang_vel - body_ang_vel) ** 2).mean(dim=-1).mean(dim=-1)
+    r_pos = torch.exp(-specs["k_pos"] * e_pos)
+    r_rot = torch.exp(-specs["k_rot"] * e_rot)
+    r_vel = torch.exp(-specs["k_vel"] * e_vel)
+    r_ang = torch.exp(-specs["k_ang_vel"] * e_ang)
+    rew = specs["w_pos"] * r_pos + specs["w_rot"] * r_rot + specs["w_vel"] * r_vel + specs["w_ang_vel"] * r_ang
+    return rew, torch.stack([r_pos, r_rot, r_vel, r_ang], dim=-1)
+
+
+def im_reset(reset_buf, progress_buf, body_pos_subset, ref_pos_subset, pass_time, termination_distance,
+             enable_early_termination: bool = True, use_mean: bool = False,
+             disable_collision: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """humanoid_im.py:1600-1628 (compute_humanoid_im_reset). int64 outputs."""
+    terminated = torch.zeros_like(reset_buf)
+    if enable_early_termination:
+        dist = torch.norm(body_pos_subset - ref_pos_subset, dim=-1)
+        if use_mean:
+            fallen = torch.any(dist.mean(dim=-1, keepdim=True) > termination_distance[0], dim=-1)
+        else:
+            fallen = torch.any(dist > termination_distance, dim=-1)
+        fallen = fallen & (progress_buf > 1)
+        if disable_collision:
+            fallen = torch.zeros_like(fallen)
+        terminated = torch.where(fallen, torch.ones_like(reset_buf), terminated)
+    reset = torch.where(pass_time, torch.ones_like(reset_buf), terminated)
+    return reset, terminated
+
+
+def amp_dof_subset() -> torch.Tensor:
+    keep = [k for k in range(NUM_DOF) if (k // 3) not in AMP_DROPPED_JOINTS]
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def amp_obs_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos,
+                 dof_subset: Optional[torch.Tensor] = None, local_root_obs: bool = True,
+                 root_height_obs: bool = True) -> torch.Tensor:
+    """humanoid_amp.py:924-969 (build_amp_observations_smpl), upright, no shape/limb obs.
+
+    [h | six(hinv*q0) | R v0 | R w0 | six(exp_map_to_quat(dof)) per kept joint | dof_vel kept | R (key-p0)].
+    """
+    n = root_pos.shape[0]
+    hinv = heading_quat(root_rot, inverse=True)
+    root6 = quat_to_six(quat_mul(hinv, root_rot) if local_root_obs else root_rot)
+    lv = quat_rotate(hinv, root_vel)
+    la = quat_rotate(hinv, root_ang_vel)
+    nk = key_body_pos.shape[1]
+    key = quat_rotate(hinv.unsqueeze(1).expand(n, nk, 4), key_body_pos - root_pos.unsqueeze(1)).reshape(n, -1)
+    if dof_subset is not None:
+        dof_pos = dof_pos[:, dof_subset]
+        dof_vel = dof_vel[:, dof_subset]
+    dof6 = quat_to_six(exp_map_to_quat(dof_pos.reshape(-1, 3))).reshape(n, -1)  # humanoid.py:1436-1446
+    parts = [root6, lv, la, dof6, dof_vel, key]
+    if root_height_obs:
+        parts.insert(0, root_pos[:, 2:3])
+    return torch.cat(parts, dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# one HumanoidIm post-physics step (reward -> reset -> observation), SURVEY Appendix A.9
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ImStepConfig:
+    dt: float = STEP_DT
+    power_reward: bool = True            # env_im.yaml:23
+    power_coefficient: float = 0.0005    # humanoid_im.py:91
+    max_episode_length: int = 300        # env_im.yaml:8
+    enable_early_termination: bool = True
+    termination_distance: float = 0.25   # env_im.yaml:41
+    cycle_motion: bool = False           # env_im.yaml:17
+    use_mean_reset: bool = False         # flags.im_eval and not strict_eval
+    reset_body_ids: Tuple[int, ...] = RESET_BODY_IDS
+    reward_specs: Dict[str, float] = field(default_factory=lambda: dict(REWARD_SPECS))
+
+
+def im_motion_times(progress_buf, start_times, start_offset, dt: float, plus_one: bool) -> torch.Tensor:
+    """humanoid_im.py:732 / :859 / :1120 -- three separate fp32 ops on an int64 progress counter."""
+    p = progress_buf + 1 if plus_one else progress_buf
+    return p * dt + start_times + start_offset
+
+
+def humanoid_im_step(tb: MotionTables, cfg: ImStepConfig, body_state: torch.Tensor, dof_vel: torch.Tensor,
+                     dof_force: torch.Tensor, progress_buf: torch.Tensor, motion_ids: torch.Tensor,
+                     start_times: torch.Tensor, start_offset: torch.Tensor, global_offset: torch.Tensor,
+                     cycle_counter: torch.Tensor, reset_buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """HumanoidIm.post_physics_step compute, non-cycling branch, after `progress_buf += 1`.
+
+    humanoid_im.py:853-919 (_compute_reward), :1119-1192 (_compute_reset), :677-851
+    (_compute_observations / _compute_task_obs, obs_v 6), humanoid.py:1137-1213 (_compute_humanoid_obs).
+    `body_state` is the Isaac Gym rigid-body-state view [N,24,13] = pos, quat xyzw, linvel, angvel.
+    """
+    pos, rot, vel, ang = body_state[..., 0:3], body_state[..., 3:7], body_state[..., 7:10], body_state[..., 10:13]
+    out: Dict[str, torch.Tensor] = {}
+
+    # reward at t = progress*dt + start + offset
+    t_rew = im_motion_times(progress_buf, start_times, start_offset, cfg.dt, plus_one=False)
+    ref = motion_state(tb, motion_ids, t_rew, global_offset)
+    rew, raw = imitation_reward(pos, rot, vel, ang, ref["rg_pos"], ref["rb_rot"], ref["body_vel"],
+                                ref["body_ang_vel"], cfg.reward_specs)
+    if cfg.power_reward:
+        power = torch.abs(torch.multiply(dof_force, dof_vel)).sum(dim=-1)
+        p_rew = -cfg.power_coefficient * power
+        p_rew = torch.where(progress_buf <= 3, torch.zeros_like(p_rew), p_rew)
+        rew = rew + p_rew
+        raw = torch.cat([raw, p_rew[:, None]], dim=-1)
+    out["rew_buf"], out["reward_raw"] = rew, raw
+
+    # reset at the same t (the reference reuses the cached query, humanoid_im.py:950-964)
+    if cfg.cycle_motion:
+        pass_time = progress_buf >= cfg.max_episode_length - 1
+    else:
+        pass_time = t_rew >= tb.lengths[motion_ids]
+    rb = torch.tensor(cfg.reset_body_ids, dtype=torch.long)
+    term_dist = torch.full((1, NUM_BODIES), cfg.termination_distance, dtype=F32)[..., rb]
+    reset, terminated = im_reset(reset_buf, progress_buf, pos[:, rb], ref["rg_pos"][:, rb], pass_time, term_dist,
+                                 cfg.enable_early_termination, cfg.use_mean_reset)
+    recovering = torch.logical_and(~pass_time, cycle_counter > 0)
+    reset = torch.where(recovering, torch.zeros_like(reset), reset)
+    terminated = torch.where(recovering, torch.zeros_like(terminated), terminated)
+    out["reset_buf"], out["terminate_buf"] = reset, terminated
+    out["frame_idx_rew"] = torch.stack([ref["frame_idx0"], ref["frame_idx1"]], dim=-1)
+
+    # observation at t + dt
+    t_obs = im_motion_times(progress_buf, start_times, start_offset, cfg.dt, plus_one=True)
+    nxt = motion_state(tb, motion_ids, t_obs, global_offset)
+    self_obs = self_obs_smpl_max(pos, rot, vel, ang)
+    task_obs = imitation_obs_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, nxt["rg_pos"], nxt["rb_rot"],
+                                nxt["body_vel"], nxt["body_ang_vel"])
+    out["obs_buf"] = torch.cat([self_obs, task_obs], dim=-1)
+    out["ref_body_pos"], out["ref_body_rot"], out["ref_body_vel"] = nxt["rg_pos"], nxt["rb_rot"], nxt["body_vel"]
+    out["ref_dof_pos"] = nxt["dof_pos"]
+    out["frame_idx_obs"] = torch.stack([nxt["frame_idx0"], nxt["frame_idx1"]], dim=-1)
+    return out
+
+
+def amp_obs_step(amp_obs_buf: torch.Tensor, body_state: torch.Tensor, dof_pos: torch.Tensor,
+                 dof_vel: torch.Tensor) -> torch.Tensor:
+    """humanoid_amp.py:622-630 + 632-667: hist[1:] <- buf[:-1]; buf[0] <- current AMP obs. Returns new buffer."""
+    cur = amp_obs_smpl(body_state[:, 0, 0:3], body_state[:, 0, 3:7], body_state[:, 0, 7:10], body_state[:, 0, 10:13],
+                       dof_pos, dof_vel, body_state[:, list(KEY_BODY_IDS), 0:3], amp_dof_subset())
+    return torch.cat([cur.unsqueeze(1), amp_obs_buf[:, :-1]], dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# rollout post-processing: GAE, returns, advantage normalisation
+# ------------------------------------------------------------------------------------------------
+def discount_values(fdones, values, rewards, next_values, gamma: float = 0.99, tau: float = 0.95) -> torch.Tensor:
+    """common_agent.py:493-505. Shapes [T,N] dones, [T,N,1] others."""
+    last = 0
+    advs = torch.zeros_like(rewards)
+    for t in reversed(range(rewards.shape[0])):
+        not_done = (1.0 - fdones[t]).unsqueeze(1)
+        delta = rewards[t] + gamma * next_values[t] - values[t]
+        last = delta + gamma * tau * not_done * last
+        advs[t] = last
+    return advs
+
+
+def swap_and_flatten01(x: torch.Tensor) -> torch.Tensor:
+    """rl_games a2c_common.swap_and_flatten01 [3P-memory]: [T,N,...] -> env-major [N*T,...]."""
+    return x.transpose(0, 1).reshape(x.shape[0] * x.shape[1], *x.shape[2:])
+
+
+def normalized_advantages(returns: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
+    """common_agent.py:589-599 (_calc_advs, normalize_advantage=True)."""
+    adv = torch.sum(returns - values, dim=1)
+    return (adv - adv.mean()) / (adv.std() + 1e-8)
+
+
+class RunningMeanStd:
+    """phc/utils/running_mean_std.py:9-109 (per-feature, fp64 statistics, clamp +-5)."""
+
+    def __init__(self, size: int, epsilon: float = 1e-5):
+        self.mean = torch.zeros(size, dtype=torch.float64)
+        self.var = torch.ones(size, dtype=torch.float64)
+        self.count = torch.ones((), dtype=torch.float64)
+        self.eps = epsilon
+
+    def update(self, x: torch.Tensor) -> None:
+        mean, var, n = x.mean(0), x.var(0), x.shape[0]
+        delta = mean - self.mean
+        tot = self.count + n
+        new_mean = self.mean + delta * n / tot
+        m2 = self.var * self.count + var * n + delta ** 2 * self.count * n / tot
+        self.mean, self.var, self.count = new_mean, m2 / tot, tot
+
+    def normalize(self, x: torch.Tensor, unnorm: bool = False) -> torch.Tensor:
+        if unnorm:
+            y = torch.clamp(x, min=-5.0, max=5.0)
+            return torch.sqrt(self.var.float() + self.eps) * y + self.mean.float()
+        y = (x - self.mean.float()) / torch.sqrt(self.var.float() + self.eps)
+        return torch.clamp(y, min=-5.0, max=5.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# networks and losses
+# ------------------------------------------------------------------------------------------------
+def mlp_forward(x: torch.Tensor, weights, biases, activation: str = "relu", last_linear: bool = False) -> torch.Tensor:
+    """network_builder.py:105-124 style Linear+activation stack (fp32)."""
+    act = {"relu": torch.relu, "silu": torch.nn.functional.silu}[activation]
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        x = torch.nn.functional.linear(x, w, b)
+        if not (last_linear and i == len(weights) - 1):
+            x = act(x)
+    return x
+
+
+def gaussian_neglogp(x, mu, sigma, logstd) -> torch.Tensor:
+    """rl_games ModelA2CContinuousLogStd.neglogp [3P-memory]."""
+    return 0.5 * (((x - mu) / sigma) ** 2).sum(dim=-1) + 0.5 * math.log(2.0 * math.pi) * x.shape[-1] + logstd.sum(dim=-1)
+
+
+def actor_loss(old_neglogp, neglogp, advantage, e_clip: float = 0.2) -> torch.Tensor:
+    """common_agent.py:564-574."""
+    ratio = torch.exp(old_neglogp - neglogp)
+    return torch.max(-advantage * ratio, -advantage * torch.clamp(ratio, 1.0 - e_clip, 1.0 + e_clip))
+
+
+def critic_loss(values, returns) -> torch.Tensor:
+    """common_agent.py:576-587 with clip_value False (im.yaml:75)."""
+    return (returns - values) ** 2
+
+
+def bound_loss(mu, soft_bound: float = 1.0) -> torch.Tensor:
+    """common_agent.py:512-520."""
+    hi = torch.clamp_min(mu - soft_bound, 0.0) ** 2
+    lo = torch.clamp_max(mu + soft_bound, 0.0) ** 2
+    return (lo + hi).sum(dim=-1)
+
+
+def policy_kl(mu0, sigma0, mu1, sigma1) -> torch.Tensor:
+    """rl_games torch_ext.policy_kl, reduce=True [3P-memory]."""
+    c1 = torch.log(sigma1 / sigma0 + 1e-5)
+    c2 = (sigma0 ** 2 + (mu1 - mu0) ** 2) / (2.0 * (sigma1 ** 2 + 1e-5))
+    return (c1 + c2 - 0.5).sum(dim=-1).mean()
+
+
+def disc_reward(logits, scale: float = 2.0) -> torch.Tensor:
+    """amp_agent.py:1027-1041 (no disc-reward normaliser)."""
+    prob = 1 / (1 + torch.exp(-logits))
+    return -torch.log(torch.maximum(1 - prob, torch.tensor(0.0001))) * scale
+
+
+def kl_multi(mu_q, logvar_q, mu_p, logvar_p) -> torch.Tensor:
+    """phc/learning/loss_functions.py:3-11: KL(q||p) of diagonal Gaussians, summed over the latent."""
+    per_dim = 0.5 * (logvar_p - logvar_q + logvar_q.exp() / logvar_p.exp()
+                     + (mu_q - mu_p).pow(2) / logvar_p.exp() - 1)
+    return per_dim.sum(-1)
+
+
+def ppo_total_loss(mu, value, old_neglogp, advantage, returns, actions, logstd, e_clip=0.2,
+                   critic_coef=5.0, bounds_coef=10.0) -> Dict[str, torch.Tensor]:
+    """amp_agent.py:691-710 without the discriminator term (entropy_coef 0)."""
+    sigma = torch.exp(logstd).expand_as(mu)
+    neglogp = gaussian_neglogp(actions, mu, sigma, logstd.expand_as(mu))
+    a = actor_loss(old_neglogp, neglogp, advantage, e_clip).mean()
+    c = critic_loss(value, returns).mean()
+    b = bound_loss(mu).mean()
+    return {"a_loss": a, "c_loss": c, "b_loss": b, "loss": a + critic_coef * c + bounds_coef * b, "neglogp": neglogp}

@@ -1,0 +1,158 @@
+"""Pins oracle/pulse_oracle.py to the fixtures the reference produced (tests/golden/make_golden.py).
+
+Integer outputs must be identical.  Float outputs are compared with atol 2e-6 (same PyTorch CPU
+library and op order as the reference; the slack only covers reduction-order differences).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pulse_oracle as po
+from tests.helpers import load_npz, oracle_tables
+
+ATOL = 2e-6
+
+
+def close(a, b, atol=ATOL, rtol=1e-6):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    torch.testing.assert_close(a, b, atol=atol, rtol=rtol, equal_nan=True)
+
+
+def test_quaternion_primitives():
+    z = load_npz("quat.npz")
+    close(po.slerp(z["qa"], z["qb"], z["t"]), z["slerp"])
+    close(po.quat_mul(z["qa"], z["qb"]), z["quat_mul"])
+    close(po.quat_rotate(z["qa"], z["qb"][:, :3]), z["rotate"])
+    close(po.quat_to_exp_map(z["qe"]), z["exp_map"])
+    ang, axis = po.quat_to_angle_axis(z["qe"])
+    close(ang, z["angle"])
+    close(axis, z["axis"])
+    close(po.quat_to_six(z["qe"]), z["tan_norm"])
+    close(po.heading_angle(z["qe"]), z["heading"])
+    close(po.heading_quat(z["qe"]), z["heading_quat"])
+    close(po.heading_quat(z["qe"], inverse=True), z["heading_quat_inv"])
+    close(po.exp_map_to_quat(z["em"]), z["exp_map_to_quat"])
+
+
+def test_motion_state_queries():
+    tb = oracle_tables()
+    z = load_npz("motion_state.npz")
+    out = po.motion_state(tb, z["ids"], z["times"], z["offset"])
+    assert torch.equal(out["frame_idx0"], z["frame_idx0"])
+    assert torch.equal(out["frame_idx1"], z["frame_idx1"])
+    assert torch.equal(out["blend"], z["blend"])
+    for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa", "rg_pos", "rb_rot",
+              "body_vel", "body_ang_vel"):
+        close(out[k], z[k])
+    close(po.root_pos_smpl(tb, z["ids"], z["times"]), z["root_pos_smpl"])
+    assert torch.equal(po.sample_time_interval(tb, z["ids"], z["phase"]), z["sampled_time"])
+
+
+@pytest.mark.parametrize("tag", ["n2", "n257"])
+def test_humanoid_im_step(tag):
+    tb = oracle_tables()
+    z = load_npz(f"step_{tag}.npz")
+    assert np.float32(z["dt"]) == np.float32(po.STEP_DT)
+    out = po.humanoid_im_step(tb, po.ImStepConfig(), z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"],
+                              z["motion_ids"], z["start_times"], z["start_offset"], z["global_offset"], z["cycle_counter"],
+                              z["reset_buf_in"])
+    assert torch.equal(out["frame_idx_rew"], z["frame_idx_rew"])
+    assert torch.equal(out["frame_idx_obs"], z["frame_idx_obs"])
+    assert torch.equal(out["reset_buf"], z["reset_buf"])
+    assert torch.equal(out["terminate_buf"], z["terminate_buf"])
+    assert out["reset_buf"].dtype == torch.int64
+    close(out["rew_buf"], z["rew_buf"])
+    close(out["reward_raw"], z["reward_raw"])
+    close(out["obs_buf"], z["obs_buf"])
+    close(out["obs_buf"][:, :po.SELF_OBS], z["self_obs"])
+    close(out["ref_body_pos"], z["ref_body_pos"])
+    close(out["ref_body_rot"], z["ref_body_rot"])
+    close(out["ref_dof_pos"], z["ref_dof_pos"])
+    # the fixture has terminations, time-outs and recovering envs in it
+    if tag == "n257":
+        assert 0 < int(z["terminate_buf"].sum()) < 257 and int(z["reset_buf"].sum()) > int(z["terminate_buf"].sum())
+
+
+def test_mean_reset_and_v7_obs():
+    tb = oracle_tables()
+    z = load_npz("step_n257.npz")
+    cfg = po.ImStepConfig(use_mean_reset=True, termination_distance=0.08)
+    out = po.humanoid_im_step(tb, cfg, z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"],
+                              z["start_times"], z["start_offset"], z["global_offset"], torch.zeros_like(z["cycle_counter"]),
+                              z["reset_buf_in"])
+    assert torch.equal(out["reset_buf"], z["reset_buf_mean"])
+    assert torch.equal(out["terminate_buf"], z["terminate_buf_mean"])
+    bs = z["body_state"]
+    track = [13, 18, 23]
+    t_obs = po.im_motion_times(z["progress_buf"], z["start_times"], z["start_offset"], po.STEP_DT, True)
+    nxt = po.motion_state(tb, z["motion_ids"], t_obs, z["global_offset"])
+    v7 = po.imitation_obs_v7(bs[:, 0, 0:3], bs[:, 0, 3:7], bs[:, track, 0:3], bs[:, track, 7:10],
+                             nxt["rg_pos"][:, track], nxt["body_vel"][:, track])
+    close(v7, z["task_obs_v7"])
+
+
+def test_amp_observation():
+    z = load_npz("step_n257.npz")
+    bs = z["body_state"]
+    cur = po.amp_obs_smpl(bs[:, 0, 0:3], bs[:, 0, 3:7], bs[:, 0, 7:10], bs[:, 0, 10:13], z["dof_pos"], z["dof_vel"],
+                          bs[:, list(po.KEY_BODY_IDS), 0:3], po.amp_dof_subset())
+    assert cur.shape[1] == po.AMP_OBS
+    close(cur, z["amp_cur"])
+    nh = z["amp_hist_in"].shape[0]
+    new = po.amp_obs_step(z["amp_hist_in"], bs[:nh], z["dof_pos"][:nh], z["dof_vel"][:nh])
+    close(new, z["amp_hist_out"])
+
+
+def test_agent_arithmetic():
+    z = load_npz("agent.npz")
+    advs = po.discount_values(z["fdones"], z["values"], z["rewards"], z["next_values"])
+    close(advs, z["advs"])
+    close(advs + z["values"], z["returns"])
+    adv_norm = po.normalized_advantages(po.swap_and_flatten01(z["returns"]), po.swap_and_flatten01(z["values"]))
+    close(adv_norm, z["adv_norm"])
+    close(po.actor_loss(z["old_neglogp"], z["new_neglogp"], z["adv_b"]), z["actor_loss"])
+    close(po.critic_loss(z["critic_values"], z["critic_returns"]), z["critic_loss"])
+    close(po.bound_loss(z["mu"]), z["bound_loss"])
+    close(po.disc_reward(z["disc_logits"]), z["disc_reward"])
+    close(po.kl_multi(z["kl_qm"], z["kl_qv"], z["kl_pm"], z["kl_pv"]), z["kl_multi"])
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    close(bce(z["disc_logits"], torch.zeros_like(z["disc_logits"])), z["bce_neg"])
+    close(bce(z["disc_logits"], torch.ones_like(z["disc_logits"])), z["bce_pos"])
+    rms = po.RunningMeanStd(7)
+    y1 = rms.normalize(z["rms_x1"]); rms.update(z["rms_x1"])
+    y2 = rms.normalize(z["rms_x2"]); rms.update(z["rms_x2"])
+    y3 = rms.normalize(z["rms_x1"])
+    close(y1, z["rms_y1"]); close(y2, z["rms_y2"]); close(y3, z["rms_y3"])
+    torch.testing.assert_close(rms.mean, z["rms_mean"], atol=1e-12, rtol=1e-12)
+    torch.testing.assert_close(rms.var, z["rms_var"], atol=1e-12, rtol=1e-12)
+    assert float(rms.count) == float(z["rms_count"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_oracle_against_live_reference():
+    """Re-pin against the reference itself on fresh random inputs (container only)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "refshim"))
+    from load_reference import load_reference
+    ref = load_reference()
+    g = torch.Generator().manual_seed(123)
+    n = 500
+    unit = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    pos, vel, ang = (torch.randn(n, 24, 3, generator=g) for _ in range(3))
+    rot = unit(torch.randn(n, 24, 4, generator=g))
+    rpos, rvel, rang = (torch.randn(n, 24, 3, generator=g) for _ in range(3))
+    rrot = unit(torch.randn(n, 24, 4, generator=g))
+    empty = torch.zeros(n, 0)
+    a = ref.humanoid.compute_humanoid_observations_smpl_max(pos, rot, vel, ang, empty, empty, True, True, True, False, False)
+    close(po.self_obs_smpl_max(pos, rot, vel, ang), a)
+    b = ref.humanoid_im.compute_imitation_observations_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, rpos, rrot, rvel, rang, 1, True)
+    close(po.imitation_obs_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, rpos, rrot, rvel, rang), b)
+    r, raw = ref.humanoid_im.compute_imitation_reward(pos[:, 0], rot[:, 0], pos, rot, vel, ang, rpos, rrot, rvel, rang, dict(po.REWARD_SPECS))
+    r2, raw2 = po.imitation_reward(pos, rot, vel, ang, rpos, rrot, rvel, rang)
+    close(r2, r); close(raw2, raw)
+    q0, q1 = unit(torch.randn(4000, 4, generator=g)), unit(torch.randn(4000, 4, generator=g))
+    t = torch.rand(4000, 1, generator=g)
+    close(po.slerp(q0, q1, t), ref.torch_utils.slerp(q0, q1, t))
