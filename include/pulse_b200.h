@@ -1,0 +1,207 @@
+/*
+ * pulse_b200.h -- C ABI of the B200-native PULSE hot path (libpulse_b200.so).
+ *
+ * Boundary rules:
+ *   - plain C types only: device pointers, element strides, sizes, a cudaStream_t passed as void*;
+ *   - every buffer is owned by the caller (torch tensors or Isaac Gym gymtorch views); nothing is
+ *     allocated on the device inside the library;
+ *   - no hidden synchronisation: kernels are enqueued on the caller's stream and the call returns;
+ *   - every entry point returns 0 on success or a negative pulse_status; the message is available
+ *     from pulse_last_error() (thread-local).  No exceptions cross the boundary;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PULSE_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface (file:line under the PULSE tree) it replaces.
+ */
+#ifndef PULSE_B200_H_
+#define PULSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PULSE_ABI_VERSION 1
+
+enum pulse_status {
+  PULSE_OK = 0,
+  PULSE_ERR_ARG = -1,    /* null pointer / bad size / bad stride / misaligned table */
+  PULSE_ERR_CUDA = -2,   /* CUDA runtime error (launch, no device, ...) */
+  PULSE_ERR_UNSUPPORTED = -3
+};
+
+#define PULSE_NUM_BODIES 24        /* SMPL humanoid rigid bodies (smpl_humanoid.xml)        */
+#define PULSE_NUM_DOF 69           /* 23 joints x 3                                           */
+#define PULSE_BODY_STATE_W 13      /* pos3 quat4(xyzw) linvel3 angvel3, humanoid.py:215-222  */
+#define PULSE_SELF_OBS 358         /* humanoid.py:1675-1731                                   */
+#define PULSE_TASK_OBS_V6 576      /* humanoid_im.py:1328-1378                                */
+#define PULSE_IM_OBS (PULSE_SELF_OBS + PULSE_TASK_OBS_V6)
+#define PULSE_AMP_OBS 196          /* humanoid_amp.py:924-969 with dof_subset                 */
+#define PULSE_FRAME_REC 312        /* packed per-frame record: pos72 | rot96 | vel72 | angvel72 */
+#define PULSE_AUX_REC 240          /* packed per-frame record: lrs96 | dvs69 | aa72 | pad3    */
+
+int pulse_abi_version(void);
+const char* pulse_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+int64_t pulse_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MotionLib tables.  Replaces the device-resident buffers MotionLibBase.load_motions builds
+ * (phc/utils/motion_lib_base.py:287-316) with two packed per-frame records so that one query
+ * gathers one contiguous 1248-byte row per frame instead of rows of six separate tables.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pulse_motionlib pulse_motionlib_t;
+
+typedef struct {
+  /* reference tables, device pointers, contiguous fp32 / int64 (motion_lib_base.py:297-315) */
+  const float* gts;   /* [F,24,3] */
+  const float* grs;   /* [F,24,4] */
+  const float* lrs;   /* [F,24,4] */
+  const float* gvs;   /* [F,24,3] */
+  const float* gavs;  /* [F,24,3] */
+  const float* dvs;   /* [F,23,3] */
+  const float* motion_aa; /* [F,72] (may be NULL -> zeros) */
+  const float* lengths;         /* [M] _motion_lengths */
+  const float* dt;              /* [M] _motion_dt */
+  const int64_t* num_frames;    /* [M] _motion_num_frames */
+  const int64_t* length_starts; /* [M] length_starts */
+  int64_t total_frames;         /* F */
+  int64_t num_motions;          /* M */
+  /* caller-allocated packed outputs, 16-byte aligned, filled by pulse_motionlib_create */
+  float* frame_rec;   /* [F, PULSE_FRAME_REC] */
+  float* aux_rec;     /* [F, PULSE_AUX_REC]   */
+} pulse_motionlib_desc_t;
+
+/* Packs the tables (one kernel on `stream`) and returns a host-side handle that keeps the pointers.
+ * The per-motion arrays and the packed records must outlive the handle. */
+int pulse_motionlib_create(const pulse_motionlib_desc_t* desc, void* stream, pulse_motionlib_t** out);
+int pulse_motionlib_destroy(pulse_motionlib_t* lib);
+
+/* MotionLibBase.get_motion_state(motion_ids, motion_times, offset)  motion_lib_base.py:434-517
+ * (+ _calc_frame_blend :546-556, _local_rotation_to_dof_smpl :561-564).  Any output may be NULL. */
+typedef struct {
+  const int64_t* motion_ids;   /* [n] */
+  const float* motion_times;   /* [n] */
+  const float* offset;         /* [n,3] or NULL */
+  float* root_pos;      /* [n,3]   */
+  float* root_rot;      /* [n,4]   */
+  float* dof_pos;       /* [n,69]  */
+  float* root_vel;      /* [n,3]   */
+  float* root_ang_vel;  /* [n,3]   */
+  float* dof_vel;       /* [n,69]  */
+  float* motion_aa;     /* [n,72]  */
+  float* rg_pos;        /* [n,24,3] */
+  float* rb_rot;        /* [n,24,4] */
+  float* body_vel;      /* [n,24,3] */
+  float* body_ang_vel;  /* [n,24,3] */
+  int64_t* frame_idx0;  /* [n] (diagnostic: _calc_frame_blend) */
+  int64_t* frame_idx1;  /* [n] */
+  float* blend;         /* [n] */
+} pulse_motion_query_t;
+int pulse_motion_state(const pulse_motionlib_t* lib, const pulse_motion_query_t* q, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused HumanoidIm post-physics step: reward(t) -> reset(t) -> observation(t+dt) in ONE kernel.
+ * Replaces, for the default task configuration (obs_v 6, self_obs_v 1, full-body reward, 24 tracked
+ * bodies, upright start, local_root_obs, root_height_obs):
+ *   HumanoidIm._compute_reward        phc/env/tasks/humanoid_im.py:853-919  (compute_imitation_reward :1543-1574)
+ *   HumanoidIm._compute_reset         humanoid_im.py:1119-1192              (compute_humanoid_im_reset :1600-1628)
+ *   HumanoidIm._compute_observations  humanoid_im.py:677-706, _compute_task_obs :708-851
+ *                                     (compute_imitation_observations_v6 :1328-1378)
+ *   Humanoid._compute_humanoid_obs    phc/env/tasks/humanoid.py:1137-1213   (compute_humanoid_observations_smpl_max :1675-1731)
+ *   and the two MotionLib queries behind _get_state_from_motionlib_cache (humanoid_im.py:950-964).
+ * `progress_buf` is the value AFTER the reference's `progress_buf += 1` (humanoid.py:1317).
+ * ---------------------------------------------------------------------------------------------- */
+#define PULSE_STEP_REWARD 1u
+#define PULSE_STEP_RESET 2u
+#define PULSE_STEP_OBS 4u
+#define PULSE_STEP_ALL 7u
+
+typedef struct {
+  /* simulator state (Isaac Gym views, read-only) */
+  const float* body_state;   /* rigid body state; env e, body j at body_state + e*body_env_stride + j*13 */
+  int64_t body_env_stride;   /* floats between envs = bodies_per_env*13 (humanoid.py:215-222) */
+  const float* dof_vel;      /* dof velocity; element k of env e at dof_vel + e*dof_env_stride + k*dof_elem_stride */
+  int64_t dof_env_stride;    /* Isaac Gym dof-state view: dofs_per_env*2, elem stride 2 (humanoid.py:207-210) */
+  int64_t dof_elem_stride;
+  const float* dof_force;    /* [N,69] dof_force_tensor (humanoid.py:189-190); NULL disables the power term */
+  int64_t dof_force_stride;
+  /* optional env subset: warp i processes env env_ids[i] (reset path, humanoid_im.py:677-681); NULL = envs 0..n-1 */
+  const int64_t* env_ids;
+  /* task buffers (read-only) */
+  const int64_t* progress_buf;      /* [N] */
+  const int64_t* motion_ids;        /* [N] _sampled_motion_ids */
+  const float* motion_start_times;  /* [N] */
+  const float* motion_start_offset; /* [N] _motion_start_times_offset */
+  const float* global_offset;       /* [N,3] */
+  const int32_t* cycle_counter;     /* [N] or NULL */
+  const int64_t* reset_buf_in;      /* unused by the reference's formula (kept for signature parity); may be NULL */
+  const float* termination_distances; /* [24] _termination_distances (humanoid_im.py:1166-1186) */
+  uint32_t reset_body_mask;         /* bit j set = body j in reset_bodies (env_im.yaml:38) */
+  uint32_t flags;                   /* PULSE_STEP_* */
+  float dt;                         /* control dt, fp32(2/60) */
+  float k_pos, k_rot, k_vel, k_ang_vel, w_pos, w_rot, w_vel, w_ang_vel; /* reward_specs humanoid_im.py:55 */
+  float power_coefficient;          /* humanoid_im.py:91; used when dof_force != NULL */
+  int32_t cycle_motion;             /* 0: pass_time = t >= motion_len; 1: progress >= max_episode_length-1 */
+  int64_t max_episode_length;
+  int32_t enable_early_termination;
+  int32_t use_mean_reset;           /* flags.im_eval && !strict_eval (humanoid_im.py:1606) */
+  /* outputs (any may be NULL when its stage is disabled) */
+  float* obs_buf;        /* [N, obs_stride], first 934 floats written */
+  int64_t obs_stride;
+  float* self_obs_buf;   /* [N,358] optional copy (humanoid_im.py:683) */
+  float* rew_buf;        /* [N] */
+  float* reward_raw;     /* [N, raw_stride]: pos, rot, vel, ang_vel (, power) */
+  int64_t raw_stride;
+  int64_t* reset_buf;    /* [N] */
+  int64_t* terminate_buf;/* [N] */
+  uint8_t* pass_time;    /* [N] optional: t >= motion_len mask (needed by the cycle_motion host path) */
+  float* ref_body_pos;   /* [N,24,3] optional (humanoid_im.py:835-848) */
+  float* ref_body_vel;   /* [N,24,3] optional */
+  float* ref_body_rot;   /* [N,24,4] optional */
+  float* ref_dof_pos;    /* [N,69]   optional (costs 2 extra 960-byte gathers per env) */
+} pulse_im_step_args_t;
+/* num_envs = number of envs processed (= len(env_ids) when env_ids is given). */
+int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_args_t* args, int64_t num_envs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AMP observation + history shift.
+ *   HumanoidAMP._update_hist_amp_obs      phc/env/tasks/humanoid_amp.py:622-630
+ *   HumanoidAMP._compute_amp_observations humanoid_amp.py:632-667 (build_amp_observations_smpl :924-969,
+ *                                         dof_to_obs_smpl humanoid.py:1436-1446), has_dof_subset = True.
+ * amp_obs_buf is [N, num_steps, 196], index 0 = newest; in place: buf[:,1:] <- buf[:,:-1]; buf[:,0] <- new.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* body_state; int64_t body_env_stride;
+  const float* dof_pos; const float* dof_vel; int64_t dof_env_stride; int64_t dof_elem_stride;
+  float* amp_obs_buf;   /* [N, num_steps, 196] */
+  int32_t num_steps;    /* numAMPObsSteps (env_im.yaml:31) */
+  int32_t shift_history;/* 1: shift then write slot 0;  0: write slot 0 only */
+} pulse_amp_obs_args_t;
+int pulse_amp_obs(const pulse_amp_obs_args_t* args, int64_t num_envs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAE / returns.  CommonAgent.discount_values  phc/learning/common_agent.py:493-505, mb_returns =
+ * mb_advs + mb_values (amp_agent.py:427), and the first half of _calc_advs (:589-599): sums for the
+ * advantage mean / unbiased std.  Inputs are [T,N] time-major as in the rl_games ExperienceBuffer;
+ * outputs are written ENV-MAJOR [N,T] (swap_and_flatten01 layout) ready for minibatch slicing.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* rewards;      /* [T,N] */
+  const float* values;       /* [T,N] */
+  const float* next_values;  /* [T,N] already multiplied by (1-terminated), amp_agent.py:396-398 */
+  const float* fdones;       /* [T,N] 0/1 */
+  float gamma, tau;
+  float* advantages;         /* [N,T] env-major */
+  float* returns;            /* [N,T] env-major */
+  double* adv_sum;           /* [2]: sum(adv), sum(adv^2) accumulated with atomics; caller zeroes; may be NULL */
+} pulse_gae_args_t;
+int pulse_gae(const pulse_gae_args_t* args, int32_t horizon, int64_t num_envs, void* stream);
+/* advantages <- (adv - mean) / (std + 1e-8) with unbiased std from adv_sum (common_agent.py:596-597) */
+int pulse_normalize_advantages(float* advantages, const double* adv_sum, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PULSE_B200_H_ */

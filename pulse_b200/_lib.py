@@ -1,0 +1,125 @@
+"""ctypes binding of libpulse_b200.so -- the C ABI declared in include/pulse_b200.h.
+
+There is no CPU fallback: if the library is missing the import fails loudly with build
+instructions, and every compute call raises PulseError carrying pulse_last_error().
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpulse_b200.so")
+
+
+class PulseError(RuntimeError):
+    pass
+
+
+c_float_p = C.POINTER(C.c_float)
+c_i64_p = C.POINTER(C.c_int64)
+c_i32_p = C.POINTER(C.c_int32)
+c_u8_p = C.POINTER(C.c_uint8)
+c_f64_p = C.POINTER(C.c_double)
+
+
+class MotionLibDesc(C.Structure):
+    _fields_ = [
+        ("gts", C.c_void_p), ("grs", C.c_void_p), ("lrs", C.c_void_p), ("gvs", C.c_void_p), ("gavs", C.c_void_p),
+        ("dvs", C.c_void_p), ("motion_aa", C.c_void_p), ("lengths", C.c_void_p), ("dt", C.c_void_p),
+        ("num_frames", C.c_void_p), ("length_starts", C.c_void_p), ("total_frames", C.c_int64),
+        ("num_motions", C.c_int64), ("frame_rec", C.c_void_p), ("aux_rec", C.c_void_p),
+    ]
+
+
+class MotionQuery(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "motion_ids", "motion_times", "offset", "root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel",
+        "motion_aa", "rg_pos", "rb_rot", "body_vel", "body_ang_vel", "frame_idx0", "frame_idx1", "blend")]
+
+
+class ImStepArgs(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("body_env_stride", C.c_int64),
+        ("dof_vel", C.c_void_p), ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64),
+        ("dof_force", C.c_void_p), ("dof_force_stride", C.c_int64), ("env_ids", C.c_void_p),
+        ("progress_buf", C.c_void_p), ("motion_ids", C.c_void_p), ("motion_start_times", C.c_void_p),
+        ("motion_start_offset", C.c_void_p), ("global_offset", C.c_void_p), ("cycle_counter", C.c_void_p),
+        ("reset_buf_in", C.c_void_p), ("termination_distances", C.c_void_p),
+        ("reset_body_mask", C.c_uint32), ("flags", C.c_uint32), ("dt", C.c_float),
+        ("k_pos", C.c_float), ("k_rot", C.c_float), ("k_vel", C.c_float), ("k_ang_vel", C.c_float),
+        ("w_pos", C.c_float), ("w_rot", C.c_float), ("w_vel", C.c_float), ("w_ang_vel", C.c_float),
+        ("power_coefficient", C.c_float), ("cycle_motion", C.c_int32), ("max_episode_length", C.c_int64),
+        ("enable_early_termination", C.c_int32), ("use_mean_reset", C.c_int32),
+        ("obs_buf", C.c_void_p), ("obs_stride", C.c_int64), ("self_obs_buf", C.c_void_p), ("rew_buf", C.c_void_p),
+        ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+        ("pass_time", C.c_void_p), ("ref_body_pos", C.c_void_p), ("ref_body_vel", C.c_void_p),
+        ("ref_body_rot", C.c_void_p), ("ref_dof_pos", C.c_void_p),
+    ]
+
+
+class AmpObsArgs(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("body_env_stride", C.c_int64), ("dof_pos", C.c_void_p), ("dof_vel", C.c_void_p),
+        ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64), ("amp_obs_buf", C.c_void_p),
+        ("num_steps", C.c_int32), ("shift_history", C.c_int32),
+    ]
+
+
+class GaeArgs(C.Structure):
+    _fields_ = [
+        ("rewards", C.c_void_p), ("values", C.c_void_p), ("next_values", C.c_void_p), ("fdones", C.c_void_p),
+        ("gamma", C.c_float), ("tau", C.c_float), ("advantages", C.c_void_p), ("returns", C.c_void_p), ("adv_sum", C.c_void_p),
+    ]
+
+
+STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
+
+# name -> (restype, argtypes); mirrors include/pulse_b200.h one to one
+SIGNATURES = {
+    "pulse_abi_version": (C.c_int, []),
+    "pulse_last_error": (C.c_char_p, []),
+    "pulse_launch_count": (C.c_int64, []),
+    "pulse_motionlib_create": (C.c_int, [C.POINTER(MotionLibDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pulse_motionlib_destroy": (C.c_int, [C.c_void_p]),
+    "pulse_motion_state": (C.c_int, [C.c_void_p, C.POINTER(MotionQuery), C.c_int64, C.c_void_p]),
+    "pulse_im_step": (C.c_int, [C.c_void_p, C.POINTER(ImStepArgs), C.c_int64, C.c_void_p]),
+    "pulse_amp_obs": (C.c_int, [C.POINTER(AmpObsArgs), C.c_int64, C.c_void_p]),
+    "pulse_gae": (C.c_int, [C.POINTER(GaeArgs), C.c_int32, C.c_int64, C.c_void_p]),
+    "pulse_normalize_advantages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises PulseError with build instructions if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PulseError(f"{LIB_PATH} is missing: build it with `python -m pulse_b200.build` "
+                         "(nvcc, sm_100a). pulse_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pulse_abi_version() != 1:
+        raise PulseError(f"ABI version mismatch: library {lib.pulse_abi_version()} != binding 1")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().pulse_last_error().decode("utf-8", "replace")
+        raise PulseError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,263 @@
+"""HumanoidIm per-step compute on the B200: host-side mirror of the reference task's
+`_compute_reward` / `_compute_reset` / `_compute_observations` / `_compute_amp_observations`
+(phc/env/tasks/humanoid_im.py, humanoid.py, humanoid_amp.py), backed by the fused CUDA kernels.
+
+Two layers:
+  * `HumanoidImCompute` -- explicit-tensor API (what bench.py, the tests and the mixin call);
+  * `HumanoidImB200Mixin` -- drop-in overrides with the reference's method names, to be mixed in
+    front of `phc.env.tasks.humanoid_im.HumanoidIm`; Isaac Gym keeps doing the
+    physics and owns the state tensors, which are read in place through their strides.
+
+Everything runs on torch's current CUDA stream; no host synchronisation is added (the reference's
+MotionLib-cache compare, humanoid_im.py:952-953, costs one D2H sync per call and is gone).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .motion_lib import MotionLibB200
+
+NUM_BODIES, NUM_DOF = 24, 69
+SELF_OBS, TASK_OBS, AMP_OBS = 358, 576, 196
+IM_OBS = SELF_OBS + TASK_OBS
+DEFAULT_RESET_BODIES = tuple(j for j in range(24) if j not in (3, 4, 7, 8))  # env_im.yaml:38
+# dt = control_freq_inv * sim dt, with sim dt a C float inside Isaac Gym: 2 * fp32(1/60)
+STEP_DT = float(torch.tensor(1.0 / 60.0, dtype=torch.float32) * 2)
+
+
+@dataclass
+class ImConfig:
+    """The subset of cfg['env'] the step path reads (humanoid_im.py:36-110, humanoid.py:254-349)."""
+    dt: float = STEP_DT
+    reward_specs: Dict[str, float] = field(default_factory=lambda: {
+        "k_pos": 100.0, "k_rot": 10.0, "k_vel": 0.1, "k_ang_vel": 0.1, "w_pos": 0.5, "w_rot": 0.3, "w_vel": 0.1, "w_ang_vel": 0.1})
+    power_reward: bool = True
+    power_coefficient: float = 0.0005
+    reset_body_ids: Sequence[int] = DEFAULT_RESET_BODIES
+    termination_distance: float = 0.25
+    enable_early_termination: bool = True
+    cycle_motion: bool = False
+    max_episode_length: int = 300
+    use_mean_reset: bool = False     # flags.im_eval and not strict_eval
+    num_amp_obs_steps: int = 10
+
+
+def _strided(t: torch.Tensor, inner: int):
+    """(data_ptr, env stride in floats) of a [N, inner...] float32 view whose rows are contiguous runs."""
+    if t.dtype != torch.float32:
+        raise _lib.PulseError(f"expected float32 state tensor, got {t.dtype}")
+    return t.data_ptr(), t.stride(0)
+
+
+class HumanoidImCompute:
+    def __init__(self, motion_lib: MotionLibB200, cfg: Optional[ImConfig] = None):
+        self.lib = _lib.load()
+        self.motion_lib = motion_lib
+        self.cfg = cfg or ImConfig()
+        self.device = motion_lib._device
+        self.termination_distances = torch.full((NUM_BODIES,), float(self.cfg.termination_distance), device=self.device)
+        self.reset_body_mask = 0
+        for j in self.cfg.reset_body_ids:
+            self.reset_body_mask |= 1 << int(j)
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, *, body_state: torch.Tensor, progress_buf: torch.Tensor, motion_ids: torch.Tensor,
+             motion_start_times: torch.Tensor, motion_start_offset: torch.Tensor, global_offset: torch.Tensor,
+             dof_vel: Optional[torch.Tensor] = None, dof_force: Optional[torch.Tensor] = None,
+             cycle_counter: Optional[torch.Tensor] = None, obs_buf: Optional[torch.Tensor] = None,
+             self_obs_buf: Optional[torch.Tensor] = None, rew_buf: Optional[torch.Tensor] = None,
+             reward_raw: Optional[torch.Tensor] = None, reset_buf: Optional[torch.Tensor] = None,
+             terminate_buf: Optional[torch.Tensor] = None, pass_time: Optional[torch.Tensor] = None,
+             ref_body_pos=None, ref_body_vel=None, ref_body_rot=None, ref_dof_pos=None,
+             env_ids: Optional[torch.Tensor] = None, flags: int = _lib.STEP_ALL, num_envs: Optional[int] = None) -> None:
+        """One fused launch.  `body_state` is the [N, bodies_per_env, 13] rigid-body-state view (or its
+        [:, :24] slice); `dof_vel` may be the strided Isaac Gym view dof_state[..., 1]."""
+        c = self.cfg
+        a = _lib.ImStepArgs()
+        if body_state.dim() != 3 or body_state.shape[-1] != 13 or body_state.stride(-1) != 1 or body_state.stride(1) != 13:
+            raise _lib.PulseError(f"body_state must be a [N,B,13] view with row stride 13, got {tuple(body_state.shape)} / {body_state.stride()}")
+        a.body_state, a.body_env_stride = _strided(body_state, 13)
+        n_total = body_state.shape[0]
+        use_power = c.power_reward and (flags & _lib.STEP_REWARD) and dof_force is not None
+        if use_power:
+            if dof_vel is None:
+                raise _lib.PulseError("power reward needs dof_vel")
+            a.dof_vel, a.dof_env_stride, a.dof_elem_stride = dof_vel.data_ptr(), dof_vel.stride(0), dof_vel.stride(1)
+            a.dof_force, a.dof_force_stride = dof_force.data_ptr(), dof_force.stride(0)
+            if dof_force.stride(1) != 1:
+                raise _lib.PulseError("dof_force rows must be contiguous")
+        for name, t, dt_ in (("progress_buf", progress_buf, torch.int64), ("motion_ids", motion_ids, torch.int64),
+                             ("motion_start_times", motion_start_times, torch.float32),
+                             ("motion_start_offset", motion_start_offset, torch.float32), ("global_offset", global_offset, torch.float32)):
+            if t.dtype != dt_ or not t.is_contiguous() or t.shape[0] != n_total:
+                raise _lib.PulseError(f"{name}: expected contiguous {dt_} with {n_total} rows, got {t.dtype} {tuple(t.shape)}")
+            setattr(a, name, t.data_ptr())
+        if cycle_counter is not None:
+            if cycle_counter.dtype != torch.int32:
+                raise _lib.PulseError("cycle_counter must be int32 (humanoid_im.py:71)")
+            a.cycle_counter = cycle_counter.data_ptr()
+        a.termination_distances = self.termination_distances.data_ptr()
+        a.reset_body_mask = self.reset_body_mask
+        a.flags = flags
+        a.dt = c.dt
+        for k, v in c.reward_specs.items():
+            setattr(a, k, float(v))
+        a.power_coefficient = c.power_coefficient
+        a.cycle_motion = int(c.cycle_motion)
+        a.max_episode_length = int(c.max_episode_length)
+        a.enable_early_termination = int(c.enable_early_termination)
+        a.use_mean_reset = int(c.use_mean_reset)
+        if flags & _lib.STEP_OBS:
+            if obs_buf is None or obs_buf.dtype != torch.float32 or obs_buf.stride(-1) != 1 or obs_buf.shape[-1] < IM_OBS:
+                raise _lib.PulseError("obs_buf must be float32 [N, >=934] with contiguous rows")
+            a.obs_buf, a.obs_stride = obs_buf.data_ptr(), obs_buf.stride(0)
+            if self_obs_buf is not None:
+                a.self_obs_buf = self_obs_buf.data_ptr()
+            for name, t in (("ref_body_pos", ref_body_pos), ("ref_body_vel", ref_body_vel), ("ref_body_rot", ref_body_rot),
+                            ("ref_dof_pos", ref_dof_pos)):
+                if t is not None:
+                    if not t.is_contiguous():
+                        raise _lib.PulseError(f"{name} must be contiguous")
+                    setattr(a, name, t.data_ptr())
+        if flags & _lib.STEP_REWARD:
+            a.rew_buf = rew_buf.data_ptr()
+            if reward_raw is not None:
+                a.reward_raw, a.raw_stride = reward_raw.data_ptr(), reward_raw.stride(0)
+        if flags & _lib.STEP_RESET:
+            if reset_buf.dtype != torch.int64 or terminate_buf.dtype != torch.int64:
+                raise _lib.PulseError("reset_buf / terminate_buf must be int64 (base_task.py:99-105)")
+            a.reset_buf, a.terminate_buf = reset_buf.data_ptr(), terminate_buf.data_ptr()
+        if pass_time is not None:
+            a.pass_time = pass_time.data_ptr()
+        n = n_total if num_envs is None else num_envs
+        if env_ids is not None:
+            if env_ids.dtype != torch.int64 or not env_ids.is_contiguous():
+                raise _lib.PulseError("env_ids must be contiguous int64")
+            a.env_ids = env_ids.data_ptr()
+            n = int(env_ids.shape[0])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_im_step(self.motion_lib.handle, C.byref(a), n, _lib.current_stream(self.device)), "pulse_im_step")
+
+    # ------------------------------------------------------------------------------------------
+    def amp_obs(self, *, body_state: torch.Tensor, dof_pos: torch.Tensor, dof_vel: torch.Tensor, amp_obs_buf: torch.Tensor,
+                shift_history: bool = True) -> None:
+        """humanoid_amp.py:622-630 + :632-667 in one launch; amp_obs_buf [N, steps, 196] updated in place."""
+        a = _lib.AmpObsArgs()
+        a.body_state, a.body_env_stride = _strided(body_state, 13)
+        if dof_pos.stride() != dof_vel.stride():
+            raise _lib.PulseError("dof_pos and dof_vel must share strides (views of one dof-state tensor)")
+        a.dof_pos, a.dof_vel = dof_pos.data_ptr(), dof_vel.data_ptr()
+        a.dof_env_stride, a.dof_elem_stride = dof_pos.stride(0), dof_pos.stride(1)
+        if not amp_obs_buf.is_contiguous() or amp_obs_buf.shape[-1] != AMP_OBS:
+            raise _lib.PulseError("amp_obs_buf must be contiguous [N, steps, 196]")
+        a.amp_obs_buf = amp_obs_buf.data_ptr()
+        a.num_steps = int(amp_obs_buf.shape[1])
+        a.shift_history = int(shift_history)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_amp_obs(C.byref(a), int(body_state.shape[0]), _lib.current_stream(self.device)), "pulse_amp_obs")
+
+
+class HumanoidImB200Mixin:
+    """Overrides for `phc.env.tasks.humanoid_im.HumanoidIm` (method names and buffer names are the
+    reference's).  Usage:
+
+        class HumanoidImB200(HumanoidImB200Mixin, HumanoidIm): pass
+        phc.utils.parse_task.HumanoidIm = HumanoidImB200      # parse_task.py:67 resolves by name
+
+    `Humanoid.post_physics_step` (humanoid.py:1315-1346) calls, in order, `_compute_reward`,
+    `_compute_reset`, `_compute_observations()`.  With cycle_motion off nothing between them mutates
+    state, so the first call launches the fused kernel for all three and the other two return.
+    """
+
+    _pulse_ready = False
+
+    def _pulse_setup(self):
+        ml = self._motion_lib
+        self._pulse_motion_lib = ml if isinstance(ml, MotionLibB200) else MotionLibB200.from_reference(ml, device=self.device)
+        cfg = ImConfig(
+            dt=float(torch.tensor(self.dt, dtype=torch.float32)), reward_specs={k: float(v) for k, v in self.reward_specs.items()},
+            power_reward=bool(self.power_reward), power_coefficient=float(self.power_coefficient),
+            reset_body_ids=tuple(int(i) for i in self._reset_bodies_id.tolist()),
+            enable_early_termination=bool(self._enable_early_termination), cycle_motion=bool(self.cycle_motion),
+            max_episode_length=int(self.max_episode_length), num_amp_obs_steps=int(getattr(self, "_num_amp_obs_steps", 10)))
+        self._pulse = HumanoidImCompute(self._pulse_motion_lib, cfg)
+        self._pulse.termination_distances = self._termination_distances.reshape(-1)[:NUM_BODIES].to(self.device, torch.float32).contiguous()
+        self._pulse_fused_pending = False
+        self._pulse_pass_time = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        unsupported = (getattr(self, "obs_v", 6) != 6 or getattr(self, "self_obs_v", 1) != 1 or getattr(self, "_fut_tracks", False)
+                       or getattr(self, "zero_out_far", False) or getattr(self, "_occl_training", False)
+                       or not getattr(self, "_full_body_reward", True) or len(self._track_bodies_id) != NUM_BODIES
+                       or getattr(self, "add_obs_noise", False))
+        if unsupported:
+            raise _lib.PulseError("HumanoidImB200Mixin covers the default HumanoidIm configuration only "
+                                  "(obs_v 6, self_obs_v 1, 24 tracked bodies, full-body reward, no fut_tracks / zero_out_far / occlusion)")
+        self._pulse_ready = True
+
+    def resample_motions(self):
+        super().resample_motions()
+        self._pulse_ready = False  # tables changed: rebuild the packed records lazily
+
+    def _pulse_args(self):
+        if not self._pulse_ready:
+            self._pulse_setup()
+        from .flags_compat import im_eval_mean_reset
+        self._pulse.cfg.use_mean_reset = im_eval_mean_reset(self)
+        return dict(body_state=self._rigid_body_state_reshaped, dof_vel=self._dof_vel, dof_force=self.dof_force_tensor,
+                    progress_buf=self.progress_buf, motion_ids=self._sampled_motion_ids,
+                    motion_start_times=self._motion_start_times, motion_start_offset=self._motion_start_times_offset,
+                    global_offset=self._global_offset, cycle_counter=self._cycle_counter, obs_buf=self.obs_buf,
+                    self_obs_buf=self.self_obs_buf, rew_buf=self.rew_buf, reward_raw=self.reward_raw,
+                    reset_buf=self.reset_buf, terminate_buf=self._terminate_buf, pass_time=self._pulse_pass_time,
+                    ref_body_pos=self.ref_body_pos, ref_body_vel=self.ref_body_vel, ref_body_rot=self.ref_body_rot,
+                    ref_dof_pos=self.ref_dof_pos)
+
+    def _compute_reward(self, actions):
+        args = self._pulse_args()
+        if self.cycle_motion:
+            self._pulse.step(flags=_lib.STEP_REWARD, **args)
+        else:
+            self._pulse.step(flags=_lib.STEP_ALL, **args)
+            self._pulse_fused_pending = True
+
+    def _compute_reset(self):
+        if self._pulse_fused_pending:
+            return
+        # cycle_motion: wrapped envs get a new start time / offset before the reset + obs queries
+        # (humanoid_im.py:1125-1146); this host-side block keeps the reference's ops (and its syncs).
+        wrapped = self._pulse_pass_time.bool()
+        if wrapped.any():
+            self._motion_start_times_offset[wrapped] = -self.progress_buf[wrapped] * self.dt
+            self._motion_start_times[wrapped] = self._sample_time(self._sampled_motion_ids[wrapped])
+            self._cycle_counter[wrapped] = 60
+            root = self._pulse_motion_lib.get_root_pos_smpl(self._sampled_motion_ids[wrapped], self._motion_start_times[wrapped])
+            self._global_offset[wrapped, :2] = self._humanoid_root_states[wrapped, :2] - root["root_pos"][:, :2]
+        self._pulse.step(flags=_lib.STEP_RESET | _lib.STEP_OBS, **self._pulse_args())
+        self._pulse_fused_pending = True
+
+    def _compute_observations(self, env_ids=None):
+        if env_ids is None and self._pulse_fused_pending:
+            self._pulse_fused_pending = False
+            return
+        self._pulse_fused_pending = False
+        args = self._pulse_args()
+        if env_ids is not None:
+            if len(env_ids) == 0:
+                return
+            args["env_ids"] = env_ids.to(torch.int64).contiguous()
+        self._pulse.step(flags=_lib.STEP_OBS, **args)
+
+    def _update_hist_amp_obs(self, env_ids=None):
+        if env_ids is None:
+            return  # folded into _compute_amp_observations (one launch does shift + write)
+        super()._update_hist_amp_obs(env_ids)
+
+    def _compute_amp_observations(self, env_ids=None):
+        if env_ids is not None or getattr(self, "amp_obs_v", 1) != 1 or not getattr(self, "_has_dof_subset", True):
+            return super()._compute_amp_observations(env_ids)
+        if not self._pulse_ready:
+            self._pulse_setup()
+        self._pulse.amp_obs(body_state=self._rigid_body_state_reshaped, dof_pos=self._dof_pos, dof_vel=self._dof_vel,
+                            amp_obs_buf=self._amp_obs_buf, shift_history=True)
