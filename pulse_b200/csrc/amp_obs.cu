@@ -45,8 +45,9 @@ __global__ void __launch_bounds__(128) amp_obs_kernel(const pulse_amp_obs_args_t
   const float* bs = a.body_state + e * a.body_env_stride;
   const Vec3 p0 = {bs[0], bs[1], bs[2]};
   const Quat q0 = {bs[3], bs[4], bs[5], bs[6]};
-  const float hd = heading_angle(q0);
-  const Quat h_inv = yaw_quat(-hd);
+  float hs, hc;
+  heading_half(q0, hs, hc);
+  const Quat h_inv = {0.0f, 0.0f, -hs, hc};
   const Yaw yr = make_yaw(h_inv);
   float* o = buf;
   if (lane == 0) {

@@ -1,56 +1,122 @@
 // Fused HumanoidIm post-physics step kernel: reward(t) -> reset(t) -> observation(t+dt).
 //
-// One warp owns one env; lane j (< 24) owns rigid body j.  Per env the warp
-//   1. reads the per-env task scalars and the per-motion constants, computes the two motion times
-//      and the frame indices with the reference's exact fp32 operation order;
-//   2. stages up to four packed 1248-byte frame records (deduplicated when the reward and the
-//      observation query share a frame) plus the env's 24x13 rigid-body state into shared memory
-//      with cp.async (16-byte, L1-bypassing), and the dof force / velocity rows for the power term;
-//   3. blends the reference pose per lane (lerp / slerp), reduces the four reward errors and the
-//      termination test across the warp with shuffles / ballot;
-//   4. builds the 934-float observation row in shared memory and streams it out with 16-byte
-//      stores (row start may be only 8-byte aligned: 934*4 = 3736; the staging buffer is phase
-//      shifted so that global 16-byte boundaries coincide with shared ones).
+// Persistent, warp-specialised CTAs (2 per SM), each looping over groups of 8 envs:
+//   producer  (1 warp, lane = env): per-env task scalars, per-motion constants, the two motion times
+//             and frame indices in the reference's exact fp32 order; each lane then launches its env's
+//             bulk async copies (cp.async.bulk: four 1248-byte packed frame records + the 24x13
+//             rigid-body state) onto the stage's "full" mbarrier.  It runs one group AHEAD of the
+//             consumers (two shared-memory stages), so the dependent load chain scalars -> motion
+//             constants -> frame rows is hidden behind the previous group's math.
+//   consumers (6 warps = 8 envs x 24 bodies, one thread per (env, body), no idle lanes): blend the
+//             reference pose (lerp / slerp), per-body reward errors and termination distance into
+//             shared partials, observation pieces into registers; then the 934-float observation row
+//             is staged in the bytes the frame records occupied and leaves with ONE bulk async store
+//             per env (16-byte aligned middle; <= 3 ragged floats at either end stored directly);
+//             48 threads column-sum the partials, 8 threads (lane = env) finish reward / reset; the
+//             stage goes back to the producer through the "empty" mbarrier.
 //
-// HBM-bound by design: algorithmic traffic is 9 396 B per env-step and nothing is
-// re-read.  References: humanoid_im.py:853-919, :1119-1192, :677-851, :1328-1378, :1543-1628;
-// humanoid.py:1675-1731; motion_lib_base.py:434-517, :546-556.
+// HBM-bound by design: algorithmic traffic is 9 396 B per env-step, nothing is
+// re-read from DRAM.  References: humanoid_im.py:853-919, :1119-1192, :677-851, :1328-1378,
+// :1543-1628; humanoid.py:1675-1731; motion_lib_base.py:434-517, :546-556.
 #include "pulse_common.cuh"
 #include "quat_math.cuh"
 
 namespace pulse {
 namespace {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kFrame = PULSE_FRAME_REC;  // 312 floats
 constexpr int kNB = PULSE_NUM_BODIES;
-constexpr int kObs = PULSE_IM_OBS;  // 934
-constexpr int kObsPad = 944;        // 934 + 3 phase slack, rounded up to a multiple of 4
+constexpr int kEnvs = 8;                   // envs per group
+constexpr int kConsumers = kEnvs * kNB;    // 192 threads: one per (env, body)
+constexpr int kConsumerWarps = kConsumers / 32;
+constexpr int kThreads = kConsumers + 64;  // + planner warp + copy-issuer warp
+constexpr int kStages = 2;                 // data stages (frame records + body state)
+constexpr int kBatch = 4;                  // groups planned per planner pass (4 x 8 envs = 32 lanes)
+constexpr int kPlanSlots = 2;              // plan ring: batches in flight
+constexpr int kFrame = PULSE_FRAME_REC;    // 312 floats = 1248 B
+constexpr int kObs = PULSE_IM_OBS;         // 934
+constexpr int kRed = 6;                    // pos, rot, vel, ang-vel, power, distance (mean criterion)
+constexpr unsigned kFrameBytes = kFrame * 4;
+static_assert(kConsumers % 32 == 0, "consumer threads must fill whole warps");
 
-struct __align__(16) WarpStage {
-  float frames[4][kFrame];  // 4 x 1248 B
-  float body[kFrame + 8];   // rigid-body state rows of this env (+ phase slack)
-  float obs[kObsPad];       // observation row staging
+struct EnvParams {
+  long long env;     // env index after the env_ids indirection
+  long long prog;    // progress_buf
+  long long aux0, aux1;  // aux-record rows of the observation query (ref_dof_pos)
+  float b_rew, b_obs;
+  float gx, gy, gz;
+  float t_rew, mlen;
+  int cyc;
+  int valid;
+  int body_bulk;
 };
-static_assert(sizeof(WarpStage) % 16 == 0, "stage must keep 16-byte alignment");
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+struct PlanEntry {           // planner -> issuer
+  EnvParams prm;
+  long long rows[2];         // reward-query rows (the observation-query rows are prm.aux0/aux1)
+  const float* body_src;
+};
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
+struct __align__(16) Stage {
+  float frames[kEnvs][4 * kFrame];  // 4 frame records per env; env k's obs row is staged here afterwards
+  float body[kEnvs][kFrame];        // rigid-body state rows
+  EnvParams prm[kEnvs];
+};
 
-__device__ __forceinline__ Vec3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+struct __align__(16) CtaSmem {
+  Stage stage[kStages];
+  float red[kEnvs][kRed][kNB + 1];  // per-body partials, column kNB = sum
+  unsigned fallen[kEnvs];
+  PlanEntry plan[kPlanSlots][kBatch][kEnvs];
+  unsigned long long full[kStages];        // issuer -> consumers: records landed (tx bytes)
+  unsigned long long empty[kStages];       // consumers -> issuer: stage may be overwritten
+  unsigned long long plan_full[kPlanSlots];   // planner -> issuer
+  unsigned long long plan_empty[kPlanSlots];  // issuer -> planner
+};
+static_assert((kObs + 3) <= 4 * kFrame, "obs staging must fit inside the frame buffers");
+
+// ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kConsumers) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  // bounded: a byte-count bug must surface as a launch error, never as a hung GPU
+  for (int spin = 0; spin < (1 << 24); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 __device__ __forceinline__ Quat ld4(const float* p) {
   float4 v = *reinterpret_cast<const float4*>(p);
   return {v.x, v.y, v.z, v.w};
@@ -61,14 +127,14 @@ struct RefPose {
   Vec3 p, v, w;
   Quat q;
 };
-__device__ __forceinline__ RefPose blend_pose(const float* f0, const float* f1, int j, float b, Vec3 goff) {
+__device__ __forceinline__ RefPose blend_pose(const float* f0, const float* f1, int j, float b, float gx, float gy, float gz) {
   RefPose r;
   // position feeds the reset mask: reproduce ((1-b)*p0 + b*p1) + off without contraction
-  r.p.x = __fadd_rn(lerp_rn(f0[3 * j + 0], f1[3 * j + 0], b), goff.x);
-  r.p.y = __fadd_rn(lerp_rn(f0[3 * j + 1], f1[3 * j + 1], b), goff.y);
-  r.p.z = __fadd_rn(lerp_rn(f0[3 * j + 2], f1[3 * j + 2], b), goff.z);
+  r.p.x = __fadd_rn(lerp_rn(f0[3 * j + 0], f1[3 * j + 0], b), gx);
+  r.p.y = __fadd_rn(lerp_rn(f0[3 * j + 1], f1[3 * j + 1], b), gy);
+  r.p.z = __fadd_rn(lerp_rn(f0[3 * j + 2], f1[3 * j + 2], b), gz);
   r.q = slerp(ld4(f0 + 72 + 4 * j), ld4(f1 + 72 + 4 * j), b);
-  float a = 1.0f - b;
+  const float a = 1.0f - b;
   const float* v0 = f0 + 168 + 3 * j;
   const float* v1 = f1 + 168 + 3 * j;
   r.v = {a * v0[0] + b * v1[0], a * v0[1] + b * v1[1], a * v0[2] + b * v1[2]};
@@ -78,253 +144,346 @@ __device__ __forceinline__ RefPose blend_pose(const float* f0, const float* f1, 
   return r;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) im_step_kernel(const pulse_motionlib_desc_t lib,
-                                                                    const pulse_im_step_args_t a, long long num_envs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long widx = (long long)blockIdx.x * kWarpsPerCta + warp;
-  if (widx >= num_envs) return;
-  const long long e = a.env_ids != nullptr ? a.env_ids[widx] : widx;
-  WarpStage& st = reinterpret_cast<WarpStage*>(smem_raw)[warp];
+__device__ __forceinline__ void st3(float* o, Vec3 v) {
+  o[0] = v.x;
+  o[1] = v.y;
+  o[2] = v.z;
+}
 
-  const bool do_rew = a.flags & PULSE_STEP_REWARD;
-  const bool do_reset = a.flags & PULSE_STEP_RESET;
-  const bool do_obs = a.flags & PULSE_STEP_OBS;
+// ---- planner: one pass plans kBatch groups (lane = group-in-batch * 8 + env slot) ----------------------
+__device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, const pulse_im_step_args_t& a, long long num_envs,
+                                           long long ngroups, long long first_group, long long group_stride,
+                                           PlanEntry (*slot)[kEnvs], int lane, bool do_reset) {
+  const int gb = lane / kEnvs, ks = lane - gb * kEnvs;
+  const long long group = first_group + gb * group_stride;
+  const long long widx = group * kEnvs + ks;
+  PlanEntry& E = slot[gb][ks];
+  if (group < ngroups && widx < num_envs) {
+    const long long e = a.env_ids != nullptr ? a.env_ids[widx] : widx;
+    const long long prog = a.progress_buf[e];
+    const long long mid = a.motion_ids[e];
+    const float t_start = a.motion_start_times[e];
+    const float t_off = a.motion_start_offset[e];
+    const float mlen = lib.lengths[mid];
+    const float mdt = lib.dt[mid];
+    const long long nf = lib.num_frames[mid];
+    const long long row0 = lib.length_starts[mid];
+    const float t_rew = motion_time_rn(prog, a.dt, t_start, t_off);
+    const float t_obs = motion_time_rn(prog + 1, a.dt, t_start, t_off);
+    long long i0r, i1r, i0o, i1o;
+    float b_rew, b_obs;
+    frame_blend_rn(t_rew, mlen, nf, mdt, i0r, i1r, b_rew);
+    frame_blend_rn(t_obs, mlen, nf, mdt, i0o, i1o, b_obs);
+    const float* bsrc = a.body_state + e * a.body_env_stride;
+    E.rows[0] = row0 + i0r;
+    E.rows[1] = row0 + i1r;
+    E.body_src = bsrc;
+    EnvParams& P = E.prm;
+    P.env = e;
+    P.prog = prog;
+    P.aux0 = row0 + i0o;
+    P.aux1 = row0 + i1o;
+    P.b_rew = b_rew;
+    P.b_obs = b_obs;
+    P.gx = a.global_offset[3 * e + 0];
+    P.gy = a.global_offset[3 * e + 1];
+    P.gz = a.global_offset[3 * e + 2];
+    P.t_rew = t_rew;
+    P.mlen = mlen;
+    P.cyc = (do_reset && a.cycle_counter != nullptr) ? a.cycle_counter[e] : 0;
+    P.valid = 1;
+    P.body_bulk = (reinterpret_cast<uintptr_t>(bsrc) & 15u) == 0 ? 1 : 0;
+  } else {
+    E.prm.valid = 0;
+    E.prm.body_bulk = 0;
+  }
+}
 
-  // ---- 1. per-env scalars, motion constants, frame indices (uniform across the warp) ----------
-  const long long prog = a.progress_buf[e];
-  const long long mid = a.motion_ids[e];
-  const float t_start = a.motion_start_times[e];
-  const float t_off = a.motion_start_offset[e];
-  const Vec3 goff = {a.global_offset[3 * e + 0], a.global_offset[3 * e + 1], a.global_offset[3 * e + 2]};
-  const float mlen = lib.lengths[mid];
-  const float mdt = lib.dt[mid];
-  const long long nf = lib.num_frames[mid];
-  const long long row0 = lib.length_starts[mid];
-
-  const float t_rew = motion_time_rn(prog, a.dt, t_start, t_off);
-  const float t_obs = motion_time_rn(prog + 1, a.dt, t_start, t_off);
-  long long i0r, i1r, i0o, i1o;
-  float b_rew, b_obs;
-  frame_blend_rn(t_rew, mlen, nf, mdt, i0r, i1r, b_rew);
-  frame_blend_rn(t_obs, mlen, nf, mdt, i0o, i1o, b_obs);
-  const bool need_t = do_rew || do_reset;
-  long long rows[4] = {row0 + i0r, row0 + i1r, row0 + i0o, row0 + i1o};
-  int slot[4];
-  bool fetch[4];
+// ---- issuer: launch one planned group's bulk copies into a free stage (warp-collective) -------------------
+__device__ __forceinline__ void issue_group(const pulse_motionlib_desc_t& lib, const PlanEntry* plan, Stage& sg,
+                                            unsigned long long* full, int lane, bool need_t, bool do_obs) {
+  unsigned bytes = 0;
+  PlanEntry E;
+  const bool v = lane < kEnvs && plan[lane < kEnvs ? lane : 0].prm.valid != 0;
+  if (lane < kEnvs) {
+    E = plan[lane];
+    sg.prm[lane] = E.prm;
+    if (v) bytes = (need_t ? 2u : 0u) * kFrameBytes + (do_obs ? 2u : 0u) * kFrameBytes + (E.prm.body_bulk ? kFrameBytes : 0u);
+  }
+  unsigned total = bytes;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    bool wanted = (k < 2) ? need_t : do_obs;
-    slot[k] = k;
-    fetch[k] = wanted;
-#pragma unroll
-    for (int m = 0; m < k; ++m) {
-      if (fetch[k] && fetch[m] && slot[m] == m && rows[m] == rows[k]) {
-        slot[k] = m;
-        fetch[k] = false;
-      }
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+  __syncwarp();                                    // prm[] writes ordered before lane 0's release-arrive
+  if (lane == 0) mbar_arrive_expect_tx(full, total);
+  __syncwarp();                                    // the expectation is posted before any copy can complete
+  if (v) {
+    if (need_t) {
+      bulk_g2s(&sg.frames[lane][0 * kFrame], lib.frame_rec + E.rows[0] * kFrame, kFrameBytes, full);
+      bulk_g2s(&sg.frames[lane][1 * kFrame], lib.frame_rec + E.rows[1] * kFrame, kFrameBytes, full);
     }
-  }
-
-  // ---- 2. stage frame records + body state -----------------------------------------------------
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (fetch[k]) {
-      const float* src = lib.frame_rec + rows[k] * kFrame;
-      for (int c = lane; c < kFrame / 4; c += 32) cp_async16(&st.frames[k][4 * c], src + 4 * c);
+    if (do_obs) {
+      bulk_g2s(&sg.frames[lane][2 * kFrame], lib.frame_rec + E.prm.aux0 * kFrame, kFrameBytes, full);
+      bulk_g2s(&sg.frames[lane][3 * kFrame], lib.frame_rec + E.prm.aux1 * kFrame, kFrameBytes, full);
     }
+    if (E.prm.body_bulk) bulk_g2s(&sg.body[lane][0], E.body_src, kFrameBytes, full);
   }
-  const float* bsrc = a.body_state + e * a.body_env_stride;
-  const int bphase = static_cast<int>((reinterpret_cast<uintptr_t>(bsrc) >> 2) & 3);
-  float* body = st.body + bphase;  // 16-byte boundaries of the source line up with shared memory
-  {
-    const int head = (4 - bphase) & 3;  // scalars before the first aligned chunk
-    const int nvec = (kFrame - head) / 4;
-    const int tail0 = head + 4 * nvec;
-    if (lane < head) cp_async4(body + lane, bsrc + lane);
-    for (int c = lane; c < nvec; c += 32) cp_async16(body + head + 4 * c, bsrc + head + 4 * c);
-    if (lane < kFrame - tail0) cp_async4(body + tail0 + lane, bsrc + tail0 + lane);
-  }
-  // power term operands straight to registers while the copies are in flight
-  float pw = 0.0f;
-  const bool do_power = do_rew && a.dof_force != nullptr;
-  if (do_power) {
+}
+
+// raw dof force / velocity operands of the power term for (env slot k of `group`, body lane j)
+struct PowerOps {
+  float f[3], v[3];
+};
+__device__ __forceinline__ PowerOps power_load(const pulse_im_step_args_t& a, long long num_envs, long long group, int k, int j) {
+  PowerOps o;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) o.f[m] = o.v[m] = 0.0f;
+  const long long widx = group * kEnvs + k;
+  if (widx < num_envs) {
+    const long long e = a.env_ids != nullptr ? a.env_ids[widx] : widx;
     const float* fr = a.dof_force + e * a.dof_force_stride;
     const float* dv = a.dof_vel + e * a.dof_env_stride;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      int d = lane + 32 * k;
-      if (d < PULSE_NUM_DOF) pw += fabsf(fr[d] * dv[d * a.dof_elem_stride]);
+    for (int m = 0; m < 3; ++m) {
+      const int d = j + kNB * m;
+      if (d < PULSE_NUM_DOF) {
+        o.f[m] = fr[d];
+        o.v[m] = dv[d * a.dof_elem_stride];
+      }
     }
   }
-  float term_j = 0.0f;
-  if (do_reset && lane < kNB) term_j = a.termination_distances[lane];
-  const int cyc = (do_reset && a.cycle_counter != nullptr) ? a.cycle_counter[e] : 0;
-  cp_async_wait_all();
-  __syncwarp();
+  return o;
+}
 
-  // ---- 3. per-body state, heading ----------------------------------------------------------------
-  const int j = lane < kNB ? lane : kNB - 1;
-  const bool active = lane < kNB;
-  const float* bj = body + j * PULSE_BODY_STATE_W;
-  const Vec3 p = {bj[0], bj[1], bj[2]};
-  const Quat q = {bj[3], bj[4], bj[5], bj[6]};
-  const Vec3 v = {bj[7], bj[8], bj[9]};
-  const Vec3 w = {bj[10], bj[11], bj[12]};
-  const Vec3 p_root = {body[0], body[1], body[2]};
-  const Quat q_root = {body[3], body[4], body[5], body[6]};
+// Persistent, warp-specialised: planner warp -> (plan ring) -> issuer warp -> (data stages) -> consumers.
+__global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motionlib_desc_t lib, const pulse_im_step_args_t a,
+                                                              long long num_envs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const bool do_rew = a.flags & PULSE_STEP_REWARD;
+  const bool do_reset = a.flags & PULSE_STEP_RESET;
+  const bool do_obs = a.flags & PULSE_STEP_OBS;
+  const bool need_t = do_rew || do_reset;
+  const bool do_power = do_rew && a.dof_force != nullptr;
+  const long long ngroups = (num_envs + kEnvs - 1) / kEnvs;
 
-  // ---- reward + reset at t -----------------------------------------------------------------------
-  if (need_t) {
-    const RefPose r = blend_pose(st.frames[slot[0]], st.frames[slot[1]], j, b_rew, goff);
-    const bool pass_time = a.cycle_motion ? (prog >= a.max_episode_length - 1) : (t_rew >= mlen);
-    if (do_rew) {
-      float e_pos = active ? sq3(r.p - p) : 0.0f;
-      float e_vel = active ? sq3(r.v - v) : 0.0f;
-      float e_ang = active ? sq3(r.w - w) : 0.0f;
-      float th = quat_angle(qmul(r.q, qconj(q)));
-      float e_rot = active ? th * th : 0.0f;
-      e_pos = warp_sum(e_pos) * (1.0f / (3.0f * kNB));
-      e_vel = warp_sum(e_vel) * (1.0f / (3.0f * kNB));
-      e_ang = warp_sum(e_ang) * (1.0f / (3.0f * kNB));
-      e_rot = warp_sum(e_rot) * (1.0f / kNB);
-      const float r_pos = expf(-a.k_pos * e_pos);
-      const float r_rot = expf(-a.k_rot * e_rot);
-      const float r_vel = expf(-a.k_vel * e_vel);
-      const float r_ang = expf(-a.k_ang_vel * e_ang);
-      float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
-      float p_rew = 0.0f;
-      if (do_power) {
-        pw = warp_sum(pw);
-        p_rew = (prog <= 3) ? 0.0f : -a.power_coefficient * pw;
-        rew += p_rew;
-      }
-      if (lane == 0) a.rew_buf[e] = rew;
-      if (a.reward_raw != nullptr) {
-        float val = lane == 0 ? r_pos : lane == 1 ? r_rot : lane == 2 ? r_vel : lane == 3 ? r_ang : p_rew;
-        if (lane < 4 || (lane == 4 && do_power)) a.reward_raw[e * a.raw_stride + lane] = val;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < kPlanSlots; ++s) {
+      mbar_init(&sm.plan_full[s], 1);
+      mbar_init(&sm.plan_empty[s], 1);
+    }
+  }
+  __syncthreads();
+  // this CTA handles groups blockIdx.x + n * gridDim.x, n = 0 .. my_groups-1
+  const long long my_groups = (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (tid >= kConsumers + 32) {
+    // ================================ planner warp: runs up to kPlanSlots batches ahead ================
+    const int lane = tid - (kConsumers + 32);
+    for (long long b = 0; b * kBatch < my_groups; ++b) {
+      const int ps = static_cast<int>(b % kPlanSlots);
+      if (b >= kPlanSlots) mbar_wait(&sm.plan_empty[ps], ((b / kPlanSlots) - 1) & 1);
+      plan_batch(lib, a, num_envs, ngroups, blockIdx.x + b * kBatch * gridDim.x, gridDim.x, sm.plan[ps], lane, do_reset);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.plan_full[ps]);
+    }
+    return;
+  }
+  if (tid >= kConsumers) {
+    // ================================ issuer warp: bulk copies as soon as a stage is free ===============
+    const int lane = tid - kConsumers;
+    for (long long n = 0; n < my_groups; ++n) {
+      const long long b = n / kBatch;
+      const int ps = static_cast<int>(b % kPlanSlots), gb = static_cast<int>(n % kBatch);
+      const int s = static_cast<int>(n % kStages);
+      mbar_wait(&sm.plan_full[ps], (b / kPlanSlots) & 1);
+      if (n >= kStages) mbar_wait(&sm.empty[s], ((n / kStages) - 1) & 1);  // consumers released this stage
+      issue_group(lib, sm.plan[ps][gb], sm.stage[s], &sm.full[s], lane, need_t, do_obs);
+      if (gb == kBatch - 1 || n == my_groups - 1) {
+        __syncwarp();                                  // every lane has read its plan entry
+        if (lane == 0) mbar_arrive(&sm.plan_empty[ps]);
       }
     }
-    if (do_reset) {
-      const bool in_mask = active && ((a.reset_body_mask >> j) & 1u);
-      const float dist = norm3_rn(__fsub_rn(p.x, r.p.x), __fsub_rn(p.y, r.p.y), __fsub_rn(p.z, r.p.z));
-      bool fallen;
-      if (a.use_mean_reset) {
-        // mean over the reset bodies vs the first reset body's distance (humanoid_im.py:1606)
-        const unsigned m = a.reset_body_mask & 0xffffffu;
-        const float mean = warp_sum(in_mask ? dist : 0.0f) / static_cast<float>(__popc(m));
-        const float d0 = __shfl_sync(kFull, term_j, __ffs(m) - 1);
-        fallen = mean > d0;
-      } else {
-        fallen = __ballot_sync(kFull, in_mask && (dist > term_j)) != 0u;
-      }
-      fallen = fallen && (prog > 1) && a.enable_early_termination;
-      long long terminated = fallen ? 1 : 0;
-      long long reset = pass_time ? 1 : terminated;
-      if (!pass_time && cyc > 0) {  // recovering envs: humanoid_im.py:1188-1190
-        reset = 0;
-        terminated = 0;
-      }
-      if (lane == 0) {
-        a.reset_buf[e] = reset;
-        a.terminate_buf[e] = terminated;
-      }
-    }
-    if (lane == 0 && a.pass_time != nullptr) a.pass_time[e] = (t_rew >= mlen) ? 1 : 0;
+    return;
   }
 
-  // ---- observation at t + dt ---------------------------------------------------------------------
-  if (do_obs) {
-    const RefPose r = blend_pose(st.frames[slot[2]], st.frames[slot[3]], j, b_obs, goff);
-    const float hd = heading_angle(q_root);
-    const Quat h_inv = yaw_quat(-hd);
-    const Quat h_fwd = yaw_quat(hd);
-    const Yaw yr = make_yaw(h_inv);
+  // ================================== consumers: thread = (env slot k, body j) ========================
+  const int k = tid / kNB;
+  const int j = tid - k * kNB;
+  const float term_j = do_reset ? a.termination_distances[j] : 0.0f;
+  PowerOps pw_ops = {};
+  if (do_power) pw_ops = power_load(a, num_envs, blockIdx.x, k, j);
+  int it = 0;
+  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+    const int s = it % kStages;
+    Stage& sg = sm.stage[s];
+    const float pw = fabsf(pw_ops.f[0] * pw_ops.v[0]) + fabsf(pw_ops.f[1] * pw_ops.v[1]) + fabsf(pw_ops.f[2] * pw_ops.v[2]);
+    // operands of the NEXT group's power term stay in flight (registers) across this group's math
+    if (do_power && g + gridDim.x < ngroups) pw_ops = power_load(a, num_envs, g + gridDim.x, k, j);
+    mbar_wait(&sm.full[s], (it / kStages) & 1);  // frame records + body state have landed, prm[] visible
 
-    float* orow = a.obs_buf + e * a.obs_stride;
-    const int ophase = static_cast<int>((reinterpret_cast<uintptr_t>(orow) >> 2) & 3);
-    float* o = st.obs + ophase;
-    if (active) {
+    const EnvParams P = sg.prm[k];
+    const bool valid = P.valid != 0;
+    // rigid-body state: shared memory when it came through the bulk path, else straight from global
+    const float* body = P.body_bulk ? sg.body[k] : (valid ? a.body_state + P.env * a.body_env_stride : sg.body[k]);
+    const float* bj = body + j * PULSE_BODY_STATE_W;
+    const Vec3 p = {bj[0], bj[1], bj[2]};
+    const Quat q = {bj[3], bj[4], bj[5], bj[6]};
+    const Vec3 v = {bj[7], bj[8], bj[9]};
+    const Vec3 w = {bj[10], bj[11], bj[12]};
+    const Vec3 p_root = {body[0], body[1], body[2]};
+    const Quat q_root = {body[3], body[4], body[5], body[6]};
+    const float* fr = sg.frames[k];
+    if (tid < kEnvs) sm.fallen[tid] = 0u;  // OR-ed after the first consumer_sync, read after the second
+
+    // ---- reward + reset partials at t -----------------------------------------------------------------
+    RefPose r2;
+    bool is_fallen = false;
+    if (valid && need_t) {
+      const RefPose r = blend_pose(fr, fr + kFrame, j, P.b_rew, P.gx, P.gy, P.gz);
+      if (do_rew) {
+        const float th = quat_angle(qmul(r.q, qconj(q)));
+        sm.red[k][0][j] = sq3(r.p - p);
+        sm.red[k][1][j] = th * th;
+        sm.red[k][2][j] = sq3(r.v - v);
+        sm.red[k][3][j] = sq3(r.w - w);
+        sm.red[k][4][j] = pw;
+      }
+      if (do_reset) {
+        const bool in_mask = (a.reset_body_mask >> j) & 1u;
+        const float dist = norm3_rn(__fsub_rn(p.x, r.p.x), __fsub_rn(p.y, r.p.y), __fsub_rn(p.z, r.p.z));
+        sm.red[k][5][j] = in_mask ? dist : 0.0f;
+        is_fallen = in_mask && dist > term_j;
+      }
+    }
+    // ---- observation at t + dt: fold the frames into registers --------------------------------------------
+    if (valid && do_obs) r2 = blend_pose(fr + 2 * kFrame, fr + 3 * kFrame, j, P.b_obs, P.gx, P.gy, P.gz);
+    consumer_sync();  // all frame records consumed: their bytes become the obs rows; partials complete
+
+    float* orow = nullptr;
+    int ophase = 0;
+    if (valid && do_obs) {
+      float hs, hc;
+      heading_half(q_root, hs, hc);
+      const Yaw yr = make_yaw(Quat{0.0f, 0.0f, -hs, hc});
+      orow = a.obs_buf + P.env * a.obs_stride;
+      ophase = static_cast<int>((reinterpret_cast<uintptr_t>(orow) >> 2) & 3);
+      float* o = sg.frames[k] + ophase;  // global 16-byte boundaries coincide with shared ones
       // self observation (humanoid.py:1675-1731)
-      if (j == 0) {
-        o[0] = p_root.z;
-      } else {
-        Vec3 lp = yaw_rot(yr, p - p_root);
-        o[1 + 3 * (j - 1) + 0] = lp.x;
-        o[1 + 3 * (j - 1) + 1] = lp.y;
-        o[1 + 3 * (j - 1) + 2] = lp.z;
-      }
-      qsix(qmul(h_inv, q), o + 70 + 6 * j);
-      Vec3 lv = yaw_rot(yr, v);
-      o[214 + 3 * j + 0] = lv.x;
-      o[214 + 3 * j + 1] = lv.y;
-      o[214 + 3 * j + 2] = lv.z;
-      Vec3 lw = yaw_rot(yr, w);
-      o[286 + 3 * j + 0] = lw.x;
-      o[286 + 3 * j + 1] = lw.y;
-      o[286 + 3 * j + 2] = lw.z;
+      if (j == 0) o[0] = p_root.z;
+      else st3(o + 1 + 3 * (j - 1), yaw_rot(yr, p - p_root));
+      qsix(yaw_mul_left(-hs, hc, q), o + 70 + 6 * j);
+      st3(o + 214 + 3 * j, yaw_rot(yr, v));
+      st3(o + 286 + 3 * j, yaw_rot(yr, w));
       // task observation v6 (humanoid_im.py:1328-1378), block-major
       float* t = o + PULSE_SELF_OBS;
-      Vec3 dp = yaw_rot(yr, r.p - p);
-      t[3 * j + 0] = dp.x;
-      t[3 * j + 1] = dp.y;
-      t[3 * j + 2] = dp.z;
-      qsix(qmul(qmul(h_inv, qmul(r.q, qconj(q))), h_fwd), t + 72 + 6 * j);
-      Vec3 dv = yaw_rot(yr, r.v - v);
-      t[216 + 3 * j + 0] = dv.x;
-      t[216 + 3 * j + 1] = dv.y;
-      t[216 + 3 * j + 2] = dv.z;
-      Vec3 dw = yaw_rot(yr, r.w - w);
-      t[288 + 3 * j + 0] = dw.x;
-      t[288 + 3 * j + 1] = dw.y;
-      t[288 + 3 * j + 2] = dw.z;
-      Vec3 rp = yaw_rot(yr, r.p - p_root);
-      t[360 + 3 * j + 0] = rp.x;
-      t[360 + 3 * j + 1] = rp.y;
-      t[360 + 3 * j + 2] = rp.z;
-      qsix(qmul(h_inv, r.q), t + 432 + 6 * j);
+      st3(t + 3 * j, yaw_rot(yr, r2.p - p));
+      qsix(yaw_mul_right(yaw_mul_left(-hs, hc, qmul(r2.q, qconj(q))), hs, hc), t + 72 + 6 * j);
+      st3(t + 216 + 3 * j, yaw_rot(yr, r2.v - v));
+      st3(t + 288 + 3 * j, yaw_rot(yr, r2.w - w));
+      st3(t + 360 + 3 * j, yaw_rot(yr, r2.p - p_root));
+      qsix(yaw_mul_left(-hs, hc, r2.q), t + 432 + 6 * j);
       // reference-pose side buffers (humanoid_im.py:835-848)
-      if (a.ref_body_pos != nullptr) {
-        float* d = a.ref_body_pos + e * (kNB * 3) + 3 * j;
-        d[0] = r.p.x; d[1] = r.p.y; d[2] = r.p.z;
-      }
-      if (a.ref_body_vel != nullptr) {
-        float* d = a.ref_body_vel + e * (kNB * 3) + 3 * j;
-        d[0] = r.v.x; d[1] = r.v.y; d[2] = r.v.z;
-      }
+      if (a.ref_body_pos != nullptr) st3(a.ref_body_pos + P.env * (kNB * 3) + 3 * j, r2.p);
+      if (a.ref_body_vel != nullptr) st3(a.ref_body_vel + P.env * (kNB * 3) + 3 * j, r2.v);
       if (a.ref_body_rot != nullptr) {
-        float* d = a.ref_body_rot + e * (kNB * 4) + 4 * j;
-        d[0] = r.q.x; d[1] = r.q.y; d[2] = r.q.z; d[3] = r.q.w;
+        float* d = a.ref_body_rot + P.env * (kNB * 4) + 4 * j;
+        d[0] = r2.q.x; d[1] = r2.q.y; d[2] = r2.q.z; d[3] = r2.q.w;
+      }
+      if (a.ref_dof_pos != nullptr && j >= 1) {
+        // dof_pos = exp_map(slerp(lrs[f0, j], lrs[f1, j], blend)), joints 1..23 (motion_lib_base.py:489-490)
+        const float* x0 = lib.aux_rec + P.aux0 * PULSE_AUX_REC + 4 * j;
+        const float* x1 = lib.aux_rec + P.aux1 * PULSE_AUX_REC + 4 * j;
+        st3(a.ref_dof_pos + P.env * PULSE_NUM_DOF + 3 * (j - 1), quat_exp_map(slerp(ld4(x0), ld4(x1), P.b_obs)));
       }
     }
-    if (a.ref_dof_pos != nullptr && lane >= 1 && lane < kNB) {
-      // dof_pos = exp_map(slerp(lrs[f0, j], lrs[f1, j], blend)), joints 1..23 (motion_lib_base.py:489-490)
-      const float* x0 = lib.aux_rec + rows[2] * PULSE_AUX_REC + 4 * lane;
-      const float* x1 = lib.aux_rec + rows[3] * PULSE_AUX_REC + 4 * lane;
-      Vec3 em = quat_exp_map(slerp(ld4(x0), ld4(x1), b_obs));
-      float* d = a.ref_dof_pos + e * PULSE_NUM_DOF + 3 * (lane - 1);
-      d[0] = em.x; d[1] = em.y; d[2] = em.z;
-    }
-    __syncwarp();
-    // stream the row out: 16-byte stores on aligned slots, scalars on the ragged ends
-    const int nslot = (ophase + kObs + 3) / 4;
-    for (int s = lane; s < nslot; s += 32) {
-      const int k0 = 4 * s - ophase;  // obs index of the slot's first float
-      if (k0 >= 0 && k0 + 3 < kObs) {
-        *reinterpret_cast<float4*>(orow + k0) = *reinterpret_cast<const float4*>(st.obs + 4 * s);
-      } else {
+    // column sums of the partials: thread (kk, c) adds 24 values; fallen flags OR-ed per env
+    if (need_t && tid < kEnvs * kRed) {
+      const int kk = tid / kRed, c = tid - kk * kRed;
+      float sum = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int k = k0 + i;
-          if (k >= 0 && k < kObs) orow[k] = st.obs[4 * s + i];
+      for (int b = 0; b < kNB; ++b) sum += sm.red[kk][c][b];
+      sm.red[kk][c][kNB] = sum;
+    }
+    if (is_fallen) atomicOr(&sm.fallen[k], 1u);  // zeroed before the first consumer_sync of this iteration
+    fence_proxy_async();  // generic-proxy writes of the obs rows -> visible to the bulk (async proxy) store
+    consumer_sync();
+
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    if (valid && do_obs) {
+      const int head = (4 - ophase) & 3;         // floats before the first 16-byte boundary
+      const int nmid = ((kObs - head) / 4) * 4;  // floats in the aligned middle
+      const float* o = sg.frames[k] + ophase;
+      if (j == 0) {
+        bulk_s2g(orow + head, o + head, static_cast<unsigned>(nmid) * 4u);
+        bulk_commit();
+      } else if (j <= 3) {
+        if (j - 1 < head) orow[j - 1] = o[j - 1];
+      } else if (j <= 6) {
+        const int i = head + nmid + (j - 4);
+        if (i < kObs) orow[i] = o[i];
+      }
+      if (a.self_obs_buf != nullptr) {
+        float* srow = a.self_obs_buf + P.env * PULSE_SELF_OBS;
+        for (int i = j; i < PULSE_SELF_OBS; i += kNB) srow[i] = o[i];
+      }
+    }
+    if (tid < kEnvs && sg.prm[tid].valid && need_t) {  // lane = env slot: finish reward / reset
+      const EnvParams& Q = sg.prm[tid];
+      const long long ee = Q.env;
+      const bool pass_time = a.cycle_motion ? (Q.prog >= a.max_episode_length - 1) : (Q.t_rew >= Q.mlen);
+      if (do_rew) {
+        const float e_pos = sm.red[tid][0][kNB] * (1.0f / (3.0f * kNB));
+        const float e_rot = sm.red[tid][1][kNB] * (1.0f / kNB);
+        const float e_vel = sm.red[tid][2][kNB] * (1.0f / (3.0f * kNB));
+        const float e_ang = sm.red[tid][3][kNB] * (1.0f / (3.0f * kNB));
+        const float r_pos = expf(-a.k_pos * e_pos);
+        const float r_rot = expf(-a.k_rot * e_rot);
+        const float r_vel = expf(-a.k_vel * e_vel);
+        const float r_ang = expf(-a.k_ang_vel * e_ang);
+        float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
+        float p_rew = 0.0f;
+        if (do_power) {
+          p_rew = (Q.prog <= 3) ? 0.0f : -a.power_coefficient * sm.red[tid][4][kNB];
+          rew += p_rew;
+        }
+        a.rew_buf[ee] = rew;
+        if (a.reward_raw != nullptr) {
+          float* rr = a.reward_raw + ee * a.raw_stride;
+          rr[0] = r_pos; rr[1] = r_rot; rr[2] = r_vel; rr[3] = r_ang;
+          if (do_power) rr[4] = p_rew;
         }
       }
+      if (do_reset) {
+        bool fallen;
+        if (a.use_mean_reset) {
+          // mean over the reset bodies vs the first reset body's distance (humanoid_im.py:1606)
+          const unsigned m = a.reset_body_mask & 0xffffffu;
+          fallen = (sm.red[tid][5][kNB] / static_cast<float>(__popc(m))) > a.termination_distances[__ffs(m) - 1];
+        } else {
+          fallen = sm.fallen[tid] != 0u;
+        }
+        fallen = fallen && (Q.prog > 1) && a.enable_early_termination;
+        long long terminated = fallen ? 1 : 0;
+        long long reset = pass_time ? 1 : terminated;
+        if (!pass_time && Q.cyc > 0) {  // recovering envs: humanoid_im.py:1188-1190
+          reset = 0;
+          terminated = 0;
+        }
+        a.reset_buf[ee] = reset;
+        a.terminate_buf[ee] = terminated;
+      }
+      if (a.pass_time != nullptr) a.pass_time[ee] = (Q.t_rew >= Q.mlen) ? 1 : 0;
     }
-    if (a.self_obs_buf != nullptr) {
-      float* srow = a.self_obs_buf + e * PULSE_SELF_OBS;
-      for (int k = lane; k < PULSE_SELF_OBS; k += 32) srow[k] = o[k];
-    }
+    if (valid && do_obs && j == 0) bulk_wait_read();  // the stage's bytes are free once the store has read them
+    consumer_sync();                                   // also orders this iteration's red[] / fallen[] reads
+    if (tid == 0) mbar_arrive(&sm.empty[s]);           // hand the stage back to the producer
   }
 }
 
@@ -344,6 +503,7 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
   PULSE_REQUIRE(a.body_env_stride >= PULSE_NUM_BODIES * PULSE_BODY_STATE_W, "pulse_im_step: body_env_stride %lld < 312",
                 (long long)a.body_env_stride);
   PULSE_REQUIRE((reinterpret_cast<uintptr_t>(a.body_state) & 3u) == 0, "pulse_im_step: body_state not 4-byte aligned");
+  PULSE_REQUIRE(aligned16(lib->d.frame_rec), "pulse_im_step: frame records not 16-byte aligned");
   if (a.flags & PULSE_STEP_REWARD) {
     PULSE_REQUIRE(a.rew_buf != nullptr, "pulse_im_step: rew_buf is null");
     if (a.dof_force) {
@@ -363,13 +523,22 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
     PULSE_REQUIRE(!a.ref_dof_pos || lib->d.aux_rec, "pulse_im_step: ref_dof_pos needs the aux records");
   }
   static bool attr_set = false;
-  const size_t smem = sizeof(WarpStage) * kWarpsPerCta;
+  const size_t smem = sizeof(CtaSmem);
   if (!attr_set) {
     PULSE_CUDA_OK(cudaFuncSetAttribute(im_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const unsigned grid = static_cast<unsigned>((num_envs + kWarpsPerCta - 1) / kWarpsPerCta);
-  im_step_kernel<<<grid, kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(lib->d, a, (long long)num_envs);
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    PULSE_CUDA_OK(cudaGetDevice(&dev));
+    PULSE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PULSE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, im_step_kernel, kThreads, smem));
+    max_ctas = sms * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
+  }
+  const long long ngroups = (num_envs + kEnvs - 1) / kEnvs;
+  const unsigned grid = static_cast<unsigned>(ngroups < max_ctas ? ngroups : max_ctas);
+  im_step_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(lib->d, a, (long long)num_envs);
   PULSE_LAUNCH_OK("im_step_kernel");
   return PULSE_OK;
 }

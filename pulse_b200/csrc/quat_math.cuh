@@ -57,6 +57,15 @@ __device__ __forceinline__ Vec3 yaw_rot(Yaw y, Vec3 v) {
   return {v.x * y.s - y.wz2 * v.y, v.y * y.s + y.wz2 * v.x, v.z * y.s + y.zz2 * v.z};
 }
 
+// (0,0,z,w) (x) q and q (x) (0,0,z,w): the Hamilton product with the zero components folded away
+// (the reference multiplies by the heading quaternion with the general quat_mul; same value to ~1e-7).
+__device__ __forceinline__ Quat yaw_mul_left(float z, float w, Quat q) {
+  return {w * q.x - z * q.y, w * q.y + z * q.x, w * q.z + z * q.w, w * q.w - z * q.z};
+}
+__device__ __forceinline__ Quat yaw_mul_right(Quat q, float z, float w) {
+  return {q.x * w + q.y * z, q.y * w - q.x * z, q.w * z + q.z * w, q.w * w - q.z * z};
+}
+
 // phc/utils/torch_utils.py:100-113 (quat_to_tan_norm): rotated x axis, then rotated z axis.
 __device__ __forceinline__ void qsix(Quat q, float* o) {
   float s = 2.0f * q.w * q.w - 1.0f;
@@ -73,22 +82,45 @@ __device__ __forceinline__ void qsix(Quat q, float* o) {
   o[5] = s + q.z * dz;
 }
 
-// isaacgym.torch_utils.normalize_angle [3P-memory]
+// isaacgym.torch_utils.normalize_angle [3P-memory]: atan2(sin x, cos x) -- general argument.
 __device__ __forceinline__ float wrap_angle(float x) { return atan2f(sinf(x), cosf(x)); }
+
+// The same function restricted to x = 2*acos(w) in [0, 2*pi]: identity below pi, x - 2*pi from
+// fp32(pi) upwards (sin(fp32(pi)) < 0, so the reference maps fp32(pi) itself to -pi).  Differs from
+// the atan2 form by < 5e-7.
+__device__ __forceinline__ float wrap_angle_0_2pi(float x) { return x >= 3.14159274f ? x - 6.28318548f : x; }
+
+// a / b with the hardware reciprocal (2 ulp); only for quantities under the 1e-4 float tolerance.
+__device__ __forceinline__ float fdiv_fast(float a, float b) { return __fdividef(a, b); }
+
+// sin(x) for x in [0, pi/2] (slerp arguments are (1-t)*h and t*h with h <= pi/2): odd Taylor
+// polynomial through x^15, truncation error < 1e-9, no range reduction, no slow path.
+__device__ __forceinline__ float sin_0_halfpi(float x) {
+  const float z = x * x;
+  float p = -7.6471637e-13f;           // -1/15!
+  p = fmaf(p, z, 1.6059044e-10f);      //  1/13!
+  p = fmaf(p, z, -2.5052108e-8f);      // -1/11!
+  p = fmaf(p, z, 2.7557319e-6f);       //  1/9!
+  p = fmaf(p, z, -1.9841270e-4f);      // -1/7!
+  p = fmaf(p, z, 8.3333333e-3f);       //  1/5!
+  p = fmaf(p, z, -1.6666667e-1f);      // -1/3!
+  return fmaf(x * z, p, x);
+}
 
 // phc/utils/torch_utils.py:57-78 (quat_to_angle_axis): angle only (used by the rotation reward).
 __device__ __forceinline__ float quat_angle(Quat q) {
   float s = sqrtf(1.0f - q.w * q.w);
-  float ang = wrap_angle(2.0f * acosf(q.w));
+  float ang = wrap_angle_0_2pi(2.0f * acosf(q.w));
   return (fabsf(s) > 1e-5f) ? ang : 0.0f;  // NaN s (|w|>1) fails the test like the reference's mask
 }
 
 // phc/utils/torch_utils.py:81-97 (quat_to_exp_map)
 __device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
   float s = sqrtf(1.0f - q.w * q.w);
-  float ang = wrap_angle(2.0f * acosf(q.w));
+  float ang = wrap_angle_0_2pi(2.0f * acosf(q.w));
   if (!(fabsf(s) > 1e-5f)) return {0.0f, 0.0f, 0.0f};  // angle 0 * default axis
-  return {ang * (q.x / s), ang * (q.y / s), ang * (q.z / s)};
+  const float k = fdiv_fast(ang, s);
+  return {k * q.x, k * q.y, k * q.z};
 }
 
 // isaacgym.torch_utils.quat_from_angle_axis with axis = +z [3P-memory], incl. the final quat_unit.
@@ -124,13 +156,16 @@ __device__ __forceinline__ Quat slerp(Quat a, Quat b, float t) {
   }
   c = fabsf(c);
   if (c >= 1.0f) return a;
-  float s = sqrtf(1.0f - c * c);
+  // 1 - c*c cancels badly near c = 1: keep the reference's two roundings (an FMA here would be MORE
+  // accurate than the reference and move the result by up to ~3e-4 relative at small angles)
+  float s = sqrtf(__fsub_rn(1.0f, __fmul_rn(c, c)));
   if (fabsf(s) < 0.001f) {
     return {0.5f * a.x + 0.5f * b.x, 0.5f * a.y + 0.5f * b.y, 0.5f * a.z + 0.5f * b.z, 0.5f * a.w + 0.5f * b.w};
   }
-  float h = acosf(c);
-  float ra = sinf((1.0f - t) * h) / s;
-  float rb = sinf(t * h) / s;
+  const float h = acosf(c);
+  const float inv_s = fdiv_fast(1.0f, s);
+  const float ra = sin_0_halfpi((1.0f - t) * h) * inv_s;
+  const float rb = sin_0_halfpi(t * h) * inv_s;
   return {ra * a.x + rb * b.x, ra * a.y + rb * b.y, ra * a.z + rb * b.z, ra * a.w + rb * b.w};
 }
 
@@ -140,6 +175,31 @@ __device__ __forceinline__ float heading_angle(Quat q) {
   float rx = s + 2.0f * q.x * q.x;
   float ry = 2.0f * q.w * q.z + 2.0f * q.x * q.y;
   return atan2f(ry, rx);
+}
+
+// calc_heading_quat / calc_heading_quat_inv (torch_utils.py:215-240) without the angle round trip:
+// from the rotated x axis (rx, ry) the half-angle sine / cosine follow algebraically, so no atan2 /
+// sincos is needed.  heading = atan2(ry, rx); returns (sin(h/2), cos(h/2)); h_fwd = (0,0,s,c),
+// h_inv = (0,0,-s,c).  Agrees with the angle form to ~2e-7 (the reference's final quat_unit included).
+__device__ __forceinline__ void heading_half(Quat q, float& s_half, float& c_half) {
+  const float s = 2.0f * q.w * q.w - 1.0f;
+  const float rx = s + 2.0f * q.x * q.x;
+  const float ry = 2.0f * q.w * q.z + 2.0f * q.x * q.y;
+  const float n2 = rx * rx + ry * ry;
+  if (!(n2 > 0.0f)) {  // atan2(0, 0) = 0
+    s_half = 0.0f;
+    c_half = 1.0f;
+    return;
+  }
+  const float inv = rsqrtf(n2);
+  const float ch = rx * inv, sh = ry * inv;
+  if (ch >= 0.0f) {
+    c_half = sqrtf(0.5f * (1.0f + ch));
+    s_half = fdiv_fast(0.5f * sh, c_half);
+  } else {
+    s_half = copysignf(sqrtf(0.5f * (1.0f - ch)), sh);
+    c_half = fdiv_fast(0.5f * sh, s_half);
+  }
 }
 
 // ---- exact-order pieces (their results decide integer outputs) ---------------------------------

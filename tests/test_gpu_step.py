@@ -62,7 +62,7 @@ def _check_step(out, ref, n_obs=934):
     torch.testing.assert_close(out["self_obs_buf"], ref["obs_buf"][:, :358], atol=OBS_ATOL, rtol=0)
     if "ref_body_pos" in out:
         torch.testing.assert_close(out["ref_body_pos"], ref["ref_body_pos"], atol=1e-5, rtol=0)
-        torch.testing.assert_close(out["ref_body_rot"], ref["ref_body_rot"], atol=1e-5, rtol=0)
+        torch.testing.assert_close(out["ref_body_rot"], ref["ref_body_rot"], atol=OBS_ATOL, rtol=0)
         torch.testing.assert_close(out["ref_body_vel"], ref["ref_body_vel"], atol=1e-5, rtol=0)
         torch.testing.assert_close(out["ref_dof_pos"], ref["ref_dof_pos"], atol=OBS_ATOL, rtol=0)
 
@@ -78,7 +78,9 @@ def test_motion_state_matches_reference_golden():
     assert torch.equal(out["blend"].cpu(), z["blend"])
     for k in ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa", "rg_pos", "rb_rot", "body_vel",
               "body_ang_vel"):
-        torch.testing.assert_close(out[k].cpu(), z[k], atol=2e-5, rtol=0, msg=lambda m, k=k: f"{k}: {m}")
+        # rotations go through slerp (acos / sin of tiny angles): the 1e-4 observation bar applies
+        tol = 1e-4 if k in ("root_rot", "rb_rot", "dof_pos") else 1e-5
+        torch.testing.assert_close(out[k].cpu(), z[k], atol=tol, rtol=0, msg=lambda m, k=k: f"{k}: {m}")
     rp = ml.get_root_pos_smpl(z["ids"].to(dev), z["times"].to(dev))["root_pos"].cpu()
     torch.testing.assert_close(rp, z["root_pos_smpl"], atol=1e-6, rtol=0)
     st = ml.sample_time_interval(z["ids"].to(dev), phase=z["phase"].to(dev)).cpu()
