@@ -1,19 +1,22 @@
 // Fused HumanoidIm post-physics step kernel: reward(t) -> reset(t) -> observation(t+dt).
 //
-// Persistent, warp-specialised CTAs (2 per SM), each looping over groups of 8 envs:
-//   producer  (1 warp, lane = env): per-env task scalars, per-motion constants, the two motion times
-//             and frame indices in the reference's exact fp32 order; each lane then launches its env's
-//             bulk async copies (cp.async.bulk: four 1248-byte packed frame records + the 24x13
-//             rigid-body state) onto the stage's "full" mbarrier.  It runs one group AHEAD of the
-//             consumers (two shared-memory stages), so the dependent load chain scalars -> motion
-//             constants -> frame rows is hidden behind the previous group's math.
-//   consumers (6 warps = 8 envs x 24 bodies, one thread per (env, body), no idle lanes): blend the
-//             reference pose (lerp / slerp), per-body reward errors and termination distance into
-//             shared partials, observation pieces into registers; then the 934-float observation row
-//             is staged in the bytes the frame records occupied and leaves with ONE bulk async store
-//             per env (16-byte aligned middle; <= 3 ragged floats at either end stored directly);
-//             48 threads column-sum the partials, 8 threads (lane = env) finish reward / reset; the
-//             stage goes back to the producer through the "empty" mbarrier.
+// One persistent, warp-specialised CTA per SM (20 warps), looping over groups of 8 envs:
+//   planner   (1 warp, lane = env, 4 groups per pass): per-env task scalars, per-motion constants, the
+//             two motion times and frame indices in the reference's exact fp32 order; deduplicates the
+//             four frame rows of the two queries into <= 3 copy slots (at 30 fps the reward query's
+//             second frame IS the observation query's first).  Runs up to two passes (8 groups) ahead
+//             through a plan ring.
+//   issuer    (1 warp): the moment a data stage is free, launches the group's bulk async copies
+//             (cp.async.bulk: 1248-byte packed frame records + the 24x13 rigid-body state) onto the
+//             stage's "full" mbarrier -- the dependent chain scalars -> motion constants -> rows is
+//             already resolved, so every stage that is not being computed on has loads in flight.
+//   consumers (3 teams x 6 warps; a team = 8 envs x 24 bodies, one thread per (env, body), no idle
+//             lanes): blend the reference pose (lerp / slerp), per-body reward errors and termination
+//             distance into shared partials, observation pieces into registers; the 934-float row is
+//             then staged in the bytes the env's records occupied and leaves with ONE bulk async store
+//             per env (16-byte aligned middle; <= 3 ragged floats at either end stored directly).  Teams
+//             take groups round-robin; five data stages keep two groups loading while three compute.  The
+//             power-term operands |tau . qdot| of a team's next group ride in registers across its math.
 //
 // HBM-bound by design: algorithmic traffic is 9 396 B per env-step, nothing is
 // re-read from DRAM.  References: humanoid_im.py:853-919, :1119-1192, :677-851, :1328-1378,
@@ -26,53 +29,61 @@ namespace {
 
 constexpr int kNB = PULSE_NUM_BODIES;
 constexpr int kEnvs = 8;                   // envs per group
-constexpr int kConsumers = kEnvs * kNB;    // 192 threads: one per (env, body)
-constexpr int kConsumerWarps = kConsumers / 32;
-constexpr int kThreads = kConsumers + 64;  // + planner warp + copy-issuer warp
-constexpr int kStages = 2;                 // data stages (frame records + body state)
+constexpr int kTeam = kEnvs * kNB;         // 192 threads: one per (env, body)
+constexpr int kTeams = 3;                  // consumer teams per CTA
+constexpr int kConsumers = kTeam * kTeams; // 576
+constexpr int kThreads = kConsumers + 64;  // + issuer warp + planner warp (20 warps: register cap 102)
+constexpr int kStages = 5;                 // data stages
 constexpr int kBatch = 4;                  // groups planned per planner pass (4 x 8 envs = 32 lanes)
-constexpr int kPlanSlots = 2;              // plan ring: batches in flight
+constexpr int kPlanSlots = 2;              // plan ring: planner passes in flight
 constexpr int kFrame = PULSE_FRAME_REC;    // 312 floats = 1248 B
+constexpr int kSlots = 3;                  // frame-record copy slots per env
 constexpr int kObs = PULSE_IM_OBS;         // 934
-constexpr int kRed = 6;                    // pos, rot, vel, ang-vel, power, distance (mean criterion)
+constexpr int kRed = 6;                    // pos, rot, vel, ang-vel, distance (mean criterion), power
 constexpr unsigned kFrameBytes = kFrame * 4;
-static_assert(kConsumers % 32 == 0, "consumer threads must fill whole warps");
+constexpr unsigned kDirect = 3;            // slot id of a 4th distinct row: read straight from global / L2
+static_assert(kTeam % 32 == 0, "a team must fill whole warps");
 
-struct EnvParams {
-  long long env;     // env index after the env_ids indirection
-  long long prog;    // progress_buf
-  long long aux0, aux1;  // aux-record rows of the observation query (ref_dof_pos)
+struct EnvParams {           // issuer -> consumers (copied into the stage)
+  long long env;             // env index after the env_ids indirection
+  long long prog;            // progress_buf
+  long long aux0, aux1;      // rows of the observation query (aux records for ref_dof_pos)
+  long long direct_row;      // row that did not get a copy slot (rare), else -1
   float b_rew, b_obs;
   float gx, gy, gz;
   float t_rew, mlen;
   int cyc;
   int valid;
   int body_bulk;
+  unsigned char sl[4];       // copy slot (0..2, or kDirect) of logical rows: rew f0, rew f1, obs f0, obs f1
 };
 
 struct PlanEntry {           // planner -> issuer
   EnvParams prm;
-  long long rows[2];         // reward-query rows (the observation-query rows are prm.aux0/aux1)
+  long long slot_row[kSlots];
   const float* body_src;
+  int nslots;
 };
 
+// Per env: [slot0 | slot1 | slot2 | body]; the obs row is staged over the same bytes once they are consumed.
+constexpr int kEnvBlock = (kSlots + 1) * kFrame;
 struct __align__(16) Stage {
-  float frames[kEnvs][4 * kFrame];  // 4 frame records per env; env k's obs row is staged here afterwards
-  float body[kEnvs][kFrame];        // rigid-body state rows
+  float env[kEnvs][kEnvBlock];
   EnvParams prm[kEnvs];
 };
+static_assert((kObs + 3) <= kEnvBlock, "obs staging must fit inside the env block");
 
 struct __align__(16) CtaSmem {
   Stage stage[kStages];
-  float red[kEnvs][kRed][kNB + 1];  // per-body partials, column kNB = sum
-  unsigned fallen[kEnvs];
+  float red[kTeams][kEnvs][kRed][kNB + 1];  // per-body partials, column kNB = sum
+  float root[kTeams][kEnvs][8];             // root position / rotation of the team's envs
   PlanEntry plan[kPlanSlots][kBatch][kEnvs];
-  unsigned long long full[kStages];        // issuer -> consumers: records landed (tx bytes)
-  unsigned long long empty[kStages];       // consumers -> issuer: stage may be overwritten
+  unsigned fallen[kTeams][kEnvs];
+  unsigned long long full[kStages];           // issuer -> consumers: records landed (tx bytes)
+  unsigned long long empty[kStages];          // consumers -> issuer: stage may be overwritten
   unsigned long long plan_full[kPlanSlots];   // planner -> issuer
   unsigned long long plan_empty[kPlanSlots];  // issuer -> planner
 };
-static_assert((kObs + 3) <= 4 * kFrame, "obs staging must fit inside the frame buffers");
 
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -86,7 +97,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kConsumers) : "memory"); }
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;\n" ::"r"(team + 1), "n"(kTeam) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
   asm volatile(
@@ -122,7 +133,7 @@ __device__ __forceinline__ Quat ld4(const float* p) {
   return {v.x, v.y, v.z, v.w};
 }
 
-// Reference pose of body j blended between two staged frame records.
+// Reference pose of body j blended between two frame records.
 struct RefPose {
   Vec3 p, v, w;
   Quat q;
@@ -153,7 +164,7 @@ __device__ __forceinline__ void st3(float* o, Vec3 v) {
 // ---- planner: one pass plans kBatch groups (lane = group-in-batch * 8 + env slot) ----------------------
 __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, const pulse_im_step_args_t& a, long long num_envs,
                                            long long ngroups, long long first_group, long long group_stride,
-                                           PlanEntry (*slot)[kEnvs], int lane, bool do_reset) {
+                                           PlanEntry (*slot)[kEnvs], int lane, bool need_t, bool do_obs, bool do_reset) {
   const int gb = lane / kEnvs, ks = lane - gb * kEnvs;
   const long long group = first_group + gb * group_stride;
   const long long widx = group * kEnvs + ks;
@@ -174,15 +185,45 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
     float b_rew, b_obs;
     frame_blend_rn(t_rew, mlen, nf, mdt, i0r, i1r, b_rew);
     frame_blend_rn(t_obs, mlen, nf, mdt, i0o, i1o, b_obs);
+    const long long rows[4] = {row0 + i0r, row0 + i1r, row0 + i0o, row0 + i1o};
+    // <= 3 copy slots for the (up to) four rows; a 4th distinct row is fetched by the consumers directly
+    long long srow[kSlots] = {-1, -1, -1};
+    long long direct = -1;
+    int ns = 0;
+    unsigned char sl[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const bool wanted = (r < 2) ? need_t : do_obs;
+      if (!wanted) continue;
+      int found = -1;
+#pragma unroll
+      for (int m = 0; m < kSlots; ++m)
+        if (m < ns && srow[m] == rows[r]) found = m;
+      if (found < 0) {
+        if (ns < kSlots) {
+          found = ns;
+#pragma unroll
+          for (int m = 0; m < kSlots; ++m)
+            if (m == ns) srow[m] = rows[r];
+          ++ns;
+        } else {
+          found = kDirect;
+          direct = rows[r];
+        }
+      }
+      sl[r] = static_cast<unsigned char>(found);
+    }
     const float* bsrc = a.body_state + e * a.body_env_stride;
-    E.rows[0] = row0 + i0r;
-    E.rows[1] = row0 + i1r;
+#pragma unroll
+    for (int m = 0; m < kSlots; ++m) E.slot_row[m] = srow[m];
+    E.nslots = ns;
     E.body_src = bsrc;
     EnvParams& P = E.prm;
     P.env = e;
     P.prog = prog;
-    P.aux0 = row0 + i0o;
-    P.aux1 = row0 + i1o;
+    P.aux0 = rows[2];
+    P.aux1 = rows[3];
+    P.direct_row = direct;
     P.b_rew = b_rew;
     P.b_obs = b_obs;
     P.gx = a.global_offset[3 * e + 0];
@@ -193,43 +234,45 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
     P.cyc = (do_reset && a.cycle_counter != nullptr) ? a.cycle_counter[e] : 0;
     P.valid = 1;
     P.body_bulk = (reinterpret_cast<uintptr_t>(bsrc) & 15u) == 0 ? 1 : 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) P.sl[r] = sl[r];
   } else {
     E.prm.valid = 0;
     E.prm.body_bulk = 0;
+    E.nslots = 0;
   }
 }
 
 // ---- issuer: launch one planned group's bulk copies into a free stage (warp-collective) -------------------
 __device__ __forceinline__ void issue_group(const pulse_motionlib_desc_t& lib, const PlanEntry* plan, Stage& sg,
-                                            unsigned long long* full, int lane, bool need_t, bool do_obs) {
+                                            unsigned long long* full, int lane) {
   unsigned bytes = 0;
-  PlanEntry E;
-  const bool v = lane < kEnvs && plan[lane < kEnvs ? lane : 0].prm.valid != 0;
-  if (lane < kEnvs) {
-    E = plan[lane];
+  const bool mine = lane < kEnvs;
+  bool v = false;
+  int ns = 0, body_bulk = 0;
+  if (mine) {
+    const PlanEntry& E = plan[lane];
     sg.prm[lane] = E.prm;
-    if (v) bytes = (need_t ? 2u : 0u) * kFrameBytes + (do_obs ? 2u : 0u) * kFrameBytes + (E.prm.body_bulk ? kFrameBytes : 0u);
+    v = E.prm.valid != 0;
+    ns = E.nslots;
+    body_bulk = E.prm.body_bulk;
+    if (v) bytes = static_cast<unsigned>(ns + (body_bulk ? 1 : 0)) * kFrameBytes;
   }
-  unsigned total = bytes;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
-  __syncwarp();                                    // prm[] writes ordered before lane 0's release-arrive
+  const unsigned total = __reduce_add_sync(kFull, bytes);  // REDUX also orders the prm[] writes before lane 0's arrive
+  __syncwarp();
   if (lane == 0) mbar_arrive_expect_tx(full, total);
   __syncwarp();                                    // the expectation is posted before any copy can complete
   if (v) {
-    if (need_t) {
-      bulk_g2s(&sg.frames[lane][0 * kFrame], lib.frame_rec + E.rows[0] * kFrame, kFrameBytes, full);
-      bulk_g2s(&sg.frames[lane][1 * kFrame], lib.frame_rec + E.rows[1] * kFrame, kFrameBytes, full);
-    }
-    if (do_obs) {
-      bulk_g2s(&sg.frames[lane][2 * kFrame], lib.frame_rec + E.prm.aux0 * kFrame, kFrameBytes, full);
-      bulk_g2s(&sg.frames[lane][3 * kFrame], lib.frame_rec + E.prm.aux1 * kFrame, kFrameBytes, full);
-    }
-    if (E.prm.body_bulk) bulk_g2s(&sg.body[lane][0], E.body_src, kFrameBytes, full);
+    const PlanEntry& E = plan[lane];
+    float* blk = sg.env[lane];
+#pragma unroll
+    for (int m = 0; m < kSlots; ++m)
+      if (m < ns) bulk_g2s(blk + m * kFrame, lib.frame_rec + E.slot_row[m] * kFrame, kFrameBytes, full);
+    if (body_bulk) bulk_g2s(blk + kSlots * kFrame, E.body_src, kFrameBytes, full);
   }
 }
 
-// raw dof force / velocity operands of the power term for (env slot k of `group`, body lane j)
+// raw dof force / velocity operands of the power term (humanoid_im.py:910-912) for (env slot k of `group`, body j)
 struct PowerOps {
   float f[3], v[3];
 };
@@ -246,16 +289,15 @@ __device__ __forceinline__ PowerOps power_load(const pulse_im_step_args_t& a, lo
     for (int m = 0; m < 3; ++m) {
       const int d = j + kNB * m;
       if (d < PULSE_NUM_DOF) {
-        o.f[m] = fr[d];
-        o.v[m] = dv[d * a.dof_elem_stride];
+        o.f[m] = __ldg(fr + d);
+        o.v[m] = __ldg(dv + d * a.dof_elem_stride);
       }
     }
   }
   return o;
 }
 
-// Persistent, warp-specialised: planner warp -> (plan ring) -> issuer warp -> (data stages) -> consumers.
-__global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motionlib_desc_t lib, const pulse_im_step_args_t a,
+__global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motionlib_desc_t lib, const pulse_im_step_args_t a,
                                                               long long num_envs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
@@ -271,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], kTeam);  // every thread of the consuming team hands the stage back itself
     }
 #pragma unroll
     for (int s = 0; s < kPlanSlots; ++s) {
@@ -284,12 +326,13 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
   const long long my_groups = (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (tid >= kConsumers + 32) {
-    // ================================ planner warp: runs up to kPlanSlots batches ahead ================
+    // ================================ planner warp: runs up to kPlanSlots passes ahead =================
     const int lane = tid - (kConsumers + 32);
     for (long long b = 0; b * kBatch < my_groups; ++b) {
       const int ps = static_cast<int>(b % kPlanSlots);
       if (b >= kPlanSlots) mbar_wait(&sm.plan_empty[ps], ((b / kPlanSlots) - 1) & 1);
-      plan_batch(lib, a, num_envs, ngroups, blockIdx.x + b * kBatch * gridDim.x, gridDim.x, sm.plan[ps], lane, do_reset);
+      plan_batch(lib, a, num_envs, ngroups, blockIdx.x + b * kBatch * gridDim.x, gridDim.x, sm.plan[ps], lane, need_t, do_obs,
+                 do_reset);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.plan_full[ps]);
     }
@@ -304,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
       const int s = static_cast<int>(n % kStages);
       mbar_wait(&sm.plan_full[ps], (b / kPlanSlots) & 1);
       if (n >= kStages) mbar_wait(&sm.empty[s], ((n / kStages) - 1) & 1);  // consumers released this stage
-      issue_group(lib, sm.plan[ps][gb], sm.stage[s], &sm.full[s], lane, need_t, do_obs);
+      issue_group(lib, sm.plan[ps][gb], sm.stage[s], &sm.full[s], lane);
       if (gb == kBatch - 1 || n == my_groups - 1) {
         __syncwarp();                                  // every lane has read its plan entry
         if (lane == 0) mbar_arrive(&sm.plan_empty[ps]);
@@ -313,68 +356,84 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
     return;
   }
 
-  // ================================== consumers: thread = (env slot k, body j) ========================
-  const int k = tid / kNB;
-  const int j = tid - k * kNB;
+  // ================================== consumers: team x (env slot k, body j) ==========================
+  const int team = tid / kTeam;
+  const int ttid = tid - team * kTeam;
+  const int k = ttid / kNB;
+  const int j = ttid - k * kNB;
   const float term_j = do_reset ? a.termination_distances[j] : 0.0f;
+  float(*red)[kRed][kNB + 1] = sm.red[team];
+  unsigned* fallen = sm.fallen[team];
   PowerOps pw_ops = {};
-  if (do_power) pw_ops = power_load(a, num_envs, blockIdx.x, k, j);
-  int it = 0;
-  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
-    const int s = it % kStages;
+  if (do_power && team < my_groups) pw_ops = power_load(a, num_envs, blockIdx.x + team * (long long)gridDim.x, k, j);
+  for (long long n = team; n < my_groups; n += kTeams) {
+    const int s = static_cast<int>(n % kStages);
     Stage& sg = sm.stage[s];
     const float pw = fabsf(pw_ops.f[0] * pw_ops.v[0]) + fabsf(pw_ops.f[1] * pw_ops.v[1]) + fabsf(pw_ops.f[2] * pw_ops.v[2]);
-    // operands of the NEXT group's power term stay in flight (registers) across this group's math
-    if (do_power && g + gridDim.x < ngroups) pw_ops = power_load(a, num_envs, g + gridDim.x, k, j);
-    mbar_wait(&sm.full[s], (it / kStages) & 1);  // frame records + body state have landed, prm[] visible
+    // operands of this team's NEXT group stay in flight (registers) across this group's math
+    if (do_power && n + kTeams < my_groups) pw_ops = power_load(a, num_envs, blockIdx.x + (n + kTeams) * gridDim.x, k, j);
+    mbar_wait(&sm.full[s], (n / kStages) & 1);  // frame records + body state have landed, prm[] visible
 
     const EnvParams P = sg.prm[k];
     const bool valid = P.valid != 0;
+    float* blk = sg.env[k];
     // rigid-body state: shared memory when it came through the bulk path, else straight from global
-    const float* body = P.body_bulk ? sg.body[k] : (valid ? a.body_state + P.env * a.body_env_stride : sg.body[k]);
+    const float* body = (P.body_bulk || !valid) ? blk + kSlots * kFrame : a.body_state + P.env * a.body_env_stride;
     const float* bj = body + j * PULSE_BODY_STATE_W;
     const Vec3 p = {bj[0], bj[1], bj[2]};
     const Quat q = {bj[3], bj[4], bj[5], bj[6]};
     const Vec3 v = {bj[7], bj[8], bj[9]};
     const Vec3 w = {bj[10], bj[11], bj[12]};
-    const Vec3 p_root = {body[0], body[1], body[2]};
-    const Quat q_root = {body[3], body[4], body[5], body[6]};
-    const float* fr = sg.frames[k];
-    if (tid < kEnvs) sm.fallen[tid] = 0u;  // OR-ed after the first consumer_sync, read after the second
+    if (j == 0) {  // the env's root state, needed by every body thread of the env in the obs part
+      float* rt = sm.root[team][k];
+      rt[0] = p.x; rt[1] = p.y; rt[2] = p.z;
+      rt[3] = q.x; rt[4] = q.y; rt[5] = q.z; rt[6] = q.w;
+    }
+    if (ttid < kEnvs) fallen[ttid] = 0u;  // OR-ed after the first team_sync, read after the second
+    const float* direct = (valid && P.direct_row >= 0) ? lib.frame_rec + P.direct_row * kFrame : blk;
 
     // ---- reward + reset partials at t -----------------------------------------------------------------
     RefPose r2;
     bool is_fallen = false;
     if (valid && need_t) {
-      const RefPose r = blend_pose(fr, fr + kFrame, j, P.b_rew, P.gx, P.gy, P.gz);
+      const float* f0 = P.sl[0] < kDirect ? blk + P.sl[0] * kFrame : direct;
+      const float* f1 = P.sl[1] < kDirect ? blk + P.sl[1] * kFrame : direct;
+      const RefPose r = blend_pose(f0, f1, j, P.b_rew, P.gx, P.gy, P.gz);
       if (do_rew) {
         const float th = quat_angle(qmul(r.q, qconj(q)));
-        sm.red[k][0][j] = sq3(r.p - p);
-        sm.red[k][1][j] = th * th;
-        sm.red[k][2][j] = sq3(r.v - v);
-        sm.red[k][3][j] = sq3(r.w - w);
-        sm.red[k][4][j] = pw;
+        red[k][0][j] = sq3(r.p - p);
+        red[k][1][j] = th * th;
+        red[k][2][j] = sq3(r.v - v);
+        red[k][3][j] = sq3(r.w - w);
+        red[k][5][j] = pw;
       }
       if (do_reset) {
         const bool in_mask = (a.reset_body_mask >> j) & 1u;
         const float dist = norm3_rn(__fsub_rn(p.x, r.p.x), __fsub_rn(p.y, r.p.y), __fsub_rn(p.z, r.p.z));
-        sm.red[k][5][j] = in_mask ? dist : 0.0f;
+        red[k][4][j] = in_mask ? dist : 0.0f;
         is_fallen = in_mask && dist > term_j;
       }
     }
     // ---- observation at t + dt: fold the frames into registers --------------------------------------------
-    if (valid && do_obs) r2 = blend_pose(fr + 2 * kFrame, fr + 3 * kFrame, j, P.b_obs, P.gx, P.gy, P.gz);
-    consumer_sync();  // all frame records consumed: their bytes become the obs rows; partials complete
+    if (valid && do_obs) {
+      const float* f0 = P.sl[2] < kDirect ? blk + P.sl[2] * kFrame : direct;
+      const float* f1 = P.sl[3] < kDirect ? blk + P.sl[3] * kFrame : direct;
+      r2 = blend_pose(f0, f1, j, P.b_obs, P.gx, P.gy, P.gz);
+    }
+    team_sync(team);  // the env blocks are consumed: their bytes become the obs rows; partials complete
 
     float* orow = nullptr;
     int ophase = 0;
     if (valid && do_obs) {
+      const float* rt = sm.root[team][k];
+      const Vec3 p_root = {rt[0], rt[1], rt[2]};
+      const Quat q_root = {rt[3], rt[4], rt[5], rt[6]};
       float hs, hc;
       heading_half(q_root, hs, hc);
       const Yaw yr = make_yaw(Quat{0.0f, 0.0f, -hs, hc});
       orow = a.obs_buf + P.env * a.obs_stride;
       ophase = static_cast<int>((reinterpret_cast<uintptr_t>(orow) >> 2) & 3);
-      float* o = sg.frames[k] + ophase;  // global 16-byte boundaries coincide with shared ones
+      float* o = blk + ophase;  // global 16-byte boundaries coincide with shared ones
       // self observation (humanoid.py:1675-1731)
       if (j == 0) o[0] = p_root.z;
       else st3(o + 1 + 3 * (j - 1), yaw_rot(yr, p - p_root));
@@ -404,22 +463,22 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
       }
     }
     // column sums of the partials: thread (kk, c) adds 24 values; fallen flags OR-ed per env
-    if (need_t && tid < kEnvs * kRed) {
-      const int kk = tid / kRed, c = tid - kk * kRed;
+    if (need_t && ttid < kEnvs * kRed) {
+      const int kk = ttid / kRed, c = ttid - kk * kRed;
       float sum = 0.0f;
 #pragma unroll
-      for (int b = 0; b < kNB; ++b) sum += sm.red[kk][c][b];
-      sm.red[kk][c][kNB] = sum;
+      for (int b = 0; b < kNB; ++b) sum += red[kk][c][b];
+      red[kk][c][kNB] = sum;
     }
-    if (is_fallen) atomicOr(&sm.fallen[k], 1u);  // zeroed before the first consumer_sync of this iteration
+    if (is_fallen) atomicOr(&fallen[k], 1u);
     fence_proxy_async();  // generic-proxy writes of the obs rows -> visible to the bulk (async proxy) store
-    consumer_sync();
+    team_sync(team);
 
     // ---- epilogue ---------------------------------------------------------------------------------------------
     if (valid && do_obs) {
       const int head = (4 - ophase) & 3;         // floats before the first 16-byte boundary
       const int nmid = ((kObs - head) / 4) * 4;  // floats in the aligned middle
-      const float* o = sg.frames[k] + ophase;
+      const float* o = blk + ophase;
       if (j == 0) {
         bulk_s2g(orow + head, o + head, static_cast<unsigned>(nmid) * 4u);
         bulk_commit();
@@ -434,15 +493,15 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
         for (int i = j; i < PULSE_SELF_OBS; i += kNB) srow[i] = o[i];
       }
     }
-    if (tid < kEnvs && sg.prm[tid].valid && need_t) {  // lane = env slot: finish reward / reset
-      const EnvParams& Q = sg.prm[tid];
+    if (ttid < kEnvs && sg.prm[ttid].valid && need_t) {  // lane = env slot: finish reward / reset
+      const EnvParams& Q = sg.prm[ttid];
       const long long ee = Q.env;
       const bool pass_time = a.cycle_motion ? (Q.prog >= a.max_episode_length - 1) : (Q.t_rew >= Q.mlen);
       if (do_rew) {
-        const float e_pos = sm.red[tid][0][kNB] * (1.0f / (3.0f * kNB));
-        const float e_rot = sm.red[tid][1][kNB] * (1.0f / kNB);
-        const float e_vel = sm.red[tid][2][kNB] * (1.0f / (3.0f * kNB));
-        const float e_ang = sm.red[tid][3][kNB] * (1.0f / (3.0f * kNB));
+        const float e_pos = red[ttid][0][kNB] * (1.0f / (3.0f * kNB));
+        const float e_rot = red[ttid][1][kNB] * (1.0f / kNB);
+        const float e_vel = red[ttid][2][kNB] * (1.0f / (3.0f * kNB));
+        const float e_ang = red[ttid][3][kNB] * (1.0f / (3.0f * kNB));
         const float r_pos = expf(-a.k_pos * e_pos);
         const float r_rot = expf(-a.k_rot * e_rot);
         const float r_vel = expf(-a.k_vel * e_vel);
@@ -450,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
         float rew = a.w_pos * r_pos + a.w_rot * r_rot + a.w_vel * r_vel + a.w_ang_vel * r_ang;
         float p_rew = 0.0f;
         if (do_power) {
-          p_rew = (Q.prog <= 3) ? 0.0f : -a.power_coefficient * sm.red[tid][4][kNB];
+          p_rew = (Q.prog <= 3) ? 0.0f : -a.power_coefficient * red[ttid][5][kNB];
           rew += p_rew;
         }
         a.rew_buf[ee] = rew;
@@ -461,16 +520,16 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
         }
       }
       if (do_reset) {
-        bool fallen;
+        bool fell;
         if (a.use_mean_reset) {
           // mean over the reset bodies vs the first reset body's distance (humanoid_im.py:1606)
           const unsigned m = a.reset_body_mask & 0xffffffu;
-          fallen = (sm.red[tid][5][kNB] / static_cast<float>(__popc(m))) > a.termination_distances[__ffs(m) - 1];
+          fell = (red[ttid][4][kNB] / static_cast<float>(__popc(m))) > a.termination_distances[__ffs(m) - 1];
         } else {
-          fallen = sm.fallen[tid] != 0u;
+          fell = fallen[ttid] != 0u;
         }
-        fallen = fallen && (Q.prog > 1) && a.enable_early_termination;
-        long long terminated = fallen ? 1 : 0;
+        fell = fell && (Q.prog > 1) && a.enable_early_termination;
+        long long terminated = fell ? 1 : 0;
         long long reset = pass_time ? 1 : terminated;
         if (!pass_time && Q.cyc > 0) {  // recovering envs: humanoid_im.py:1188-1190
           reset = 0;
@@ -482,8 +541,10 @@ __global__ void __launch_bounds__(kThreads, 2) im_step_kernel(const pulse_motion
       if (a.pass_time != nullptr) a.pass_time[ee] = (Q.t_rew >= Q.mlen) ? 1 : 0;
     }
     if (valid && do_obs && j == 0) bulk_wait_read();  // the stage's bytes are free once the store has read them
-    consumer_sync();                                   // also orders this iteration's red[] / fallen[] reads
-    if (tid == 0) mbar_arrive(&sm.empty[s]);           // hand the stage back to the producer
+    // No third team barrier: each thread releases the stage when IT is done with it.  red[] columns 0..23,
+    // fallen[] and root[] are next written only after this thread passed the second team_sync above, and the
+    // column sums / flags are next overwritten only after the next group's first team_sync.
+    mbar_arrive(&sm.empty[s]);
   }
 }
 
@@ -534,7 +595,8 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
     PULSE_CUDA_OK(cudaGetDevice(&dev));
     PULSE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PULSE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, im_step_kernel, kThreads, smem));
-    max_ctas = sms * (per_sm > 0 ? per_sm : 1);  // persistent: one resident wave
+    PULSE_REQUIRE(per_sm >= 1, "pulse_im_step: kernel does not fit on this device (smem %zu B)", smem);
+    max_ctas = sms * per_sm;  // persistent: one resident wave
   }
   const long long ngroups = (num_envs + kEnvs - 1) / kEnvs;
   const unsigned grid = static_cast<unsigned>(ngroups < max_ctas ? ngroups : max_ctas);
