@@ -201,6 +201,99 @@ int pulse_gae(const pulse_gae_args_t* args, int32_t horizon, int64_t num_envs, v
 /* advantages <- (adv - mean) / (std + 1e-8) with unbiased std from adv_sum (common_agent.py:596-597) */
 int pulse_normalize_advantages(float* advantages, const double* adv_sum, int64_t count, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers on the tensor cores: D[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T), bf16 operands (both
+ * K-major: row-major with the reduction dimension contiguous), fp32 accumulation in TMEM (tcgen05).
+ * Replaces the nn.Linear + activation stacks of the policy / value / discriminator / VAE networks
+ * (phc/learning/network_builder.py:105-124, amp_network_builder.py:58-249, amp_network_z_builder.py:341-467)
+ * and their autograd backward: forward (A=X, B=W), dgrad (A=dY, B=W^T), wgrad (A=dY^T, B=X^T).
+ * ---------------------------------------------------------------------------------------------- */
+typedef uint16_t pulse_bf16_t;  /* raw bfloat16 bits */
+#define PULSE_ACT_NONE 0
+#define PULSE_ACT_RELU 1
+#define PULSE_ACT_SILU 2
+
+typedef struct {
+  const float* bias;         /* [N] added before the activation, or NULL */
+  int32_t act;               /* PULSE_ACT_* applied to (alpha*acc + bias) */
+  int32_t gate_mode;         /* PULSE_ACT_RELU / PULSE_ACT_SILU: multiply by act'(gate) (backward through the activation) */
+  const pulse_bf16_t* gate;  /* [M, ldg] saved tensor: ReLU -> the layer OUTPUT, SiLU -> the PRE-activation; NULL = off */
+  int64_t ldg;
+  float alpha;
+  pulse_bf16_t* out;         /* [M, ldo] bf16 row-major, or NULL */
+  int64_t ldo;
+  pulse_bf16_t* out_t;       /* [N, ldot] bf16 TRANSPOSED copy (operand of the next wgrad), or NULL */
+  int64_t ldot;
+  float* out_f32;            /* [M, ldf] fp32 (heads, weight-gradient slabs), or NULL */
+  int64_t ldf;
+  int64_t split_stride;      /* floats between split-K slabs of out_f32 */
+  pulse_bf16_t* preact;      /* [M, ldp] bf16 pre-activation (saved for SiLU backward), or NULL */
+  int64_t ldp;
+} pulse_gemm_epilogue_t;
+
+/* lda / ldb in elements, multiples of 8, >= K; A and B 16-byte aligned.  split_k > 1: fp32 slabs only
+ * (slab z at out_f32 + z*split_stride); pulse_gemm_num_splits gives the number of slabs actually written. */
+int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                       const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream);
+int pulse_gemm_num_splits(int64_t k, int32_t split_k);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / reduction kernels around the GEMMs.
+ * ---------------------------------------------------------------------------------------------- */
+/* RunningMeanStd.forward, eval path (phc/utils/running_mean_std.py:69-95): y = clamp((x-mean)*rstd, -5, 5),
+ * written as bf16 [rows, ld_out] (columns >= cols zero-filled up to ld_out) and optionally transposed
+ * bf16 [ld_out, ld_t] (operand of the first layer's wgrad).  mean / rstd: fp32 [cols] (rstd = 1/sqrt(var+eps),
+ * prepared by the caller from the fp64 statistics); NULL mean = plain cast. */
+int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
+                            pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, void* stream);
+
+/* Batch moments for RunningMeanStd's training-mode update (:96-107): per-column sum and sum of squares of
+ * fp32 x [rows, cols] accumulated in fp64 into sums[2*cols] (caller zeroes). */
+int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, double* sums, void* stream);
+
+/* Gaussian policy head (rl_games ModelA2CContinuousLogStd, fixed sigma: im.yaml:21-25):
+ * actions = mu + exp(logstd)*eps;  neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*A*log(2*pi) + sum(logstd). */
+int pulse_gaussian_sample(const float* mu, int64_t ld_mu, const float* eps, const float* logstd, int64_t rows, int32_t num_actions,
+                          float* actions, float* neglogp, void* stream);
+
+/* PPO actor / critic / bound losses and their gradients w.r.t. the network outputs, one pass
+ * (common_agent.py:512-520, :564-587; amp_agent.py:691-710; torch_ext.policy_kl):
+ *   a = max(-A r, -A clip(r, 1-e, 1+e)), r = exp(old_neglogp - neglogp);  c = (ret - v)^2;
+ *   b = sum(clamp_min(mu-1,0)^2 + clamp_max(mu+1,0)^2);  loss = mean(a) + critic_coef*mean(c) + bounds_coef*mean(b).
+ * Outputs: dmu bf16 [rows, ld_dmu] (+ transposed [A_pad, ld_t]), dvalue bf16 [rows, ld_dv] (+ transposed),
+ * stats[0..5] fp64 accumulators: sum a, sum c, sum b, sum kl, clipped count, sum neglogp (caller zeroes). */
+typedef struct {
+  const float* mu; int64_t ld_mu;       /* [rows, A] network output */
+  const float* value; int64_t ld_value; /* [rows, 1] */
+  const float* actions;                 /* [rows, A] contiguous */
+  const float* old_neglogp;             /* [rows] */
+  const float* advantages;              /* [rows] */
+  const float* returns;                 /* [rows] (already value-normalised) */
+  const float* old_mu;                  /* [rows, A] contiguous, for the KL statistic; may be NULL */
+  const float* logstd;                  /* [A] */
+  int32_t num_actions;
+  float e_clip, critic_coef, bounds_coef;
+  pulse_bf16_t* dmu; int64_t ld_dmu; pulse_bf16_t* dmu_t; int64_t ld_dmu_t;
+  pulse_bf16_t* dvalue; int64_t ld_dv; pulse_bf16_t* dvalue_t; int64_t ld_dv_t;
+  double* stats;
+} pulse_ppo_loss_args_t;
+int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, void* stream);
+
+/* out[c] (+)= sum over rows of bf16 x[rows, ldx] (bias gradients). */
+int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);
+/* dst[i] = sum_s slabs[s*slab_stride + i]  (split-K weight-gradient slabs -> flat gradient buffer) */
+int pulse_reduce_slabs(const float* slabs, int64_t slab_stride, int32_t num_slabs, int64_t count, float* dst, void* stream);
+/* sumsq[0] += sum(x^2) in fp64 (global gradient norm; caller zeroes) */
+int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream);
+/* clip_grad_norm_(max_norm) + Adam step over one flat parameter buffer (amp_agent.py:725-750; torch.optim.Adam
+ * defaults beta 0.9/0.999): scale = min(1, max_norm/(sqrt(sumsq)+1e-6)) read on the device, no host sync. */
+int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sumsq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+/* refresh the bf16 operand copies of one weight matrix W fp32 [n, k] (contiguous):
+ *   w_bf16 [n, ld_k] (K-major, forward / wgrad-free) and wt_bf16 [k, ld_n] (transposed, dgrad operand); pads zeroed. */
+int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,
+                              int64_t ld_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,15 @@ class GaeArgs(C.Structure):
     ]
 
 
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p), ("act", C.c_int32), ("gate_mode", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
+        ("alpha", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int64), ("out_t", C.c_void_p), ("ldot", C.c_int64),
+        ("out_f32", C.c_void_p), ("ldf", C.c_int64), ("split_stride", C.c_int64), ("preact", C.c_void_p), ("ldp", C.c_int64),
+    ]
+
+
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
 
 # name -> (restype, argtypes); mirrors include/pulse_b200.h one to one
@@ -85,6 +94,9 @@ SIGNATURES = {
     "pulse_amp_obs": (C.c_int, [C.POINTER(AmpObsArgs), C.c_int64, C.c_void_p]),
     "pulse_gae": (C.c_int, [C.POINTER(GaeArgs), C.c_int32, C.c_int64, C.c_void_p]),
     "pulse_normalize_advantages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                     C.POINTER(GemmEpilogue), C.c_int32, C.c_void_p]),
+    "pulse_gemm_num_splits": (C.c_int, [C.c_int64, C.c_int32]),
 }
 
 _lib = None

@@ -1,0 +1,342 @@
+// bf16 NT GEMM on the 5th-generation tensor cores (sm_100a): D[M,N] = epilogue(A[M,K] . B[N,K]^T).
+//
+// This one kernel carries every dense contraction of the policy / value / discriminator / VAE MLPs
+// (network_builder.py:105-124, amp_network_builder.py:58-249, amp_network_z_builder.py:341-467):
+//   forward   Y  = act(X W^T + b)            A = X  [M,K],  B = W   [N,K]
+//   dgrad     dX = (dY W) * act'(.)          A = dY [M,N],  B = W^T [K,N]   (transposed bf16 copy kept by Adam)
+//   wgrad     dW = dY^T X                    A = dY^T [N,M], B = X^T [K,M]  (transposed copies written by epilogues)
+// so both operands are always K-major and one TMA / UMMA configuration serves all three.
+//
+// Structure (one 128x128 output tile per CTA, 2 CTAs co-resident per SM so one tile's epilogue
+// overlaps the other's main loop):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 bf16 boxes (128B swizzle) into a
+//               3-stage shared-memory ring, completion on "full" mbarriers;
+//   warp 1      allocates 128 TMEM columns, then one elected lane issues tcgen05.mma (M128 N128 K16,
+//               fp32 accumulate in TMEM) four times per stage and tcgen05.commit's the stage back to the
+//               producer ("empty") and, after the last k-block, the accumulator to the epilogue;
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / activation / activation-
+//               derivative gating -> bf16 row-major, bf16 transposed and/or fp32 outputs.
+// Split-K (blockIdx.z) writes fp32 partial slabs for the weight gradients.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "pulse_common.cuh"
+
+namespace pulse {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int kStagesG = 3;
+constexpr int kGemmThreads = 192;
+constexpr unsigned kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr unsigned kTmemCols = 128;
+
+struct __align__(1024) GemmSmem {
+  unsigned char a[kStagesG][kStageBytesA];
+  unsigned char b[kStagesG][kStageBytesB];
+  unsigned long long full[kStagesG];
+  unsigned long long empty[kStagesG];
+  unsigned long long tmem_full;
+  unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned s_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void g_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool g_mbar_try(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(s_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void g_mbar_wait(unsigned long long* bar, unsigned parity) {
+  for (int spin = 0; spin < (1 << 26); ++spin)
+    if (g_mbar_try(bar, parity)) return;
+  __trap();  // a protocol bug must surface as a launch error, never as a hung GPU
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                   s_u32(smem_dst)),
+               "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024 B between 8-row groups | version 1 [46,48) | SWIZZLE_128B (2) [61,64)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= static_cast<unsigned long long>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<unsigned long long>(1u) << 16;
+  d |= static_cast<unsigned long long>(1024u >> 4) << 32;
+  d |= static_cast<unsigned long long>(1u) << 46;
+  d |= static_cast<unsigned long long>(2u) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+constexpr unsigned kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<unsigned>(BN >> 3) << 17) |
+                                (static_cast<unsigned>(BM >> 4) << 24);
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(kInstrDesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == PULSE_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == PULSE_ACT_SILU) return x / (1.0f + __expf(-x));
+  return x;
+}
+__device__ __forceinline__ float act_grad(float g, int mode) {
+  // g: saved tensor -- ReLU: the layer's OUTPUT (>0 <=> active); SiLU: the layer's PRE-activation z
+  if (mode == PULSE_ACT_RELU) return g > 0.0f ? 1.0f : 0.0f;
+  if (mode == PULSE_ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-g));
+    return s * (1.0f + g * (1.0f - s));
+  }
+  return 1.0f;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                      const __grid_constant__ CUtensorMap map_b,
+                                                                      const pulse_gemm_epilogue_t ep, int M, int N, int K,
+                                                                      int kb_per_split) {
+  extern __shared__ unsigned char gsm_raw[];
+  // the 128-byte swizzle atoms need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
+  GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb_total = (K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, num_kb_total - kb0);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStagesG; ++s) {
+      g_mbar_init(&sm.full[s], 1);
+      g_mbar_init(&sm.empty[s], 1);
+    }
+    g_mbar_init(&sm.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp deallocates
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const unsigned tmem_d = sm.tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer ======================================================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStagesG;
+        g_mbar_wait(&sm.empty[s], ((kb / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
+        g_mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
+        tma_load_2d(sm.a[s], &map_a, (kb0 + kb) * BK, m0, &sm.full[s]);
+        tma_load_2d(sm.b[s], &map_b, (kb0 + kb) * BK, n0, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ========================================================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStagesG;
+        g_mbar_wait(&sm.full[s], (kb / kStagesG) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&sm.empty[s]);  // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+      }
+      umma_commit(&sm.tmem_full);    // accumulator complete
+    }
+  } else {
+    // ================================ epilogue warps (TMEM lane quarter = warp % 4) =======================
+    g_mbar_wait(&sm.tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < M;
+    float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(blockIdx.z) * ep.split_stride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      unsigned r[32];
+      tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
+      const int col0 = n0 + c * 32;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = __uint_as_float(r[i]) * ep.alpha;
+        const int col = col0 + i;
+        if (ep.bias != nullptr && col < N) x += __ldg(ep.bias + col);
+        v[i] = x;
+      }
+      if (ep.preact != nullptr && row_ok) {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+      }
+      if (ep.act != PULSE_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ep.act);
+      }
+      if (ep.gate != nullptr && row_ok) {
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
+      }
+      if (outf != nullptr && row_ok) {
+        float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
+        if (col0 + 32 <= N && (ep.ldf & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) p[i] = v[i];
+        }
+      }
+      if (ep.out != nullptr && row_ok) {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+        if (col0 + 32 <= N && (ep.ldo & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<unsigned*>(&h0);
+            u.y = *reinterpret_cast<unsigned*>(&h1);
+            u.z = *reinterpret_cast<unsigned*>(&h2);
+            u.w = *reinterpret_cast<unsigned*>(&h3);
+            *reinterpret_cast<uint4*>(p + i) = u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+        }
+      }
+      if (ep.out_t != nullptr && row_ok) {
+        // transposed copy: lanes hold consecutive rows -> consecutive addresses of out_t[col][row]
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N)
+            reinterpret_cast<__nv_bfloat16*>(ep.out_t)[static_cast<long long>(col0 + i) * ep.ldot + row] = __float2bfloat16(v[i]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows x cols bf16 matrix, row stride ld elements, box 128 rows x 64 cols, 128B swizzle, OOB reads return 0
+bool make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+}  // namespace pulse
+
+extern "C" int pulse_gemm_num_splits(int64_t k, int32_t split_k) {
+  const int num_kb = static_cast<int>((k + 63) / 64);
+  int splits = split_k < 1 ? 1 : (split_k > num_kb ? num_kb : split_k);
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  return (num_kb + kb_per_split - 1) / kb_per_split;  // every slab gets at least one k-block
+}
+
+extern "C" int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                                  const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream) {
+  using namespace pulse;
+  PULSE_REQUIRE(a && b && ep, "pulse_gemm_bf16_nt: null argument");
+  PULSE_REQUIRE(m > 0 && n > 0 && k > 0, "pulse_gemm_bf16_nt: empty problem %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
+  PULSE_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "pulse_gemm_bf16_nt: dimension too large");
+  PULSE_REQUIRE(lda >= k && ldb >= k && (lda % 8) == 0 && (ldb % 8) == 0, "pulse_gemm_bf16_nt: leading dimensions must be >= K and multiples of 8 (16-byte rows), got %lld %lld", (long long)lda, (long long)ldb);
+  PULSE_REQUIRE(aligned16(a) && aligned16(b), "pulse_gemm_bf16_nt: operands must be 16-byte aligned");
+  PULSE_REQUIRE(ep->out || ep->out_t || ep->out_f32, "pulse_gemm_bf16_nt: no output requested");
+  PULSE_REQUIRE(split_k >= 1, "pulse_gemm_bf16_nt: split_k must be >= 1");
+  PULSE_REQUIRE(split_k == 1 || (ep->out_f32 && !ep->out && !ep->out_t && !ep->bias && ep->act == PULSE_ACT_NONE && !ep->gate && !ep->preact),
+                "pulse_gemm_bf16_nt: split-K only supports plain fp32 partial slabs");
+  PULSE_REQUIRE(ep->gate == nullptr || ep->gate_mode == PULSE_ACT_RELU || ep->gate_mode == PULSE_ACT_SILU, "pulse_gemm_bf16_nt: bad gate_mode");
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, a, m, k, lda) || !make_map(&map_b, b, n, k, ldb)) {
+    set_error("pulse_gemm_bf16_nt: cuTensorMapEncodeTiled failed (driver entry point missing or bad strides)");
+    return PULSE_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  const size_t smem = sizeof(GemmSmem) + 1024;  // slack so the kernel can align the ring to 1024 B
+  if (!attr_set) {
+    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int num_kb = static_cast<int>((k + BK - 1) / BK);
+  const int splits = pulse_gemm_num_splits(k, split_k);
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  dim3 grid(static_cast<unsigned>((n + BN - 1) / BN), static_cast<unsigned>((m + BM - 1) / BM), static_cast<unsigned>(splits));
+  gemm_bf16_nt_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, *ep, (int)m, (int)n, (int)k,
+                                                                                      kb_per_split);
+  PULSE_LAUNCH_OK("gemm_bf16_nt_kernel");
+  return PULSE_OK;
+}

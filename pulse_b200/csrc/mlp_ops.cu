@@ -1,0 +1,364 @@
+// Element-wise and reduction kernels around the tcgen05 GEMMs: observation normalisation, Gaussian
+// policy head, PPO losses + output gradients, bias-gradient column sums, split-K slab reduction,
+// gradient-norm clip + Adam, bf16 operand refresh.  All HBM-bound streaming kernels: 16-byte accesses
+// where the layout allows, grid-stride loops sized to a multiple of the SM count.
+#include <cuda_bf16.h>
+
+#include "pulse_common.cuh"
+
+namespace pulse {
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---- RunningMeanStd normalise + clamp -> bf16 (and transposed bf16) -------------------------------------------
+// One CTA handles a 32-row x 32-col tile so the transposed copy can go through a padded shared tile.
+__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        __nv_bfloat16* __restrict__ out, long long ld_out,
+                                                        __nv_bfloat16* __restrict__ out_t, long long ld_t) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const long long col_tiles = (ld_out + 31) / 32;
+  const long long row_tiles = (rows + 31) / 32;
+  for (long long t = blockIdx.x; t < col_tiles * row_tiles; t += gridDim.x) {
+    const long long rt = t / col_tiles, ct = t - rt * col_tiles;
+    const long long c = ct * 32 + tx;
+    float m = 0.0f, rs = 1.0f;
+    if (mean != nullptr && c < cols) {
+      m = mean[c];
+      rs = rstd[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = rt * 32 + ty + 8 * i;
+      float y = 0.0f;
+      if (r < rows && c < cols) {
+        y = (x[r * ldx + c] - m) * rs;
+        if (mean != nullptr) y = fminf(fmaxf(y, -5.0f), 5.0f);
+      }
+      if (r < rows && c < ld_out && out != nullptr) out[r * ld_out + c] = __float2bfloat16(y);
+      tile[ty + 8 * i][tx] = y;
+    }
+    if (out_t != nullptr) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long cc = ct * 32 + ty + 8 * i;  // transposed: row index of out_t
+        const long long rr = rt * 32 + tx;
+        if (cc < ld_out && rr < rows) out_t[cc * ld_t + rr] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- per-column sum / sum of squares in fp64 --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) column_moments_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols,
+                                                             double* __restrict__ sums) {
+  // blockIdx.y: row chunk; each thread owns columns c = blockIdx.x*256 + threadIdx.x (coalesced across the warp)
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  double s = 0.0, q = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const double v = x[r * ldx + c];
+    s += v;
+    q += v * v;
+  }
+  atomicAdd(sums + c, s);
+  atomicAdd(sums + cols + c, q);
+}
+
+// ---- Gaussian head ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gaussian_sample_kernel(const float* __restrict__ mu, long long ld_mu, const float* __restrict__ eps,
+                                                              const float* __restrict__ logstd, long long rows, int A,
+                                                              float* __restrict__ actions, float* __restrict__ neglogp) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc = 0.0f, ls = 0.0f;
+  for (int k = lane; k < A; k += 32) {
+    const float l = logstd[k];
+    const float sg = expf(l);
+    const float e = eps[row * A + k];
+    const float m = mu[row * ld_mu + k];
+    const float a = m + sg * e;
+    actions[row * A + k] = a;
+    const float z = (a - m) / sg;
+    acc += z * z;
+    ls += l;
+  }
+  acc = warp_sum_f(acc);
+  ls = warp_sum_f(ls);
+  if (lane == 0) neglogp[row] = 0.5f * acc + 0.5f * 1.8378770664093453f * A + ls;  // log(2*pi)
+}
+
+// ---- PPO losses + gradients w.r.t. mu / value ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ppo_loss_kernel(const pulse_ppo_loss_args_t a, long long rows) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  __shared__ double s_stats[4][6];
+  const int warp = threadIdx.x >> 5;
+  double st[6] = {0, 0, 0, 0, 0, 0};
+  if (row < rows) {
+    const int A = a.num_actions;
+    const float inv_rows = 1.0f / static_cast<float>(rows);
+    // pass 1: neglogp, bound loss, kl
+    float z2 = 0.0f, ls = 0.0f, bl = 0.0f, kl = 0.0f;
+    for (int k = lane; k < A; k += 32) {
+      const float l = a.logstd[k];
+      const float sg = expf(l);
+      const float m = a.mu[row * a.ld_mu + k];
+      const float z = (a.actions[row * A + k] - m) / sg;
+      z2 += z * z;
+      ls += l;
+      const float hi = fmaxf(m - 1.0f, 0.0f), lo = fminf(m + 1.0f, 0.0f);
+      bl += hi * hi + lo * lo;
+      if (a.old_mu != nullptr) {
+        // policy_kl(p0 = current, p1 = old) with equal sigma: log(s1/s0 + 1e-5) + (s0^2 + (mu1-mu0)^2)/(2(s1^2+1e-5)) - 0.5
+        const float d = a.old_mu[row * A + k] - m;
+        kl += logf(1.0f + 1e-5f) + (sg * sg + d * d) / (2.0f * (sg * sg + 1e-5f)) - 0.5f;
+      }
+    }
+    z2 = warp_sum_f(z2);
+    ls = warp_sum_f(ls);
+    bl = warp_sum_f(bl);
+    kl = warp_sum_f(kl);
+    const float nlp = 0.5f * z2 + 0.5f * 1.8378770664093453f * A + ls;
+    const float adv = a.advantages[row];
+    const float ratio = expf(a.old_neglogp[row] - nlp);
+    const float rc = fminf(fmaxf(ratio, 1.0f - a.e_clip), 1.0f + a.e_clip);
+    const float s1 = -adv * ratio, s2 = -adv * rc;
+    const float a_loss = fmaxf(s1, s2);
+    // d a_loss / d nlp: the unclipped branch is active when s1 >= s2 (torch.max sends the gradient there on ties);
+    // the clipped branch has zero gradient unless ratio is inside the clip range, where both coincide.
+    const float da_dnlp = (s1 >= s2) ? adv * ratio : 0.0f;
+    const float v = a.value[row * a.ld_value];
+    const float ret = a.returns[row];
+    const float c_loss = (ret - v) * (ret - v);
+    // pass 2: gradients
+    for (int k = lane; k < A; k += 32) {
+      const float l = a.logstd[k];
+      const float sg = expf(l);
+      const float m = a.mu[row * a.ld_mu + k];
+      const float dnlp_dmu = -(a.actions[row * A + k] - m) / (sg * sg);
+      const float hi = fmaxf(m - 1.0f, 0.0f), lo = fminf(m + 1.0f, 0.0f);
+      const float g = (da_dnlp * dnlp_dmu + a.bounds_coef * 2.0f * (hi + lo)) * inv_rows;
+      const __nv_bfloat16 gb = __float2bfloat16(g);
+      if (a.dmu != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu)[row * a.ld_dmu + k] = gb;
+      if (a.dmu_t != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu_t)[k * a.ld_dmu_t + row] = gb;
+    }
+    if (lane == 0) {
+      const __nv_bfloat16 gv = __float2bfloat16(-2.0f * (ret - v) * a.critic_coef * inv_rows);
+      if (a.dvalue != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dvalue)[row * a.ld_dv] = gv;
+      if (a.dvalue_t != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dvalue_t)[row] = gv;
+      st[0] = a_loss;
+      st[1] = c_loss;
+      st[2] = bl;
+      st[3] = kl;
+      st[4] = fabsf(ratio - 1.0f) > a.e_clip ? 1.0 : 0.0;
+      st[5] = nlp;
+    }
+  }
+  if (lane == 0)
+    for (int i = 0; i < 6; ++i) s_stats[warp][i] = st[i];
+  __syncthreads();
+  if (threadIdx.x < 6 && a.stats != nullptr) {
+    const double t = s_stats[0][threadIdx.x] + s_stats[1][threadIdx.x] + s_stats[2][threadIdx.x] + s_stats[3][threadIdx.x];
+    atomicAdd(a.stats + threadIdx.x, t);
+  }
+}
+
+// ---- column sums of a bf16 matrix (bias gradients) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) column_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows,
+                                                              long long cols, float* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  float s = 0.0f;
+  for (long long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ldx + c]);
+  atomicAdd(out + c, s);
+}
+
+__global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restrict__ slabs, long long slab_stride, int num_slabs,
+                                                           long long count, float* __restrict__ dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < num_slabs; ++k) s += slabs[k * slab_stride + i];
+    dst[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_squares_kernel(const float* __restrict__ x, long long count, double* __restrict__ out) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    s += v * v;
+  }
+  s = warp_sum_d(s);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long count, const double* __restrict__ sumsq, float max_norm,
+                                                   float lr, float b1, float b2, float eps, float bc1, float bc2) {
+  float scale = 1.0f;
+  if (sumsq != nullptr && max_norm > 0.0f) {
+    const float norm = static_cast<float>(sqrt(*sumsq));
+    scale = fminf(1.0f, max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * scale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256) refresh_weight_kernel(const float* __restrict__ w, long long n, long long k,
+                                                             __nv_bfloat16* __restrict__ wb, long long ld_k,
+                                                             __nv_bfloat16* __restrict__ wt, long long ld_n) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long kt = (max(k, ld_k) + 31) / 32, nt = (max(n, ld_n) + 31) / 32;
+  for (long long t = blockIdx.x; t < kt * nt; t += gridDim.x) {
+    const long long rn = t / kt, ck = t - rn * kt;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = rn * 32 + ty + 8 * i, c = ck * 32 + tx;
+      const float val = (r < n && c < k) ? w[r * k + c] : 0.0f;
+      if (wb != nullptr && r < n && c < ld_k) wb[r * ld_k + c] = __float2bfloat16(val);
+      tile[ty + 8 * i][tx] = val;
+    }
+    __syncthreads();
+    if (wt != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long c = ck * 32 + ty + 8 * i, r = rn * 32 + tx;  // wt[c][r]
+        if (c < k && r < ld_n) wt[c * ld_n + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+inline unsigned grid_for(long long work_items, int per_block, int waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(kSMs) * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace
+}  // namespace pulse
+
+using namespace pulse;
+
+extern "C" int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
+                                       pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, void* stream) {
+  PULSE_REQUIRE(x && (out || out_t), "pulse_normalize_to_bf16: null buffer");
+  PULSE_REQUIRE(rows > 0 && cols > 0 && ld_out >= cols && ldx >= cols, "pulse_normalize_to_bf16: bad shape");
+  PULSE_REQUIRE((mean == nullptr) == (rstd == nullptr), "pulse_normalize_to_bf16: mean and rstd go together");
+  PULSE_REQUIRE(out_t == nullptr || ld_t >= rows, "pulse_normalize_to_bf16: ld_t < rows");
+  const long long tiles = ((ld_out + 31) / 32) * ((rows + 31) / 32);
+  normalize_kernel<<<grid_for(tiles, 1, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, reinterpret_cast<__nv_bfloat16*>(out_t), ld_t);
+  PULSE_LAUNCH_OK("normalize_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, double* sums, void* stream) {
+  PULSE_REQUIRE(x && sums && rows > 0 && cols > 0, "pulse_column_moments: bad argument");
+  dim3 grid(static_cast<unsigned>((cols + 255) / 256), static_cast<unsigned>(rows >= 4096 ? 128 : 1));
+  column_moments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, rows, cols, sums);
+  PULSE_LAUNCH_OK("column_moments_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_gaussian_sample(const float* mu, int64_t ld_mu, const float* eps, const float* logstd, int64_t rows,
+                                     int32_t num_actions, float* actions, float* neglogp, void* stream) {
+  PULSE_REQUIRE(mu && eps && logstd && actions && neglogp && rows > 0 && num_actions > 0, "pulse_gaussian_sample: bad argument");
+  gaussian_sample_kernel<<<static_cast<unsigned>((rows * 32 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      mu, ld_mu, eps, logstd, rows, num_actions, actions, neglogp);
+  PULSE_LAUNCH_OK("gaussian_sample_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, void* stream) {
+  PULSE_REQUIRE(args != nullptr && rows > 0, "pulse_ppo_loss: bad argument");
+  const pulse_ppo_loss_args_t& a = *args;
+  PULSE_REQUIRE(a.mu && a.value && a.actions && a.old_neglogp && a.advantages && a.returns && a.logstd, "pulse_ppo_loss: null input");
+  PULSE_REQUIRE(a.num_actions > 0, "pulse_ppo_loss: num_actions");
+  ppo_loss_kernel<<<static_cast<unsigned>((rows * 32 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  PULSE_LAUNCH_OK("ppo_loss_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream) {
+  PULSE_REQUIRE(x && out && rows > 0 && cols > 0, "pulse_column_sum_bf16: bad argument");
+  dim3 grid(static_cast<unsigned>((cols + 255) / 256), static_cast<unsigned>(rows >= 4096 ? 64 : 1));
+  column_sum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, cols, out);
+  PULSE_LAUNCH_OK("column_sum_bf16_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_reduce_slabs(const float* slabs, int64_t slab_stride, int32_t num_slabs, int64_t count, float* dst, void* stream) {
+  PULSE_REQUIRE(slabs && dst && num_slabs >= 1 && count > 0, "pulse_reduce_slabs: bad argument");
+  reduce_slabs_kernel<<<grid_for(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(slabs, slab_stride, num_slabs, count, dst);
+  PULSE_LAUNCH_OK("reduce_slabs_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream) {
+  PULSE_REQUIRE(x && sumsq && count > 0, "pulse_sum_squares: bad argument");
+  sum_squares_kernel<<<grid_for(count, 256 * 8, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, count, sumsq);
+  PULSE_LAUNCH_OK("sum_squares_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                               const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
+                               void* stream) {
+  PULSE_REQUIRE(params && grads && exp_avg && exp_avg_sq && count > 0 && step >= 1, "pulse_adam_step: bad argument");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adam_kernel<<<grid_for(count, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, count, grad_sumsq,
+                                                                                       max_norm, lr, beta1, beta2, eps, bc1, bc2);
+  PULSE_LAUNCH_OK("adam_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,
+                                         int64_t ld_n, void* stream) {
+  PULSE_REQUIRE(w && (w_bf16 || wt_bf16) && n > 0 && k > 0, "pulse_refresh_weight_bf16: bad argument");
+  PULSE_REQUIRE((!w_bf16 || ld_k >= k) && (!wt_bf16 || ld_n >= n), "pulse_refresh_weight_bf16: leading dimension too small");
+  const long long tiles = ((std::max<long long>(k, ld_k) + 31) / 32) * ((std::max<long long>(n, ld_n) + 31) / 32);
+  refresh_weight_kernel<<<grid_for(tiles, 1, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, n, k, reinterpret_cast<__nv_bfloat16*>(w_bf16), ld_k, reinterpret_cast<__nv_bfloat16*>(wt_bf16), ld_n);
+  PULSE_LAUNCH_OK("refresh_weight_kernel");
+  return PULSE_OK;
+}

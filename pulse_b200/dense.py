@@ -1,0 +1,73 @@
+"""Dense layers on the B200 tensor cores: thin host wrapper over `pulse_gemm_bf16_nt` (tcgen05 / TMEM / TMA).
+
+`gemm_nt(a, b)` computes a @ b.T for bf16 row-major a [M,K], b [N,K] with fp32 accumulation and a fused
+epilogue (bias, ReLU / SiLU, activation-derivative gating, transposed copy, fp32 output, split-K slabs).
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ACT = {"none": _lib.ACT_NONE, None: _lib.ACT_NONE, "relu": _lib.ACT_RELU, "silu": _lib.ACT_SILU}
+
+
+def _check_bf16(t, name):
+    if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.PulseError(f"{name} must be a 2-D bf16 tensor with contiguous rows, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+
+
+def num_splits(k: int, split_k: int) -> int:
+    return int(_lib.load().pulse_gemm_num_splits(k, split_k))
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act=None, gate: Optional[torch.Tensor] = None,
+            gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None, out_t: Optional[torch.Tensor] = None,
+            out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None, split_k: int = 1) -> None:
+    lib = _lib.load()
+    _check_bf16(a, "a")
+    _check_bf16(b, "b")
+    M, K = a.shape
+    N, Kb = b.shape
+    if K != Kb:
+        raise _lib.PulseError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
+    ep = _lib.GemmEpilogue()
+    ep.alpha = alpha
+    ep.act = ACT[act] if not isinstance(act, int) else act
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous():
+            raise _lib.PulseError("bias must be contiguous fp32 [N]")
+        ep.bias = bias.data_ptr()
+    if gate is not None:
+        _check_bf16(gate, "gate")
+        ep.gate, ep.ldg = gate.data_ptr(), gate.stride(0)
+        ep.gate_mode = ACT[gate_mode] if not isinstance(gate_mode, int) else gate_mode
+    if out is not None:
+        _check_bf16(out, "out")
+        if out.shape[0] < M or out.shape[1] < N:
+            raise _lib.PulseError("out too small")
+        ep.out, ep.ldo = out.data_ptr(), out.stride(0)
+    if out_t is not None:
+        _check_bf16(out_t, "out_t")
+        if out_t.shape[0] < N or out_t.shape[1] < M:
+            raise _lib.PulseError("out_t too small")
+        ep.out_t, ep.ldot = out_t.data_ptr(), out_t.stride(0)
+    if preact is not None:
+        _check_bf16(preact, "preact")
+        ep.preact, ep.ldp = preact.data_ptr(), preact.stride(0)
+    if out_f32 is not None:
+        if out_f32.dtype != torch.float32 or out_f32.stride(-1) != 1:
+            raise _lib.PulseError("out_f32 must be fp32 with contiguous rows")
+        if out_f32.dim() == 3:  # [splits, M, N] slabs
+            if out_f32.shape[0] < num_splits(K, split_k):
+                raise _lib.PulseError("out_f32 has fewer slabs than split-K needs")
+            ep.split_stride, ep.ldf = out_f32.stride(0), out_f32.stride(1)
+        else:
+            if split_k != 1:
+                raise _lib.PulseError("split_k > 1 needs a [splits, M, N] out_f32")
+            ep.ldf = out_f32.stride(0)
+        ep.out_f32 = out_f32.data_ptr()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.pulse_gemm_bf16_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, C.byref(ep), split_k,
+                                          _lib.current_stream(a.device)), "pulse_gemm_bf16_nt")

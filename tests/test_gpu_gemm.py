@@ -1,0 +1,86 @@
+"""tcgen05 bf16 GEMM vs a plain PyTorch fp32 reference of the same op (bf16-rounded inputs)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias=None, act=None, alpha=1.0):
+    y = alpha * (a.float() @ b.float().T)
+    if bias is not None:
+        y = y + bias
+    pre = y
+    if act == "relu":
+        y = torch.relu(y)
+    elif act == "silu":
+        y = torch.nn.functional.silu(y)
+    return y, pre
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 960), (300, 200, 136), (128, 128, 1024), (16384, 1024, 960), (77, 69, 512)])
+def test_gemm_fp32_and_bf16_outputs(M, N, K):
+    from pulse_b200.dense import gemm_nt
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    of = torch.full((M, N), float("nan"), device=dev)
+    ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    gemm_nt(a, b, bias=bias, act="relu", out=ob, out_f32=of)
+    torch.cuda.synchronize()
+    ref, _ = _ref(a, b, bias, "relu")
+    torch.testing.assert_close(of, ref, atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(ob.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_gemm_epilogue_variants():
+    from pulse_b200.dense import gemm_nt
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    M, N, K = 384, 264, 200
+    a = torch.randn(M, 208, device=dev, generator=g).bfloat16()[:, :K]     # lda 208 > K
+    b = (torch.randn(N, 256, device=dev, generator=g) / K ** 0.5).bfloat16()[:, :K]
+    bias = torch.randn(N, device=dev, generator=g)
+    out = torch.zeros(M, 272, device=dev, dtype=torch.bfloat16)[:, :N]
+    out_t = torch.zeros(N, M, device=dev, dtype=torch.bfloat16)
+    pre = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    gemm_nt(a, b, bias=bias, act="silu", out=out, out_t=out_t, preact=pre, alpha=0.5)
+    ref, refpre = _ref(a, b, bias, "silu", alpha=0.5)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(out_t.float(), ref.T, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(pre.float(), refpre, atol=2e-2, rtol=2e-2)
+    # backward-style gating: result * relu'(saved output) and * silu'(saved pre-activation)
+    gate = torch.randn(M, N, device=dev, generator=g).bfloat16()
+    of = torch.zeros(M, N, device=dev)
+    gemm_nt(a, b, gate=gate, gate_mode="relu", out_f32=of)
+    torch.testing.assert_close(of, _ref(a, b)[0] * (gate.float() > 0), atol=2e-3, rtol=2e-3)
+    gemm_nt(a, b, gate=gate, gate_mode="silu", out_f32=of)
+    z = gate.float()
+    s = torch.sigmoid(z)
+    torch.testing.assert_close(of, _ref(a, b)[0] * (s * (1 + z * (1 - s))), atol=2e-3, rtol=2e-3)
+
+
+def test_gemm_split_k_slabs():
+    from pulse_b200.dense import gemm_nt, num_splits
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(9)
+    M, N, K = 256, 192, 4096 + 64
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    b = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    ns = num_splits(K, 6)
+    slabs = torch.zeros(ns, M, N, device=dev)
+    gemm_nt(a, b, out_f32=slabs, split_k=6)
+    torch.testing.assert_close(slabs.sum(0), _ref(a, b)[0], atol=3e-3, rtol=3e-3)
+
+
+def test_gemm_rejects_bad_arguments():
+    from pulse_b200 import PulseError
+    from pulse_b200.dense import gemm_nt
+    dev = torch.device("cuda:0")
+    a = torch.zeros(128, 70, device=dev, dtype=torch.bfloat16)
+    b = torch.zeros(128, 70, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(PulseError):
+        gemm_nt(a, b, out_f32=torch.zeros(128, 128, device=dev))  # lda = 70 not a multiple of 8
+    with pytest.raises(PulseError):
+        gemm_nt(a[:, :64].contiguous(), b[:, :64].contiguous())      # no output
