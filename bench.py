@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 
 TOTAL_ENVS = 16384
 HORIZON = 32
+MINIBATCH = 16384      # im.yaml:72 (per rank, as under Horovod)
+MINI_EPOCHS = 6        # im.yaml:73
 ALGO_BYTES_PER_ENV_STEP = 9396  # fused step kernel, core total incl. power term
 METRIC = "env-steps/sec at 16384 humanoid envs, 1/2/4/8 B200; obs-kernel HBM GB/s"
 
@@ -88,7 +90,7 @@ def pick_cpu_threads(max_threads):
     for t in sorted({1, 4, 8, 16, 32, 64, max_threads}):
         if t > max_threads:
             continue
-        rate, _ = cpu_port_rate(1024, 1, t, gae=False)
+        rate, _ = cpu_port_rate(512, 1, t, gae=True)
         if rate > best_rate:
             best, best_rate = t, rate
     return best
@@ -118,18 +120,55 @@ def cpu_port_rate(n_envs, n_iters, threads, gae=True):
         adv = po.discount_values(d, v, r, nv)
         return po.normalized_advantages(po.swap_and_flatten01(adv + v), po.swap_and_flatten01(v))
 
+    # networks of im.yaml as plain fp32 torch modules (what the reference trains: mixed_precision False, im.yaml:51)
+    def mlp(i, o):
+        return torch.nn.Sequential(torch.nn.Linear(i, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512), torch.nn.ReLU(), torch.nn.Linear(512, o))
+    actor, critic, disc = mlp(934, 69), mlp(934, 1), mlp(1960, 1)
+    opt = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=2e-5, eps=1e-8)
+    obs = torch.randn(n_envs, 934)
+    ampx = torch.randn(n_envs, 1960)
+    logstd = torch.full((69,), -2.9)
+    adv_b, ret_b = torch.randn(n_envs), torch.randn(n_envs)
+
+    def rollout_nets():
+        with torch.no_grad():
+            x = torch.clamp(obs, -5, 5)
+            mu = actor(x)
+            critic(x)
+            critic(x)                      # next-value evaluation
+            disc(torch.clamp(ampx, -5, 5))
+            a_ = mu + torch.exp(logstd) * torch.randn_like(mu)
+            return a_, po.gaussian_neglogp(a_, mu, torch.exp(logstd).expand_as(mu), logstd.expand_as(mu))
+
+    def update_minibatch(a_, nlp):
+        x = torch.clamp(obs, -5, 5)
+        out = po.ppo_total_loss(actor(x), critic(x).squeeze(1), nlp, adv_b, ret_b, a_, logstd)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(list(actor.parameters()) + list(critic.parameters()), 50.0)
+        opt.step()
+
     one_env_step()
     t0 = time.perf_counter()
     for _ in range(n_iters):
         one_env_step()
     t_step = (time.perf_counter() - t0) / n_iters
-    t_gae = 0.0
+    t_gae = t_net = t_upd = 0.0
     if gae:
         gae_pass()
         t0 = time.perf_counter()
         gae_pass()
         t_gae = time.perf_counter() - t0
-    per_iter = HORIZON * t_step + t_gae  # one PPO iteration over n_envs
+        a_, nlp = rollout_nets()
+        t0 = time.perf_counter()
+        a_, nlp = rollout_nets()
+        t_net = time.perf_counter() - t0
+        update_minibatch(a_, nlp)
+        t0 = time.perf_counter()
+        update_minibatch(a_, nlp)
+        t_upd = time.perf_counter() - t0
+    # one PPO iteration over n_envs: 32 env steps (+ net forwards), GAE, 6 epochs x 32 minibatches of n_envs rows
+    per_iter = HORIZON * (t_step + t_net) + t_gae + MINI_EPOCHS * HORIZON * t_upd
     return HORIZON * n_envs / per_iter, per_iter
 
 
@@ -140,7 +179,7 @@ def run_reference(a):
     if rank != 0:
         return
     threads = pick_cpu_threads(os.cpu_count() or 1)
-    n = min(a.envs, 4096)
+    n = min(a.envs, 2048)
     vals, per = [], []
     for i in range(a.warmup + a.steps):
         rate, per_iter = cpu_port_rate(n, 2, threads)
@@ -154,22 +193,43 @@ def run_reference(a):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, 1, a.envs),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n} envs x 2 env-steps + one GAE pass per step, scaled to a 32-step iteration; torch {torch.__version__} CPU"},
+                         "sample": f"{n} envs: 2 env-steps (obs/reward/reset/AMP) + policy/critic/disc fwd + one PPO minibatch fwd/bwd/Adam + GAE, fp32, scaled to a 32-step iteration with 6 mini-epochs; torch {torch.__version__} CPU"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(a, world, envs_total):
+    mb = HORIZON * (envs_total // world) // MINIBATCH
     return {
         "workload": "HumanoidIm PPO iteration, 16384 envs total, AMASS-shaped synthetic MotionLib (one clip per env, "
-                    f"lognormal lengths, median {a.median_frames} frames @30fps), horizon 32 (BASELINE configs[3])",
-        "envs_total": envs_total, "envs_per_gpu": envs_total // world, "horizon": HORIZON, "parallelism": f"env-shard x{world}",
-        "phases": ["32x fused reward+reset+obs kernel (K1-K5)", "32x AMP obs + history kernel (K6)", "GAE + returns + adv-norm (K11,K12)"],
-        "not_yet": ["policy/value/disc MLP forward (K7-K10)", "PPO/disc update: fwd+bwd+Adam+grad allreduce (K13-K16)"],
-        "physics": "excluded (Isaac Gym not installable; state tensors are synthetic, resident in HBM)",
-        "l2": "256 MiB L2 flush write before every timed iteration; per-iteration inputs (tables 3.9 GB/rank at N=1) exceed L2",
+                    f"lognormal lengths, median {a.median_frames} frames @30fps), horizon 32, im.yaml nets (BASELINE configs[3])",
+        "envs_total": envs_total, "envs_per_gpu": envs_total // world, "horizon": HORIZON, "minibatch": MINIBATCH,
+        "mini_epochs": MINI_EPOCHS, "minibatches_per_epoch_per_gpu": mb, "parallelism": f"env-shard x{world}, grad all-reduce per minibatch",
+        "phases": ["32x [obs normalise + actor/critic MLP fwd (tcgen05) + Gaussian sample (K7-K9)]",
+                   "32x fused reward+reset+obs kernel (K1-K5)", "32x AMP obs + history kernel (K6)",
+                   "32x critic fwd on next obs (next_values)", "discriminator fwd + AMP reward over 32xN rows (K10)",
+                   "GAE + returns + adv-norm (K11,K12)", "value/return normalisation (running stats)",
+                   f"{MINI_EPOCHS} mini-epochs x minibatches: obs-RMS update, actor/critic fwd, PPO loss, bwd (dgrad+wgrad), "
+                   "NCCL grad all-reduce (N>1), grad-norm clip + Adam, bf16 weight refresh (K13,K15,K16)"],
+        "not_yet": ["discriminator UPDATE (BCE + logit reg + gradient penalty, K14) and AMP replay/demo buffers",
+                    "action -> PD target (K22)"],
+        "physics": "excluded (Isaac Gym not installable; simulator state tensors are synthetic, resident in HBM)",
+        "l2": "256 MiB L2 flush write before every timed iteration; per-iteration working set (tables 3.9 GB + 6 GB rollout buffers at N=1) exceeds L2",
     }
+
+
+# per env-step MLP FLOPs actually executed inside the timed region (2 x MAC), im.yaml nets with K padded 934->960, 1960->1960
+def mlp_flops_per_env_step():
+    a = 960 * 1024 + 1024 * 512 + 512 * 69     # actor fwd MACs
+    c = 960 * 1024 + 1024 * 512 + 512 * 1      # critic fwd MACs
+    d = 1960 * 1024 + 1024 * 512 + 512 * 1     # disc fwd MACs
+    rollout = a + 2 * c + d                    # actor + critic (values) + critic (next values) + disc reward
+    # update: fwd + wgrad for every layer, dgrad for all but the first layer of each net
+    dgrad_a = 1024 * 512 + 512 * 69
+    dgrad_c = 1024 * 512 + 512 * 1
+    update = MINI_EPOCHS * (2 * (a + c) + dgrad_a + dgrad_c)
+    return 2.0 * (rollout + update)
 
 
 def main():
@@ -181,6 +241,8 @@ def main():
     from pulse_b200 import _lib
     from pulse_b200.humanoid_im import HumanoidImCompute
     from pulse_b200.motion_lib import MotionLibB200
+    from pulse_b200.nets import MLP, FlatParams, pad8
+    from pulse_b200.ppo import PPOPolicy, RunningMeanStdB200
     from pulse_b200.rollout import discount_values
     from tools.synth import device_step_inputs, device_tables
 
@@ -194,6 +256,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = a.envs // world
     lib = _lib.load()
+    T = HORIZON
+    assert (T * n) % MINIBATCH == 0, "rollout batch must be a multiple of the minibatch"
+    num_mb = T * n // MINIBATCH
 
     # ---- synthetic inputs, resident in HBM (shard: envs [rank*n, (rank+1)*n), one clip per env) ----
     tabs = device_tables(n, dev, seed=100 + rank, median_frames=a.median_frames)
@@ -201,16 +266,29 @@ def main():
     del tabs
     z = device_step_inputs(ml, n, seed=200 + rank)
     comp = HumanoidImCompute(ml)
-    T = HORIZON
-    obses = torch.zeros(T, n, 934, device=dev)          # experience buffer slice the obs kernel writes into
+    policy = PPOPolicy(device=dev, seed=0)            # replicated: same seed on every rank (Horovod broadcast equivalent)
+    dflat = FlatParams(dev)
+    disc = MLP(dflat, 1960, (1024, 512), 1, "relu")   # discriminator, forward only here (amp_network_builder.py:230-249)
+    dflat.finalize()
+    disc.init_default(torch.Generator(device=dev).manual_seed(1))
+    amp_rms = RunningMeanStdB200(1960, dev)
+    amp_x = torch.zeros(T * n, pad8(1960), device=dev, dtype=torch.bfloat16)
+
+    # experience buffers, ENV-MAJOR so a minibatch (512 envs x 32 steps) is a contiguous row range
+    obses = torch.zeros(n, T, 934, device=dev)
+    obs_carry = torch.zeros(n, 934, device=dev)
+    actions = torch.zeros(n, T, 69, device=dev)
+    mus = torch.zeros(n, T, 69, device=dev)
+    neglogp = torch.zeros(n, T, device=dev)
+    amp_obs = torch.zeros(T, n, 1960, device=dev)
+    values = torch.zeros(T, n, 1, device=dev)
+    next_values = torch.zeros(T, n, 1, device=dev)
     rewards = torch.zeros(T, n, device=dev)
+    dones = torch.zeros(T, n, device=dev)
     reward_raw = torch.zeros(n, 5, device=dev)
     reset_buf = torch.zeros(n, dtype=torch.long, device=dev)
     term_buf = torch.zeros(n, dtype=torch.long, device=dev)
-    dones = torch.zeros(T, n, device=dev)
     amp_buf = torch.zeros(n, 10, 196, device=dev)
-    values = torch.randn(T, n, 1, device=dev)            # stand-ins until the critic MLP is in the loop
-    next_values = torch.randn(T, n, 1, device=dev)
     progress0 = z["progress_buf"].clone()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # pinned host mirrors for the end-to-end arm
@@ -222,34 +300,106 @@ def main():
     h_term = torch.empty(n, dtype=torch.long).pin_memory()
     h2d = h_body.numel() * 4 + h_dof.numel() * 4 + h_force.numel() * 4
     d2h = n * (4 + 8 + 8)
-    step_events = []
+    step_events, update_events = [], []
+    step_kw = dict(body_state=z["body_state"], dof_vel=z["dof_vel"], dof_force=z["dof_force"], progress_buf=z["progress_buf"],
+                   motion_ids=z["motion_ids"], motion_start_times=z["motion_start_times"], motion_start_offset=z["motion_start_offset"],
+                   global_offset=z["global_offset"], cycle_counter=z["cycle_counter"], reward_raw=reward_raw, reset_buf=reset_buf,
+                   terminate_buf=term_buf)
+    # first observation of the first iteration
+    comp.step(obs_buf=obs_carry, rew_buf=rewards[0], **step_kw)
+
+    adv_buf = torch.zeros(T * n, device=dev)
+    ret_buf = torch.zeros(T * n, device=dev)
+    obs_f, act_f, mu_f, nlp_f = obses.view(T * n, 934), actions.view(T * n, 69), mus.view(T * n, 69), neglogp.view(T * n)
+
+    def pre_step(t, e2e):
+        """everything of rollout step t before the fused env kernel"""
+        if e2e:
+            z["body_state"].copy_(h_body, non_blocking=True)
+            z["dof_state"].copy_(h_dof, non_blocking=True)
+            z["dof_force"].copy_(h_force, non_blocking=True)
+        res = policy.act(obses[:, t])                       # get_action_values (common_agent.py:262-288)
+        actions[:, t].copy_(res["actions"])
+        mus[:, t].copy_(res["mus"])
+        neglogp[:, t].copy_(res["neglogpacs"])
+        values[t].copy_(res["values"])
+        z["progress_buf"] += 1                                # physics would run here (excluded); post_physics_step follows
+
+    def env_step(t):
+        nxt = obses[:, t + 1] if t + 1 < T else obs_carry
+        comp.step(obs_buf=nxt, rew_buf=rewards[t], **step_kw)
+
+    def post_step(t, e2e):
+        nxt = obses[:, t + 1] if t + 1 < T else obs_carry
+        comp.amp_obs(body_state=z["body_state"], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], amp_obs_buf=amp_buf)
+        amp_obs[t].copy_(amp_buf.view(n, 1960))
+        dones[t].copy_(reset_buf)
+        nv = policy.critic_values(nxt)                       # _eval_critic on the next obs (amp_agent.py:396-398)
+        next_values[t].copy_(nv * (1.0 - term_buf.unsqueeze(1).float()))
+        if e2e:
+            h_rew.copy_(rewards[t], non_blocking=True)
+            h_reset.copy_(reset_buf, non_blocking=True)
+            h_term.copy_(term_buf, non_blocking=True)
+
+    def post_rollout():
+        # discriminator reward over the whole horizon (amp_agent.py:422-424, :1027-1041)
+        amp_rms.normalize_into(amp_obs.view(T * n, 1960), amp_x)
+        logits = disc.forward(amp_x)
+        prob = 1.0 / (1.0 + torch.exp(-logits))
+        disc_r = -torch.log(torch.clamp(1.0 - prob, min=1e-4)) * 2.0
+        mb_rewards = 0.5 * rewards.unsqueeze(-1) + 0.5 * disc_r.view(T, n, 1)   # _combine_rewards, task_w = disc_w = 0.5
+        adv, ret = discount_values(dones, values, mb_rewards, next_values, normalize_advantage=True)
+        # value / return normalisation in train mode (prepare_dataset, common_agent.py:372-374)
+        policy.value_rms.update(values.view(T, n).t().reshape(T * n, 1))
+        policy.value_rms.update(ret.view(-1, 1))
+        adv_buf.copy_(adv)
+        ret_buf.copy_(policy.value_rms.normalize_values(ret.view(-1, 1)).view(-1))
+
+    def update_mb(i):
+        r0, r1 = i * MINIBATCH, (i + 1) * MINIBATCH
+        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], adv_buf[r0:r1], ret_buf[r0:r1], old_mu=mu_f[r0:r1], world_size=world)
+
+    # ---- CUDA graphs: every launch sequence with fixed buffers is captured once and replayed -----------------
+    use_graphs = os.environ.get("PULSE_NO_GRAPHS", "0") != "1"
+    graphs = {}
+    pool = torch.cuda.graph_pool_handle() if use_graphs else None   # replays are sequential: one shared private pool
+
+    def run(key, fn, *args):
+        if not use_graphs:
+            return fn(*args)
+        g = graphs.get(key)
+        if g is None:
+            fn(*args)                                   # eager once (lazy workspaces, one-time attribute calls)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn(*args)
+            graphs[key] = g
+        g.replay()
 
     def iteration(e2e, record):
         z["progress_buf"].copy_(progress0)
+        obses[:, 0].copy_(obs_carry)
         for t in range(T):
-            if e2e:
-                z["body_state"].copy_(h_body, non_blocking=True)
-                z["dof_state"].copy_(h_dof, non_blocking=True)
-                z["dof_force"].copy_(h_force, non_blocking=True)
-            z["progress_buf"] += 1
+            run(("pre", t, e2e), pre_step, t, e2e)
             if record:
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-            comp.step(body_state=z["body_state"], dof_vel=z["dof_vel"], dof_force=z["dof_force"], progress_buf=z["progress_buf"],
-                      motion_ids=z["motion_ids"], motion_start_times=z["motion_start_times"], motion_start_offset=z["motion_start_offset"],
-                      global_offset=z["global_offset"], cycle_counter=z["cycle_counter"], obs_buf=obses[t], rew_buf=rewards[t],
-                      reward_raw=reward_raw, reset_buf=reset_buf, terminate_buf=term_buf)
+            env_step(t)                                      # eager, so the dominant HBM kernel is timed live by events
             if record:
                 e.record()
                 step_events.append((s, e))
-            comp.amp_obs(body_state=z["body_state"], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], amp_obs_buf=amp_buf)
-            dones[t].copy_(reset_buf)
-            if e2e:
-                h_rew.copy_(rewards[t], non_blocking=True)
-                h_reset.copy_(reset_buf, non_blocking=True)
-                h_term.copy_(term_buf, non_blocking=True)
-        adv, ret = discount_values(dones, values, rewards, next_values, normalize_advantage=True)
-        return adv
+            run(("post", t, e2e), post_step, t, e2e)
+        run(("post_rollout",), post_rollout)
+        if record:
+            us, ue = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            us.record()
+        for _ in range(MINI_EPOCHS):
+            for i in range(num_mb):
+                run(("upd", i), update_mb, i)
+        if record:
+            ue.record()
+            update_events.append((us, ue))
 
     def barrier():
         if world > 1:
@@ -277,42 +427,61 @@ def main():
             total_ms += float(ms.item())
         return total_ms / steps, (lib.pulse_launch_count() - launches0) // steps
 
+    # count our kernels per iteration once, eagerly (graph replays do not pass through the library's counter)
+    use_graphs, saved = False, use_graphs
+    iteration(False, False)
+    l0 = lib.pulse_launch_count()
+    iteration(False, False)
+    launches_eager = lib.pulse_launch_count() - l0
+    use_graphs = saved
+
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, launches = timed(False, a.steps, True)
     clocks = sampler.stop()
     ms_e2e, _ = timed(True, max(2, a.steps // 2), False)
 
-    # dominant kernel: fused step kernel, live CUDA-event duration inside the timed region
     torch.cuda.synchronize()
     k_ms = sorted(s.elapsed_time(e) for s, e in step_events)
     k_avg = sum(k_ms) / len(k_ms)
+    u_ms = sum(s.elapsed_time(e) for s, e in update_events) / len(update_events)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (k_avg * 1e-3) / 1e9
     env_steps = T * a.envs
+    upd_flops = 2.0 * MINI_EPOCHS * (2 * (960 * 1024 + 1024 * 512 + 512 * 69 + 960 * 1024 + 1024 * 512 + 512)
+                                     + 2 * 1024 * 512 + 512 * 69 + 512) * T * n
     if rank == 0:
         line = {
             "metric": METRIC, "value": env_steps / (ms_dev * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world, a.envs),
+            "dtype": "bf16 GEMM operands, fp32 accumulate / master weights / observations", "data": "synthetic",
+            "config": workload_config(a, world, a.envs),
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * h2d * world,
                     "d2h_bytes_per_step": T * d2h * world, "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches_eager), "cuda_graphs": bool(use_graphs), "clocks": clocks,
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "avg_launch_ms": k_avg, "launches_timed": len(k_ms),
-                         "note": "event pairs include launch gaps of back-to-back stream work; see profiles/ for ncu per-launch times"},
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "avg_launch_ms": k_avg, "launches_timed": len(k_ms)},
+            "roofline_update": {"kernels": "PPO update phase (tcgen05 GEMMs + loss/Adam/reduction kernels), per rank", "bound": "tensor",
+                                "achieved": upd_flops / (u_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                "frac": upd_flops / (u_ms * 1e-3) / 1e12 / peak_tf, "update_ms": u_ms,
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
+                                "note": "algorithmic GEMM FLOPs of the update / whole update-phase time (non-GEMM kernels included)"},
+            "mlp_mflop_per_env_step": mlp_flops_per_env_step() / 1e6,
         }
         if not a.no_cpu_baseline:
             threads = pick_cpu_threads(os.cpu_count() or 1)
             rate, per_iter = cpu_port_rate(2048, 2, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                                    "sample": "2048 envs x 2 env-steps + one GAE pass (oracle port of the reference PyTorch path), scaled to a 32-step iteration"}
+                                    "sample": "2048 envs: 2 env-steps (obs/reward/reset/AMP) + policy fwd + one PPO minibatch fwd/bwd + GAE "
+                                              "(oracle port of the reference PyTorch path, fp32), scaled to a 32-step iteration"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

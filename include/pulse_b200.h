@@ -251,6 +251,12 @@ int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t c
  * fp32 x [rows, cols] accumulated in fp64 into sums[2*cols] (caller zeroes). */
 int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, double* sums, void* stream);
 
+/* RunningMeanStd._update_mean_var_count_from_moments (:54-66) on the device: merges the batch sums of
+ * pulse_column_moments (n rows) into the fp64 running mean / var / count and refreshes the fp32 mean / rstd
+ * vectors pulse_normalize_to_bf16 reads.  One launch, no host round trip. */
+int pulse_rms_merge(const double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
+                    float* mean_f32, float* rstd_f32, void* stream);
+
 /* Gaussian policy head (rl_games ModelA2CContinuousLogStd, fixed sigma: im.yaml:21-25):
  * actions = mu + exp(logstd)*eps;  neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*A*log(2*pi) + sum(logstd). */
 int pulse_gaussian_sample(const float* mu, int64_t ld_mu, const float* eps, const float* logstd, int64_t rows, int32_t num_actions,
@@ -287,8 +293,9 @@ int pulse_reduce_slabs(const float* slabs, int64_t slab_stride, int32_t num_slab
 int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream);
 /* clip_grad_norm_(max_norm) + Adam step over one flat parameter buffer (amp_agent.py:725-750; torch.optim.Adam
  * defaults beta 0.9/0.999): scale = min(1, max_norm/(sqrt(sumsq)+1e-6)) read on the device, no host sync. */
+/* `step` is a DEVICE counter (int32[1]) incremented by this call, so the launch sequence is CUDA-graph replayable. */
 int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sumsq,
-                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, void* stream);
 /* refresh the bf16 operand copies of one weight matrix W fp32 [n, k] (contiguous):
  *   w_bf16 [n, ld_k] (K-major, forward / wgrad-free) and wt_bf16 [k, ld_n] (transposed, dgrad operand); pads zeroed. */
 int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,

@@ -79,6 +79,16 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class PpoLossArgs(C.Structure):
+    _fields_ = [
+        ("mu", C.c_void_p), ("ld_mu", C.c_int64), ("value", C.c_void_p), ("ld_value", C.c_int64), ("actions", C.c_void_p),
+        ("old_neglogp", C.c_void_p), ("advantages", C.c_void_p), ("returns", C.c_void_p), ("old_mu", C.c_void_p),
+        ("logstd", C.c_void_p), ("num_actions", C.c_int32), ("e_clip", C.c_float), ("critic_coef", C.c_float),
+        ("bounds_coef", C.c_float), ("dmu", C.c_void_p), ("ld_dmu", C.c_int64), ("dmu_t", C.c_void_p), ("ld_dmu_t", C.c_int64),
+        ("dvalue", C.c_void_p), ("ld_dv", C.c_int64), ("dvalue_t", C.c_void_p), ("ld_dv_t", C.c_int64), ("stats", C.c_void_p),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
 
@@ -97,6 +107,20 @@ SIGNATURES = {
     "pulse_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(GemmEpilogue), C.c_int32, C.c_void_p]),
     "pulse_gemm_num_splits": (C.c_int, [C.c_int64, C.c_int32]),
+    "pulse_normalize_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_column_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pulse_rms_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "pulse_gaussian_sample": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "pulse_ppo_loss": (C.c_int, [C.POINTER(PpoLossArgs), C.c_int64, C.c_void_p]),
+    "pulse_column_sum_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pulse_reduce_slabs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pulse_sum_squares": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pulse_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "pulse_refresh_weight_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

@@ -190,21 +190,36 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
     g_mbar_wait(&sm.tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
+    const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const int row = m0 + lrow;
     const bool row_ok = row < M;
     float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(blockIdx.z) * ep.split_stride : nullptr;
+    // The stage ring is idle once the accumulator is complete: its first 34 KB stage the TRANSPOSED tile
+    // ([col][row], pitch 136 bf16) so that out_t leaves in coalesced 16-byte segments.
+    __nv_bfloat16* tstage = reinterpret_cast<__nv_bfloat16*>(&sm.a[0][0]);
+    constexpr int TP = BM + 8;
+    static_assert(BN * TP * 2 <= kStagesG * (int)kStageBytesA, "transposed staging must fit in the A ring");
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       unsigned r[32];
       tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
       const int col0 = n0 + c * 32;
+      const bool full = col0 + 32 <= N;
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = __uint_as_float(r[i]) * ep.alpha;
-        const int col = col0 + i;
-        if (ep.bias != nullptr && col < N) x += __ldg(ep.bias + col);
-        v[i] = x;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+      if (ep.bias != nullptr) {
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));  // bias is 16-byte aligned (flat buffer slots)
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+        }
       }
       if (ep.preact != nullptr && row_ok) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
@@ -218,13 +233,27 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
       }
       if (ep.gate != nullptr && row_ok) {
         const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
+        if (full && (ep.ldg & 7) == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + i));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(h[q]);
+              v[i + 2 * q] *= act_grad(f.x, ep.gate_mode);
+              v[i + 2 * q + 1] *= act_grad(f.y, ep.gate_mode);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
+        }
       }
       if (outf != nullptr && row_ok) {
         float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
-        if (col0 + 32 <= N && (ep.ldf & 3) == 0) {
+        if (full && (ep.ldf & 3) == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -235,7 +264,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
       }
       if (ep.out != nullptr && row_ok) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
-        if (col0 + 32 <= N && (ep.ldo & 7) == 0) {
+        if (full && (ep.ldo & 7) == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
@@ -253,12 +282,33 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
             if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
         }
       }
-      if (ep.out_t != nullptr && row_ok) {
-        // transposed copy: lanes hold consecutive rows -> consecutive addresses of out_t[col][row]
+      if (ep.out_t != nullptr) {
+        // lanes hold consecutive rows -> consecutive 2-byte addresses of tstage[col][row]: conflict-free
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N)
-            reinterpret_cast<__nv_bfloat16*>(ep.out_t)[static_cast<long long>(col0 + i) * ep.ldot + row] = __float2bfloat16(v[i]);
+        for (int i = 0; i < 32; ++i) tstage[(c * 32 + i) * TP + lrow] = __float2bfloat16(v[i]);
+      }
+    }
+    if (ep.out_t != nullptr) {
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");  // the four epilogue warps only
+      const int t = threadIdx.x - 64;                    // 0..127
+      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(ep.out_t);
+      const bool vec_ok = (ep.ldot & 7) == 0;
+#pragma unroll 4
+      for (int it = 0; it < (BN * BM / 8) / 128; ++it) {
+        const int idx = it * 128 + t;
+        const int col = idx >> 4, seg = idx & 15;        // 16 segments of 8 rows per column
+        const int gcol = n0 + col, grow = m0 + seg * 8;
+        if (gcol < N && grow < M) {
+          const uint4 u = *reinterpret_cast<const uint4*>(tstage + col * TP + seg * 8);
+          __nv_bfloat16* dst = ot + static_cast<long long>(gcol) * ep.ldot + grow;
+          if (vec_ok && grow + 8 <= M) {
+            *reinterpret_cast<uint4*>(dst) = u;
+          } else {
+            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
+            for (int q = 0; q < 8; ++q)
+              if (grow + q < M) dst[q] = e[q];
+          }
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

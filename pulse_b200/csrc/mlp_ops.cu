@@ -183,15 +183,66 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(const pulse_ppo_loss_args
 }
 
 // ---- column sums of a bf16 matrix (bias gradients) ------------------------------------------------------------------
+// Block = 16 column groups (8 columns each, one 16-byte load) x 16 row lanes; blockIdx.y strides over row chunks.
 __global__ void __launch_bounds__(256) column_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows,
                                                               long long cols, float* __restrict__ out) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float part[16][129];
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const long long c0 = (long long)blockIdx.x * 128 + cg * 8;
   const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-  float s = 0.0f;
-  for (long long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ldx + c]);
-  atomicAdd(out + c, s);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool vec = (ldx & 7) == 0 && c0 + 8 <= cols;
+  if (c0 < cols) {
+    for (long long r = r0 + rl; r < r1; r += 16) {
+      const __nv_bfloat16* p = x + r * ldx + c0;
+      if (vec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      } else {
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < cols) acc[q] += __bfloat162float(p[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) part[rl][cg * 8 + q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += part[k][threadIdx.x];
+    const long long c = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+// ---- RunningMeanStd training-mode merge (running_mean_std.py:54-66, :96-107), one CTA ----------------------------------
+__global__ void __launch_bounds__(1024) rms_merge_kernel(const double* __restrict__ sums, long long n, int size, double* __restrict__ mean,
+                                                         double* __restrict__ var, double* __restrict__ count, float eps,
+                                                         float* __restrict__ mean_f32, float* __restrict__ rstd_f32) {
+  const double cnt = *count;
+  const double tot = cnt + (double)n;
+  for (int c = threadIdx.x; c < size; c += blockDim.x) {
+    const double bm = sums[c] / (double)n;
+    const double bv = (sums[size + c] - (double)n * bm * bm) / (double)(n - 1);  // unbiased, torch.var default
+    const double delta = bm - mean[c];
+    const double m2 = var[c] * cnt + bv * (double)n + delta * delta * cnt * (double)n / tot;
+    const double nm = mean[c] + delta * (double)n / tot;
+    const double nv = m2 / tot;
+    mean[c] = nm;
+    var[c] = nv;
+    mean_f32[c] = (float)nm;
+    rstd_f32[c] = 1.0f / sqrtf((float)nv + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = tot;
 }
 
 __global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restrict__ slabs, long long slab_stride, int num_slabs,
@@ -222,7 +273,9 @@ __global__ void __launch_bounds__(256) sum_squares_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long count, const double* __restrict__ sumsq, float max_norm,
-                                                   float lr, float b1, float b2, float eps, float bc1, float bc2) {
+                                                   float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr) {
+  const float step = static_cast<float>(*step_ptr);  // already incremented by bump_step_kernel
+  const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
   float scale = 1.0f;
   if (sumsq != nullptr && max_norm > 0.0f) {
     const float norm = static_cast<float>(sqrt(*sumsq));
@@ -238,6 +291,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
   }
 }
+
+__global__ void bump_step_kernel(int* step) { *step += 1; }
 
 __global__ void __launch_bounds__(256) refresh_weight_kernel(const float* __restrict__ w, long long n, long long k,
                                                              __nv_bfloat16* __restrict__ wb, long long ld_k,
@@ -321,9 +376,22 @@ extern "C" int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, v
 
 extern "C" int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream) {
   PULSE_REQUIRE(x && out && rows > 0 && cols > 0, "pulse_column_sum_bf16: bad argument");
-  dim3 grid(static_cast<unsigned>((cols + 255) / 256), static_cast<unsigned>(rows >= 4096 ? 64 : 1));
+  const unsigned gx = static_cast<unsigned>((cols + 127) / 128);
+  unsigned gy = static_cast<unsigned>((rows + 255) / 256);
+  const unsigned cap = (4 * kSMs + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, gy);
   column_sum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, cols, out);
   PULSE_LAUNCH_OK("column_sum_bf16_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_rms_merge(const double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
+                               float* mean_f32, float* rstd_f32, void* stream) {
+  PULSE_REQUIRE(sums && mean && var && count && mean_f32 && rstd_f32 && n >= 2 && size > 0, "pulse_rms_merge: bad argument");
+  rms_merge_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(sums, n, size, mean, var, count, eps, mean_f32, rstd_f32);
+  PULSE_LAUNCH_OK("rms_merge_kernel");
   return PULSE_OK;
 }
 
@@ -342,12 +410,13 @@ extern "C" int pulse_sum_squares(const float* x, int64_t count, double* sumsq, v
 }
 
 extern "C" int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
-                               const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t step,
+                               const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step,
                                void* stream) {
-  PULSE_REQUIRE(params && grads && exp_avg && exp_avg_sq && count > 0 && step >= 1, "pulse_adam_step: bad argument");
-  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  PULSE_REQUIRE(params && grads && exp_avg && exp_avg_sq && count > 0 && step != nullptr, "pulse_adam_step: bad argument");
+  bump_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step);
+  PULSE_LAUNCH_OK("bump_step_kernel");
   adam_kernel<<<grid_for(count, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, count, grad_sumsq,
-                                                                                       max_norm, lr, beta1, beta2, eps, bc1, bc2);
+                                                                                       max_norm, lr, beta1, beta2, eps, step);
   PULSE_LAUNCH_OK("adam_kernel");
   return PULSE_OK;
 }

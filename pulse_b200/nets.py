@@ -1,0 +1,259 @@
+"""MLP stacks of the PULSE / PHC agents on the B200 tensor cores.
+
+Mirrors what `phc.learning.network_builder.NetworkBuilder._build_mlp` + `AMPBuilder.Network`
+(network_builder.py:105-124, amp_network_builder.py:20-249) build -- Linear+activation stacks with a
+linear head -- but stores them for the tcgen05 GEMM: fp32 master weights in ONE flat buffer (so the
+gradient all-reduce, the norm clip and Adam are single launches), bf16 K-major operand copies of W
+and W^T refreshed after every optimizer step, activations (and their transposes, the operands of
+the weight-gradient GEMMs) written by the GEMM epilogues.
+
+Forward / backward are explicit (no autograd): forward Y = act(X W^T + b); dgrad dX = (dY W) * act'(.);
+wgrad dW = dY^T X via split-K fp32 slabs; db = column sums of dY.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .dense import gemm_nt, num_splits
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class FlatParams:
+    """One flat fp32 buffer each for parameters, gradients and the two Adam moments."""
+
+    def __init__(self, device):
+        self.device = device
+        self._shapes: List[tuple] = []
+        self._numel = 0
+        self.params = self.grads = self.exp_avg = self.exp_avg_sq = None
+        self.step = None   # device-side Adam step counter (keeps the update CUDA-graph replayable)
+        self.sumsq = None
+
+    def reserve(self, *shape) -> int:
+        off = self._numel
+        n = 1
+        for s in shape:
+            n *= s
+        self._numel += (n + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self._shapes.append((off, tuple(shape)))
+        return len(self._shapes) - 1
+
+    def finalize(self):
+        z = lambda: torch.zeros(self._numel, device=self.device, dtype=torch.float32)
+        self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        self.sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
+        self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
+
+    def view(self, idx: int, what: str = "params") -> torch.Tensor:
+        off, shape = self._shapes[idx]
+        n = 1
+        for s in shape:
+            n *= s
+        return getattr(self, what)[off:off + n].view(*shape)
+
+    @property
+    def numel(self):
+        return self._numel
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def adam_step(self, lr: float, max_norm: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        """nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam step (amp_agent.py:725-750), two launches, no host sync."""
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            st = _lib.current_stream(self.device)
+            sumsq_ptr = None
+            if max_norm and max_norm > 0:
+                self.sumsq.zero_()
+                _lib.check(lib.pulse_sum_squares(self.grads.data_ptr(), self._numel, self.sumsq.data_ptr(), st), "pulse_sum_squares")
+                sumsq_ptr = self.sumsq.data_ptr()
+            _lib.check(lib.pulse_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                           self._numel, sumsq_ptr, float(max_norm or 0.0), lr, betas[0], betas[1], eps, self.step.data_ptr(), st),
+                       "pulse_adam_step")
+
+
+class Dense:
+    """One Linear layer: W [N, Kp] (K padded to a multiple of 8 with zero columns), b [N]."""
+
+    def __init__(self, flat: FlatParams, in_features: int, out_features: int, act: Optional[str]):
+        self.K, self.N, self.act = in_features, out_features, act
+        self.Kp, self.Np = pad8(in_features), pad8(out_features)
+        self.flat = flat
+        self.w_idx = flat.reserve(out_features, self.Kp)
+        self.b_idx = flat.reserve(out_features)
+        self.w_bf16 = self.wt_bf16 = None
+
+    # views (valid after flat.finalize())
+    @property
+    def weight(self):
+        return self.flat.view(self.w_idx)
+
+    @property
+    def bias(self):
+        return self.flat.view(self.b_idx)
+
+    @property
+    def weight_grad(self):
+        return self.flat.view(self.w_idx, "grads")
+
+    @property
+    def bias_grad(self):
+        return self.flat.view(self.b_idx, "grads")
+
+    def init_default(self, gen: Optional[torch.Generator] = None):
+        """torch.nn.Linear default init (kaiming_uniform(a=sqrt(5)) -> U(-1/sqrt(K), 1/sqrt(K)) for W and b)."""
+        bound = 1.0 / math.sqrt(self.K)
+        w = (torch.rand(self.N, self.K, device=self.flat.device, generator=gen) * 2 - 1) * bound
+        b = (torch.rand(self.N, device=self.flat.device, generator=gen) * 2 - 1) * bound
+        self.set_weights(w, b)
+
+    def set_weights(self, w: torch.Tensor, b: torch.Tensor):
+        self.weight.zero_()
+        self.weight[:, :self.K].copy_(w)
+        self.bias.copy_(b)
+        self.refresh()
+
+    def refresh(self):
+        """bf16 operand copies: W [N, Kp] for forward, W^T [Kp, Np] for dgrad."""
+        lib = _lib.load()
+        dev = self.flat.device
+        if self.w_bf16 is None:
+            self.w_bf16 = torch.zeros(self.N, self.Kp, device=dev, dtype=torch.bfloat16)
+            self.wt_bf16 = torch.zeros(self.Kp, self.Np, device=dev, dtype=torch.bfloat16)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pulse_refresh_weight_bf16(self.weight.data_ptr(), self.N, self.Kp, self.w_bf16.data_ptr(), self.Kp,
+                                                     self.wt_bf16.data_ptr(), self.Np, _lib.current_stream(dev)), "pulse_refresh_weight_bf16")
+
+
+class MLP:
+    """units: hidden sizes; `head` linear output layer size (or None).  Activation 'relu' | 'silu'."""
+
+    def __init__(self, flat: FlatParams, in_features: int, units: Sequence[int], head: Optional[int], act: str = "relu"):
+        self.flat = flat
+        self.act = act
+        sizes = [in_features] + list(units)
+        self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], act) for i in range(len(units))]
+        if head is not None:
+            self.layers.append(Dense(flat, sizes[-1], head, None))
+        self.in_features, self.Kp0 = in_features, pad8(in_features)
+        self._ws: Dict[int, dict] = {}
+
+    def init_default(self, gen=None):
+        for l in self.layers:
+            l.init_default(gen)
+
+    def refresh(self):
+        for l in self.layers:
+            l.refresh()
+
+    def _workspace(self, M: int, train: bool):
+        key = (M, train)
+        if key not in self._ws:
+            dev = self.flat.device
+            bf = lambda r, c: torch.zeros(r, c, device=dev, dtype=torch.bfloat16)
+            ws = {"act": [], "act_t": [], "pre": [], "dact": [], "dact_t": [], "slabs": []}
+            for i, l in enumerate(self.layers):
+                last = i == len(self.layers) - 1
+                ws["act"].append(None if last else bf(M, l.Np))
+                if train:
+                    ws["act_t"].append(None if last else bf(l.Np, M))
+                    ws["pre"].append(bf(M, l.Np) if (l.act == "silu") else None)
+                    ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
+                    ws["dact_t"].append(None if last else bf(l.Np, M))
+                    tiles = ((l.N + 127) // 128) * ((l.Kp + 127) // 128)
+                    want = max(1, min(64, (2 * 148 + tiles - 1) // tiles))
+                    ns = num_splits(M, want)
+                    ws["slabs"].append((want, torch.zeros(ns, l.N, l.Kp, device=dev)))
+            ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
+            self._ws[key] = ws
+        return self._ws[key]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, train: bool = False, x_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer).
+        With train=True the activations / transposes needed by backward() are kept; x_t = x^T bf16 [Kp0, M]."""
+        M = x.shape[0]
+        ws = self._workspace(M, train)
+        h = x
+        for i, l in enumerate(self.layers):
+            last = i == len(self.layers) - 1
+            if last:
+                gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
+            else:
+                gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], out_t=ws["act_t"][i] if train else None,
+                        preact=ws["pre"][i] if train else None)
+                h = ws["act"][i]
+        if train:
+            ws["x"], ws["x_t"] = x, x_t
+        return ws["out"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dout: torch.Tensor, dout_t: torch.Tensor, M: int) -> None:
+        """dout bf16 [M, pad8(head)], dout_t bf16 [head, M]: gradient of the loss w.r.t. the head output.
+        Accumulates dW, db of every layer into the flat gradient buffer (overwrites the layer's slots)."""
+        lib = _lib.load()
+        ws = self._ws[(M, True)]
+        dev = self.flat.device
+        dy, dy_t = dout, dout_t
+        for i in reversed(range(len(self.layers))):
+            l = self.layers[i]
+            x_in = ws["x"] if i == 0 else ws["act"][i - 1]
+            x_in_t = ws["x_t"] if i == 0 else ws["act_t"][i - 1]
+            want, slabs = ws["slabs"][i]
+            # wgrad: dW [N, Kp] = dY^T [N, M] . X [M, Kp]  (A = dY^T, B = X^T, reduction over M)
+            gemm_nt(dy_t[:l.N], x_in_t[:l.Kp], out_f32=slabs, split_k=want)
+            with torch.cuda.device(dev):
+                st = _lib.current_stream(dev)
+                _lib.check(lib.pulse_reduce_slabs(slabs.data_ptr(), slabs.stride(0), slabs.shape[0], l.N * l.Kp, l.weight_grad.data_ptr(), st),
+                           "pulse_reduce_slabs")
+                bg = l.bias_grad
+                bg.zero_()
+                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, l.N, bg.data_ptr(), st), "pulse_column_sum_bf16")
+            if i > 0:
+                prev = self.layers[i - 1]
+                # dgrad: dX [M, K] = dY [M, N] . W [N, K], gated by act'(.) of the previous layer
+                gate = ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1]
+                gemm_nt(dy[:, :l.N], l.wt_bf16[:, :l.N], gate=gate, gate_mode=prev.act, out=ws["dact"][i - 1], out_t=ws["dact_t"][i - 1])
+                dy, dy_t = ws["dact"][i - 1], ws["dact_t"][i - 1]
+
+    # ------------------------------------------------------------------ checkpoint names
+    def state_dict(self, prefix: str, head_name: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """rl_games / nn.Sequential naming: `<prefix>.<2*i>.weight` for hidden layers, `<head_name>.weight` for the head."""
+        out = {}
+        hidden = self.layers[:-1] if head_name is not None else self.layers
+        for i, l in enumerate(hidden):
+            out[f"{prefix}.{2 * i}.weight"] = l.weight[:, :l.K].clone()
+            out[f"{prefix}.{2 * i}.bias"] = l.bias.clone()
+        if head_name is not None:
+            l = self.layers[-1]
+            out[f"{head_name}.weight"] = l.weight[:, :l.K].clone()
+            out[f"{head_name}.bias"] = l.bias.clone()
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str, head_name: Optional[str] = None):
+        hidden = self.layers[:-1] if head_name is not None else self.layers
+        for i, l in enumerate(hidden):
+            l.set_weights(sd[f"{prefix}.{2 * i}.weight"].to(self.flat.device), sd[f"{prefix}.{2 * i}.bias"].to(self.flat.device))
+        if head_name is not None:
+            l = self.layers[-1]
+            l.set_weights(sd[f"{head_name}.weight"].to(self.flat.device), sd[f"{head_name}.bias"].to(self.flat.device))
+
+
+def normalize_to_bf16(x: torch.Tensor, mean: Optional[torch.Tensor], rstd: Optional[torch.Tensor], out: torch.Tensor,
+                      out_t: Optional[torch.Tensor] = None) -> None:
+    """RunningMeanStd eval path (running_mean_std.py:69-95) fused with the bf16 cast / zero pad / transpose."""
+    lib = _lib.load()
+    rows, cols = x.shape
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        raise _lib.PulseError("normalize_to_bf16: x must be fp32 with contiguous rows")
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pulse_normalize_to_bf16(x.data_ptr(), x.stride(0), rows, cols, _lib.ptr(mean), _lib.ptr(rstd), out.data_ptr(), out.stride(0),
+                                               _lib.ptr(out_t), out_t.stride(0) if out_t is not None else 0, _lib.current_stream(x.device)),
+                   "pulse_normalize_to_bf16")

@@ -1,0 +1,189 @@
+"""PPO actor / critic on the B200: host-side mirror of the agent-side arithmetic of
+`phc.learning.common_agent.CommonAgent` / `amp_agent.AMPAgent` for the continuous-action 'amp' network
+(separate actor and critic MLPs, fixed log-std; im.yaml:13-42):
+
+  get_action_values   common_agent.py:262-288  -> PPOPolicy.act
+  _eval_critic        common_agent.py:552-562  -> PPOPolicy.critic_values
+  calc_gradients      amp_agent.py:605-760 (actor / critic / bound losses, grad-norm clip, Adam) -> PPOPolicy.train_minibatch
+  _preproc_obs        amp_agent.py:586-603 + RunningMeanStd (running_mean_std.py:69-109)          -> RunningMeanStdB200
+
+The discriminator branch of calc_gradients (AMP style loss with gradient penalty, amp_agent.py:895-952) is not
+part of this class yet.  Multi-GPU: gradients are all-reduced (average) over torch.distributed's NCCL
+communicator once per minibatch on the flat gradient buffer, replacing Horovod's DistributedOptimizer
+(amp_agent.py:735-742).
+"""
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .nets import MLP, FlatParams, normalize_to_bf16, pad8
+
+
+class RunningMeanStdB200:
+    """phc/utils/running_mean_std.py:9-109 with fp64 statistics kept on the device."""
+
+    def __init__(self, size: int, device, epsilon: float = 1e-5):
+        self.size, self.device, self.eps = size, device, epsilon
+        self.running_mean = torch.zeros(size, dtype=torch.float64, device=device)
+        self.running_var = torch.ones(size, dtype=torch.float64, device=device)
+        self.count = torch.ones((), dtype=torch.float64, device=device)
+        self._sums = torch.zeros(2 * size, dtype=torch.float64, device=device)
+        self.frozen = False
+        self.mean_f32 = torch.zeros(size, dtype=torch.float32, device=device)
+        self.rstd_f32 = torch.ones(size, dtype=torch.float32, device=device)
+        self._refresh()
+
+    def _refresh(self):
+        # in place: the buffers' addresses stay fixed, so normalise / update sequences can be captured in CUDA graphs
+        self.mean_f32.copy_(self.running_mean)
+        self.rstd_f32.copy_(1.0 / torch.sqrt(self.running_var.float() + self.eps))
+
+    def update(self, x: torch.Tensor) -> None:
+        """Training-mode statistics update (:96-107): Welford merge with the batch mean / unbiased variance."""
+        if self.frozen:
+            return
+        lib = _lib.load()
+        n = x.shape[0]
+        self._sums.zero_()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pulse_column_moments(x.data_ptr(), x.stride(0), n, self.size, self._sums.data_ptr(), _lib.current_stream(self.device)),
+                       "pulse_column_moments")
+            _lib.check(lib.pulse_rms_merge(self._sums.data_ptr(), n, self.size, self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                           self.count.data_ptr(), self.eps, self.mean_f32.data_ptr(), self.rstd_f32.data_ptr(),
+                                           _lib.current_stream(self.device)), "pulse_rms_merge")
+
+    def normalize_into(self, x: torch.Tensor, out: torch.Tensor, out_t: Optional[torch.Tensor] = None) -> None:
+        normalize_to_bf16(x, self.mean_f32, self.rstd_f32, out, out_t)
+
+    def unnormalize(self, y: torch.Tensor) -> torch.Tensor:
+        """forward(unnorm=True) (:84-87): clamp to +-5 then scale back (value de-normalisation)."""
+        return torch.clamp(y, -5.0, 5.0) * torch.sqrt(self.running_var.float() + self.eps) + self.running_mean.float()
+
+    def normalize_values(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.clamp((x - self.running_mean.float()) / torch.sqrt(self.running_var.float() + self.eps), -5.0, 5.0)
+
+
+class PPOPolicy:
+    def __init__(self, obs_size: int = 934, num_actions: int = 69, units: Sequence[int] = (1024, 512), act: str = "relu",
+                 logstd: float = -2.9, device="cuda:0", seed: int = 0, lr: float = 2e-5, e_clip: float = 0.2, critic_coef: float = 5.0,
+                 bounds_coef: float = 10.0, grad_norm: float = 50.0, normalize_value: bool = True):
+        self.device = torch.device(device)
+        self.obs_size, self.A = obs_size, num_actions
+        self.lr, self.e_clip, self.critic_coef, self.bounds_coef, self.grad_norm = lr, e_clip, critic_coef, bounds_coef, grad_norm
+        self.flat = FlatParams(self.device)
+        self.actor = MLP(self.flat, obs_size, units, num_actions, act)
+        self.critic = MLP(self.flat, obs_size, units, 1, act)
+        self.flat.finalize()
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.actor.init_default(gen)
+        self.critic.init_default(gen)
+        self.logstd = torch.full((num_actions,), logstd, device=self.device)  # fixed_sigma, const_initializer (im.yaml:21-25)
+        self.obs_rms = RunningMeanStdB200(obs_size, self.device)
+        self.value_rms = RunningMeanStdB200(1, self.device) if normalize_value else None
+        self.Kp = pad8(obs_size)
+        self._bufs: Dict[tuple, dict] = {}
+        self.stats = torch.zeros(6, dtype=torch.float64, device=self.device)
+        self.lib = _lib.load()
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, M: int, train: bool):
+        key = (M, train)
+        if key not in self._bufs:
+            dev = self.device
+            b = {"x": torch.zeros(M, self.Kp, device=dev, dtype=torch.bfloat16)}
+            if train:
+                Ap = pad8(self.A)
+                b.update(x_t=torch.zeros(self.Kp, M, device=dev, dtype=torch.bfloat16),
+                         dmu=torch.zeros(M, Ap, device=dev, dtype=torch.bfloat16), dmu_t=torch.zeros(Ap, M, device=dev, dtype=torch.bfloat16),
+                         dv=torch.zeros(M, 8, device=dev, dtype=torch.bfloat16), dv_t=torch.zeros(8, M, device=dev, dtype=torch.bfloat16))
+            else:
+                b.update(actions=torch.zeros(M, self.A, device=dev), neglogp=torch.zeros(M, device=dev))
+            self._bufs[key] = b
+        return self._bufs[key]
+
+    # ------------------------------------------------------------------ rollout side
+    def act(self, obs: torch.Tensor, eps: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """get_action_values (common_agent.py:262-288): normalise obs, actor + critic forward, sample, neglogp.
+        `eps` lets a test inject the standard-normal draw."""
+        M = obs.shape[0]
+        b = self._buf(M, False)
+        self.obs_rms.normalize_into(obs, b["x"])
+        mu = self.actor.forward(b["x"])
+        value = self.critic.forward(b["x"])
+        if eps is None:
+            eps = torch.randn(M, self.A, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_gaussian_sample(mu.data_ptr(), mu.stride(0), eps.data_ptr(), self.logstd.data_ptr(), M, self.A,
+                                                      b["actions"].data_ptr(), b["neglogp"].data_ptr(), _lib.current_stream(self.device)),
+                       "pulse_gaussian_sample")
+        values = self.value_rms.unnormalize(value) if self.value_rms is not None else value
+        return {"actions": b["actions"], "neglogpacs": b["neglogp"], "values": values, "mus": mu,
+                "sigmas": torch.exp(self.logstd).expand(M, self.A)}
+
+    def critic_values(self, obs: torch.Tensor) -> torch.Tensor:
+        """_eval_critic (common_agent.py:552-562)."""
+        M = obs.shape[0]
+        b = self._buf(M, False)
+        self.obs_rms.normalize_into(obs, b["x"])
+        value = self.critic.forward(b["x"])
+        return self.value_rms.unnormalize(value) if self.value_rms is not None else value
+
+    # ------------------------------------------------------------------ update side
+    def train_minibatch(self, obs, actions, old_neglogp, advantages, returns, old_mu=None, update_obs_rms: bool = True,
+                        world_size: int = 1) -> torch.Tensor:
+        """One calc_gradients step (amp_agent.py:605-760, PPO branch without the discriminator term).
+        `returns` are already value-normalised (prepare_dataset, common_agent.py:372-374).  Returns the fp64
+        stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
+        M = obs.shape[0]
+        b = self._buf(M, True)
+        self.obs_rms.normalize_into(obs, b["x"], b["x_t"])  # normalise with the statistics BEFORE this batch's update
+        if update_obs_rms:
+            self.obs_rms.update(obs)                         # running_mean_std.py:96-107 (train mode)
+        mu = self.actor.forward(b["x"], train=True, x_t=b["x_t"])
+        value = self.critic.forward(b["x"], train=True, x_t=b["x_t"])
+        a = _lib.PpoLossArgs(
+            mu=mu.data_ptr(), ld_mu=mu.stride(0), value=value.data_ptr(), ld_value=value.stride(0), actions=actions.data_ptr(),
+            old_neglogp=old_neglogp.data_ptr(), advantages=advantages.data_ptr(), returns=returns.data_ptr(),
+            old_mu=old_mu.data_ptr() if old_mu is not None else None, logstd=self.logstd.data_ptr(), num_actions=self.A,
+            e_clip=self.e_clip, critic_coef=self.critic_coef, bounds_coef=self.bounds_coef,
+            dmu=b["dmu"].data_ptr(), ld_dmu=b["dmu"].stride(0), dmu_t=b["dmu_t"].data_ptr(), ld_dmu_t=b["dmu_t"].stride(0),
+            dvalue=b["dv"].data_ptr(), ld_dv=b["dv"].stride(0), dvalue_t=b["dv_t"].data_ptr(), ld_dv_t=b["dv_t"].stride(0),
+            stats=self.stats.data_ptr())
+        self.stats.zero_()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream(self.device)), "pulse_ppo_loss")
+        self.actor.backward(b["dmu"], b["dmu_t"], M)
+        self.critic.backward(b["dv"], b["dv_t"], M)
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.AVG)  # one NCCL all-reduce on the flat bucket (NVLink / NVLS)
+        self.flat.adam_step(self.lr, max_norm=self.grad_norm)
+        self.actor.refresh()
+        self.critic.refresh()
+        return self.stats
+
+    # ------------------------------------------------------------------ checkpoint keys (rl_games layout)
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {}
+        sd.update({f"a2c_network.{k}": v for k, v in self.actor.state_dict("actor_mlp", "mu").items()})
+        sd.update({f"a2c_network.{k}": v for k, v in self.critic.state_dict("critic_mlp", "value").items()})
+        sd["a2c_network.sigma"] = self.logstd.clone()
+        sd["running_mean_std.running_mean"] = self.obs_rms.running_mean.clone()
+        sd["running_mean_std.running_var"] = self.obs_rms.running_var.clone()
+        sd["running_mean_std.count"] = self.obs_rms.count.clone()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        strip = {k[len("a2c_network."):]: v for k, v in sd.items() if k.startswith("a2c_network.")}
+        self.actor.load_state_dict(strip, "actor_mlp", "mu")
+        self.critic.load_state_dict(strip, "critic_mlp", "value")
+        if "sigma" in strip:
+            self.logstd.copy_(strip["sigma"].to(self.device))
+        if "running_mean_std.running_mean" in sd:
+            self.obs_rms.running_mean.copy_(sd["running_mean_std.running_mean"].to(self.device).double())
+            self.obs_rms.running_var.copy_(sd["running_mean_std.running_var"].to(self.device).double())
+            self.obs_rms.count.copy_(sd["running_mean_std.count"].to(self.device).double())
+            self.obs_rms._refresh()

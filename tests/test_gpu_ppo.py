@@ -1,0 +1,155 @@
+"""PPO actor/critic path on the GPU vs the oracle / a plain PyTorch fp32 reference of the same ops.
+
+Tolerances: the GEMMs run bf16 x bf16 -> fp32 (north_star: 'losses within 1e-3'); element-wise kernels are fp32.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _torch_mlp(mlp):
+    """fp32 nn.Sequential with the same weights as a pulse_b200.nets.MLP."""
+    mods = []
+    for i, l in enumerate(mlp.layers):
+        lin = torch.nn.Linear(l.K, l.N, device=DEV)
+        with torch.no_grad():
+            lin.weight.copy_(l.weight[:, :l.K])
+            lin.bias.copy_(l.bias)
+        mods.append(lin)
+        if l.act == "relu":
+            mods.append(torch.nn.ReLU())
+        elif l.act == "silu":
+            mods.append(torch.nn.SiLU())
+    return torch.nn.Sequential(*mods)
+
+
+def test_ppo_loss_kernel_matches_oracle():
+    from oracle import pulse_oracle as po
+    from pulse_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    M, A = 1000, 69
+    mu = (torch.randn(M, A, device=DEV, generator=g) * 0.8).requires_grad_(True)
+    value = torch.randn(M, 1, device=DEV, generator=g).requires_grad_(True)
+    logstd = torch.full((A,), -2.9, device=DEV)
+    actions = (mu.detach() + math.exp(-2.9) * torch.randn(M, A, device=DEV, generator=g)).contiguous()
+    old_mu = (mu.detach() + 0.01 * torch.randn(M, A, device=DEV, generator=g)).contiguous()
+    adv = torch.randn(M, device=DEV, generator=g)
+    ret = torch.randn(M, device=DEV, generator=g)
+    sigma = torch.exp(logstd).expand(M, A)
+    old_nlp = po.gaussian_neglogp(actions, old_mu, sigma, logstd.expand(M, A)).contiguous()
+    ref = po.ppo_total_loss(mu, value.squeeze(1), old_nlp, adv, ret, actions, logstd)
+    ref["loss"].backward()
+    dmu = torch.zeros(M, 72, device=DEV, dtype=torch.bfloat16)
+    dmu_t = torch.zeros(72, M, device=DEV, dtype=torch.bfloat16)
+    dv = torch.zeros(M, 8, device=DEV, dtype=torch.bfloat16)
+    dv_t = torch.zeros(8, M, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(6, device=DEV, dtype=torch.float64)
+    mud, vd = mu.detach().contiguous(), value.detach().contiguous()
+    a = _lib.PpoLossArgs(mu=mud.data_ptr(), ld_mu=A, value=vd.data_ptr(), ld_value=1, actions=actions.data_ptr(), old_neglogp=old_nlp.data_ptr(),
+                         advantages=adv.data_ptr(), returns=ret.data_ptr(), old_mu=old_mu.data_ptr(), logstd=logstd.data_ptr(), num_actions=A,
+                         e_clip=0.2, critic_coef=5.0, bounds_coef=10.0, dmu=dmu.data_ptr(), ld_dmu=72, dmu_t=dmu_t.data_ptr(), ld_dmu_t=M,
+                         dvalue=dv.data_ptr(), ld_dv=8, dvalue_t=dv_t.data_ptr(), ld_dv_t=M, stats=stats.data_ptr())
+    _lib.check(lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream()), "pulse_ppo_loss")
+    torch.cuda.synchronize()
+    s = stats.cpu() / M
+    assert abs(s[0].item() - ref["a_loss"].item()) < 1e-4 * max(1, abs(ref["a_loss"].item()))  # exp(old - new) at fp32 round-off
+    assert abs(s[1].item() - ref["c_loss"].item()) < 1e-4 * max(1, abs(ref["c_loss"].item()))
+    assert abs(s[2].item() - ref["b_loss"].item()) < 1e-5
+    assert abs(s[5].item() - ref["neglogp"].mean().item()) < 1e-3
+    kl = po.policy_kl(mu.detach(), sigma, old_mu, sigma)
+    assert abs(s[3].item() - kl.item()) < 1e-5
+    torch.testing.assert_close(dmu[:, :A].float(), mu.grad, atol=2e-5, rtol=1e-2)
+    torch.testing.assert_close(dmu_t[:A].float().T, mu.grad, atol=2e-5, rtol=1e-2)
+    torch.testing.assert_close(dv[:, 0].float(), value.grad[:, 0], atol=2e-5, rtol=1e-2)
+    torch.testing.assert_close(dv_t[0].float(), value.grad[:, 0], atol=2e-5, rtol=1e-2)
+
+
+def test_normalize_and_moments_match_reference_semantics():
+    from oracle import pulse_oracle as po
+    from pulse_b200.ppo import RunningMeanStdB200
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x1 = torch.randn(300, 934, device=DEV, generator=g) * 3 + 1
+    x2 = torch.randn(5000, 934, device=DEV, generator=g) * 0.5 - 2
+    rms = RunningMeanStdB200(934, DEV)
+    ref = po.RunningMeanStd(934)
+    out = torch.zeros(300, 960, device=DEV, dtype=torch.bfloat16)
+    out_t = torch.zeros(960, 300, device=DEV, dtype=torch.bfloat16)
+    for x in (x1, x2):
+        rms.update(x)
+        ref.update(x.cpu())
+    # the reference takes the batch mean / var in fp32 (input.mean / input.var) before the fp64 merge; the kernel
+    # accumulates the batch sums in fp64, so agreement is at fp32 round-off, not fp64
+    torch.testing.assert_close(rms.running_mean.cpu(), ref.mean, atol=2e-6, rtol=2e-6)
+    torch.testing.assert_close(rms.running_var.cpu(), ref.var, atol=2e-5, rtol=2e-5)
+    rms.normalize_into(x1, out, out_t)
+    y = ref.normalize(x1.cpu())
+    torch.testing.assert_close(out[:, :934].float().cpu(), y, atol=2e-2, rtol=1e-2)   # bf16 rounding of values in [-5, 5]
+    assert torch.all(out[:, 934:] == 0)
+    assert torch.equal(out_t.T.contiguous(), out)
+
+
+def test_policy_forward_and_update_match_fp32_reference():
+    from oracle import pulse_oracle as po
+    from pulse_b200.ppo import PPOPolicy
+    pol = PPOPolicy(device=DEV, seed=3)
+    actor_ref, critic_ref = _torch_mlp(pol.actor), _torch_mlp(pol.critic)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    M = 2048
+    obs = torch.randn(M, 934, device=DEV, generator=g) * 2
+    pol.obs_rms.update(obs)
+    pol.obs_rms.frozen = True
+    eps = torch.randn(M, 69, device=DEV, generator=g)
+    out = pol.act(obs, eps=eps)
+    xn = torch.clamp((obs - pol.obs_rms.mean_f32) * pol.obs_rms.rstd_f32, -5, 5)
+    mu_ref, v_ref = actor_ref(xn), critic_ref(xn)
+    torch.testing.assert_close(out["mus"], mu_ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(out["values"], v_ref, atol=2e-2, rtol=2e-2)  # value_rms is identity at init (mean 0, var 1)
+    sigma = torch.exp(pol.logstd).expand(M, 69)
+    torch.testing.assert_close(out["actions"], out["mus"] + sigma * eps, atol=1e-6, rtol=1e-6)
+    nlp = po.gaussian_neglogp(out["actions"], out["mus"], sigma, pol.logstd.expand(M, 69))
+    torch.testing.assert_close(out["neglogpacs"], nlp, atol=1e-3, rtol=1e-5)
+
+    # one PPO minibatch: losses within 1e-3, gradients aligned with fp32 autograd, Adam step applied
+    actions, old_nlp = out["actions"].clone(), out["neglogpacs"].clone()
+    adv = torch.randn(M, device=DEV, generator=g)
+    ret = torch.randn(M, device=DEV, generator=g)
+    w_before = pol.flat.params.clone()
+    ref = po.ppo_total_loss(mu_ref, v_ref.squeeze(1), old_nlp, adv, ret, actions, pol.logstd)
+    ref["loss"].backward()
+    stats = pol.train_minibatch(obs, actions, old_nlp, adv, ret, old_mu=out["mus"].clone(), update_obs_rms=False).cpu() / M
+    torch.cuda.synchronize()
+    for k, i in (("a_loss", 0), ("c_loss", 1), ("b_loss", 2)):
+        assert abs(stats[i].item() - ref[k].item()) < 1e-3 * max(1.0, abs(ref[k].item())), (k, stats[i].item(), ref[k].item())
+    for mlp, refm in ((pol.actor, actor_ref), (pol.critic, critic_ref)):
+        lins = [m for m in refm if isinstance(m, torch.nn.Linear)]
+        for l, lin in zip(mlp.layers, lins):
+            gw, gb = l.weight_grad[:, :l.K], l.bias_grad
+            cos = torch.nn.functional.cosine_similarity(gw.flatten(), lin.weight.grad.flatten(), dim=0)
+            assert cos > 0.995, (l.N, l.K, cos.item())
+            rel = (gw - lin.weight.grad).norm() / lin.weight.grad.norm()
+            assert rel < 0.15, rel.item()  # bf16 activations / gradients, ReLU masks that flip near zero
+            cosb = torch.nn.functional.cosine_similarity(gb, lin.bias.grad, dim=0)
+            assert cosb > 0.995, cosb.item()
+            assert torch.all(l.weight_grad[:, l.K:] == 0)
+    # Adam: compare against torch.optim.Adam fed the SAME (our) gradients
+    p = w_before.clone().requires_grad_(True)
+    p.grad = pol.flat.grads.clone()
+    torch.nn.utils.clip_grad_norm_([p], 50.0)
+    opt = torch.optim.Adam([p], lr=2e-5, eps=1e-8)
+    opt.step()
+    torch.testing.assert_close(pol.flat.params, p.detach(), atol=1e-7, rtol=1e-5)
+    l0 = pol.actor.layers[0]
+    torch.testing.assert_close(l0.w_bf16.float(), l0.weight, atol=1e-2, rtol=1e-2)
+    torch.testing.assert_close(l0.wt_bf16[:, :l0.N].float(), l0.weight.T, atol=1e-2, rtol=1e-2)
+    # checkpoint keys follow the rl_games layout the reference's loaders read (network_loader.py:81-99)
+    sd = pol.state_dict()
+    for k in ("a2c_network.actor_mlp.0.weight", "a2c_network.actor_mlp.2.bias", "a2c_network.mu.weight", "a2c_network.critic_mlp.0.weight",
+              "a2c_network.value.bias", "a2c_network.sigma", "running_mean_std.running_mean"):
+        assert k in sd
+    assert sd["a2c_network.actor_mlp.0.weight"].shape == (1024, 934) and sd["a2c_network.mu.weight"].shape == (69, 512)
