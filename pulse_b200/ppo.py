@@ -158,8 +158,8 @@ class PPOPolicy:
         self.actor.backward(b["dmu"], b["dmu_t"], M)
         self.critic.backward(b["dv"], b["dv_t"], M)
         if world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.AVG)  # one NCCL all-reduce on the flat bucket (NVLink / NVLS)
+            from .dist_utils import average_gradients
+            average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)
         self.flat.adam_step(self.lr, max_norm=self.grad_norm)
         self.actor.refresh()
         self.critic.refresh()
