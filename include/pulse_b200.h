@@ -229,12 +229,24 @@ typedef struct {
   int64_t split_stride;      /* floats between split-K slabs of out_f32 */
   pulse_bf16_t* preact;      /* [M, ldp] bf16 pre-activation (saved for SiLU backward), or NULL */
   int64_t ldp;
+  float* colsum;             /* [N] += column sums of the final values (bias gradient of the layer whose dY this GEMM writes), or NULL */
+  int32_t accumulate;        /* 1: out_f32 += result with fp32 atomics (weight gradients; caller zeroes), 0: overwrite */
+  int32_t reserved;
 } pulse_gemm_epilogue_t;
+
+#define PULSE_GEMM_A_MN 1u   /* A is given as [K, M] row-major (the reduction dimension is the ROW index) */
+#define PULSE_GEMM_B_MN 2u   /* B is given as [K, N] row-major */
 
 /* lda / ldb in elements, multiples of 8, >= K; A and B 16-byte aligned.  split_k > 1: fp32 slabs only
  * (slab z at out_f32 + z*split_stride); pulse_gemm_num_splits gives the number of slabs actually written. */
 int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                        const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream);
+/* General form: D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  flags select, per operand, K-major storage (A[M,K] / B[N,K],
+ * the NT case above) or MN-major storage (A[K,M] / B[K,N] row-major), so activations, output gradients and weights
+ * are consumed exactly as they sit in memory:  dgrad dX = dY . W  -> A = dY (K-major), B = W [N_out,K_in] as MN-major;
+ * wgrad dW = dY^T X -> A = dY [batch,N] MN-major, B = X [batch,K] MN-major.  No transposed copies anywhere. */
+int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                    const pulse_gemm_epilogue_t* ep, int32_t split_k, uint32_t flags, void* stream);
 int pulse_gemm_num_splits(int64_t k, int32_t split_k);
 
 /* ------------------------------------------------------------------------------------------------
@@ -293,9 +305,11 @@ int pulse_reduce_slabs(const float* slabs, int64_t slab_stride, int32_t num_slab
 int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream);
 /* clip_grad_norm_(max_norm) + Adam step over one flat parameter buffer (amp_agent.py:725-750; torch.optim.Adam
  * defaults beta 0.9/0.999): scale = min(1, max_norm/(sqrt(sumsq)+1e-6)) read on the device, no host sync. */
-/* `step` is a DEVICE counter (int32[1]) incremented by this call, so the launch sequence is CUDA-graph replayable. */
+/* `step` is a DEVICE counter (int32[1]) incremented by this call, so the launch sequence is CUDA-graph replayable.
+ * params_bf16 (optional, same flat layout): bf16 copy of the updated parameters = the GEMM operands. */
 int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sumsq,
-                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, void* stream);
+                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, pulse_bf16_t* params_bf16,
+                    void* stream);
 /* refresh the bf16 operand copies of one weight matrix W fp32 [n, k] (contiguous):
  *   w_bf16 [n, ld_k] (K-major, forward / wgrad-free) and wt_bf16 [k, ld_n] (transposed, dgrad operand); pads zeroed. */
 int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,

@@ -76,7 +76,11 @@ class GemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int32), ("gate_mode", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
         ("alpha", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int64), ("out_t", C.c_void_p), ("ldot", C.c_int64),
         ("out_f32", C.c_void_p), ("ldf", C.c_int64), ("split_stride", C.c_int64), ("preact", C.c_void_p), ("ldp", C.c_int64),
+        ("colsum", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+GEMM_A_MN, GEMM_B_MN = 1, 2
 
 
 class PpoLossArgs(C.Structure):
@@ -106,6 +110,8 @@ SIGNATURES = {
     "pulse_normalize_advantages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pulse_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                      C.POINTER(GemmEpilogue), C.c_int32, C.c_void_p]),
+    "pulse_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                  C.POINTER(GemmEpilogue), C.c_int32, C.c_uint32, C.c_void_p]),
     "pulse_gemm_num_splits": (C.c_int, [C.c_int64, C.c_int32]),
     "pulse_normalize_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_int64, C.c_void_p]),
@@ -119,7 +125,7 @@ SIGNATURES = {
     "pulse_reduce_slabs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_sum_squares": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
-                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pulse_refresh_weight_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

@@ -80,16 +80,32 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   d |= static_cast<unsigned long long>(2u) << 61;
   return d;
 }
+// MN-major operand (the NON-reduction dimension is the contiguous one, e.g. dY[batch, n] or W[n, k_out] read as
+// the operand of a reduction over its rows): the stage holds two [64 reduction rows][64 elements] boxes
+// (8 KB each, 128-byte rows, 128B swizzle).  Canonical layout (cute make_umma_desc<Major::MN>, B128):
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> LBO = 8192 B between the 64-element MN chunks,
+// SBO = 1024 B between 8-row reduction groups.
+__device__ __forceinline__ unsigned long long umma_desc_mn(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= static_cast<unsigned long long>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<unsigned long long>(8192u >> 4) << 16;
+  d |= static_cast<unsigned long long>(1024u >> 4) << 32;
+  d |= static_cast<unsigned long long>(1u) << 46;
+  d |= static_cast<unsigned long long>(2u) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
-// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-constexpr unsigned kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<unsigned>(BN >> 3) << 17) |
-                                (static_cast<unsigned>(BM >> 4) << 24);
-__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+// a_major / b_major at bits 15 / 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr unsigned instr_desc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<unsigned>(BN >> 3) << 17) | (static_cast<unsigned>(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(kInstrDesc), "r"(accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
@@ -123,7 +139,9 @@ __device__ __forceinline__ float act_grad(float g, int mode) {
   return 1.0f;
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a,
+// A_MN / B_MN: operand is MN-major in global memory ([reduction rows, non-reduction cols] row-major) instead of K-major.
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_b,
                                                                       const pulse_gemm_epilogue_t ep, int M, int N, int K,
                                                                       int kb_per_split) {
@@ -164,8 +182,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
         const int s = kb % kStagesG;
         g_mbar_wait(&sm.empty[s], ((kb / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
         g_mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
-        tma_load_2d(sm.a[s], &map_a, (kb0 + kb) * BK, m0, &sm.full[s]);
-        tma_load_2d(sm.b[s], &map_b, (kb0 + kb) * BK, n0, &sm.full[s]);
+        const int kk = (kb0 + kb) * BK;
+        if (A_MN) {  // box = [64 reduction rows][64 contiguous m]: two boxes cover the 128-wide tile
+          tma_load_2d(sm.a[s], &map_a, m0, kk, &sm.full[s]);
+          tma_load_2d(sm.a[s] + 8192, &map_a, m0 + 64, kk, &sm.full[s]);
+        } else {
+          tma_load_2d(sm.a[s], &map_a, kk, m0, &sm.full[s]);
+        }
+        if (B_MN) {
+          tma_load_2d(sm.b[s], &map_b, n0, kk, &sm.full[s]);
+          tma_load_2d(sm.b[s] + 8192, &map_b, n0 + 64, kk, &sm.full[s]);
+        } else {
+          tma_load_2d(sm.b[s], &map_b, kk, n0, &sm.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -178,8 +207,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
         const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), (kb | k) != 0 ? 1u : 0u);
+          // K-major: 16 bf16 = 32 bytes inside the 128-byte swizzle atom; MN-major: 16 reduction rows = two 1024-byte groups
+          const unsigned long long da = A_MN ? umma_desc_mn(a_addr + k * 2048) : umma_desc(a_addr + k * 32);
+          const unsigned long long db = B_MN ? umma_desc_mn(b_addr + k * 2048) : umma_desc(b_addr + k * 32);
+          umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&sm.empty[s]);  // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
       }
@@ -251,7 +282,31 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_nt_kernel(const __g
             if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
         }
       }
-      if (outf != nullptr && row_ok) {
+      if (ep.colsum != nullptr) {
+        // column sums of this warp's 32x32 block by a shuffle reduce-scatter (31 shuffles): lane l ends up with
+        // the sum over the warp's 32 rows of column l (bias gradients without a second pass over dY)
+        float w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = row_ok ? v[i] : 0.0f;
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1) {
+          const bool upper = (lane & half) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float mine = upper ? w[i + half] : w[i];
+            const float send = upper ? w[i] : w[i + half];
+            w[i] = mine + __shfl_xor_sync(0xffffffffu, send, half);
+          }
+        }
+        // after the scatter, lane l holds column bitrev-free index: with this exchange pattern lane l owns column l
+        if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, w[0]);
+      }
+      if (outf != nullptr && row_ok && ep.accumulate) {
+        float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) atomicAdd(p + i, v[i]);
+      } else if (outf != nullptr && row_ok) {
         float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
         if (full && (ep.ldf & 3) == 0) {
 #pragma unroll
@@ -335,16 +390,32 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rows x cols bf16 matrix, row stride ld elements, box 128 rows x 64 cols, 128B swizzle, OOB reads return 0
-bool make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+// rows x cols bf16 matrix, row stride ld elements, box `box_rows` rows x 64 cols, 128B swizzle, OOB reads return 0.
+// K-major operand: rows = M (or N), cols = K, box 128 x 64.  MN-major operand: rows = K (reduction), cols = M (or N), box 64 x 64.
+bool make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, unsigned box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t box[2] = {BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_gemm_epilogue_t& ep, int m, int n, int k, int splits,
+                int kb_per_split, cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(GemmSmem) + 1024;  // slack so the kernel can align the ring to 1024 B
+  if (!attr_set) {
+    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>((n + BN - 1) / BN), static_cast<unsigned>((m + BM - 1) / BM), static_cast<unsigned>(splits));
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, smem, stream>>>(map_a, map_b, ep, m, n, k, kb_per_split);
+  PULSE_LAUNCH_OK("gemm_bf16_kernel");
+  return PULSE_OK;
 }
 
 }  // namespace
@@ -357,36 +428,42 @@ extern "C" int pulse_gemm_num_splits(int64_t k, int32_t split_k) {
   return (num_kb + kb_per_split - 1) / kb_per_split;  // every slab gets at least one k-block
 }
 
-extern "C" int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
-                                  const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream) {
+// flags: bit 0 = A is MN-major ([K, M] row-major in memory), bit 1 = B is MN-major ([K, N] row-major in memory)
+extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                               const pulse_gemm_epilogue_t* ep, int32_t split_k, uint32_t flags, void* stream) {
   using namespace pulse;
-  PULSE_REQUIRE(a && b && ep, "pulse_gemm_bf16_nt: null argument");
-  PULSE_REQUIRE(m > 0 && n > 0 && k > 0, "pulse_gemm_bf16_nt: empty problem %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
-  PULSE_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "pulse_gemm_bf16_nt: dimension too large");
-  PULSE_REQUIRE(lda >= k && ldb >= k && (lda % 8) == 0 && (ldb % 8) == 0, "pulse_gemm_bf16_nt: leading dimensions must be >= K and multiples of 8 (16-byte rows), got %lld %lld", (long long)lda, (long long)ldb);
-  PULSE_REQUIRE(aligned16(a) && aligned16(b), "pulse_gemm_bf16_nt: operands must be 16-byte aligned");
-  PULSE_REQUIRE(ep->out || ep->out_t || ep->out_f32, "pulse_gemm_bf16_nt: no output requested");
-  PULSE_REQUIRE(split_k >= 1, "pulse_gemm_bf16_nt: split_k must be >= 1");
-  PULSE_REQUIRE(split_k == 1 || (ep->out_f32 && !ep->out && !ep->out_t && !ep->bias && ep->act == PULSE_ACT_NONE && !ep->gate && !ep->preact),
-                "pulse_gemm_bf16_nt: split-K only supports plain fp32 partial slabs");
-  PULSE_REQUIRE(ep->gate == nullptr || ep->gate_mode == PULSE_ACT_RELU || ep->gate_mode == PULSE_ACT_SILU, "pulse_gemm_bf16_nt: bad gate_mode");
+  PULSE_REQUIRE(a && b && ep, "pulse_gemm_bf16: null argument");
+  PULSE_REQUIRE(m > 0 && n > 0 && k > 0, "pulse_gemm_bf16: empty problem %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
+  PULSE_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "pulse_gemm_bf16: dimension too large");
+  PULSE_REQUIRE((flags & ~3u) == 0, "pulse_gemm_bf16: bad flags");
+  const bool a_mn = flags & PULSE_GEMM_A_MN, b_mn = flags & PULSE_GEMM_B_MN;
+  PULSE_REQUIRE(lda >= (a_mn ? m : k) && ldb >= (b_mn ? n : k) && (lda % 8) == 0 && (ldb % 8) == 0,
+                "pulse_gemm_bf16: leading dimensions must cover the contiguous extent and be multiples of 8 (16-byte rows), got %lld %lld",
+                (long long)lda, (long long)ldb);
+  PULSE_REQUIRE(aligned16(a) && aligned16(b), "pulse_gemm_bf16: operands must be 16-byte aligned");
+  PULSE_REQUIRE(ep->out || ep->out_t || ep->out_f32, "pulse_gemm_bf16: no output requested");
+  PULSE_REQUIRE(split_k >= 1, "pulse_gemm_bf16: split_k must be >= 1");
+  PULSE_REQUIRE(split_k == 1 || (ep->out_f32 && !ep->out && !ep->out_t && !ep->bias && ep->act == PULSE_ACT_NONE && !ep->gate && !ep->preact && !ep->colsum),
+                "pulse_gemm_bf16: split-K only supports plain fp32 outputs (slabs or atomic accumulation)");
+  PULSE_REQUIRE(ep->gate == nullptr || ep->gate_mode == PULSE_ACT_RELU || ep->gate_mode == PULSE_ACT_SILU, "pulse_gemm_bf16: bad gate_mode");
   CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, a, m, k, lda) || !make_map(&map_b, b, n, k, ldb)) {
-    set_error("pulse_gemm_bf16_nt: cuTensorMapEncodeTiled failed (driver entry point missing or bad strides)");
+  const bool ok_a = a_mn ? make_map(&map_a, a, k, m, lda, 64) : make_map(&map_a, a, m, k, lda, BM);
+  const bool ok_b = b_mn ? make_map(&map_b, b, k, n, ldb, 64) : make_map(&map_b, b, n, k, ldb, BN);
+  if (!ok_a || !ok_b) {
+    set_error("pulse_gemm_bf16: cuTensorMapEncodeTiled failed (driver entry point missing or bad strides)");
     return PULSE_ERR_CUDA;
-  }
-  static bool attr_set = false;
-  const size_t smem = sizeof(GemmSmem) + 1024;  // slack so the kernel can align the ring to 1024 B
-  if (!attr_set) {
-    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   const int num_kb = static_cast<int>((k + BK - 1) / BK);
   const int splits = pulse_gemm_num_splits(k, split_k);
   const int kb_per_split = (num_kb + splits - 1) / splits;
-  dim3 grid(static_cast<unsigned>((n + BN - 1) / BN), static_cast<unsigned>((m + BM - 1) / BM), static_cast<unsigned>(splits));
-  gemm_bf16_nt_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, *ep, (int)m, (int)n, (int)k,
-                                                                                      kb_per_split);
-  PULSE_LAUNCH_OK("gemm_bf16_nt_kernel");
-  return PULSE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a_mn && b_mn) return launch_gemm<true, true>(map_a, map_b, *ep, (int)m, (int)n, (int)k, splits, kb_per_split, st);
+  if (a_mn) return launch_gemm<true, false>(map_a, map_b, *ep, (int)m, (int)n, (int)k, splits, kb_per_split, st);
+  if (b_mn) return launch_gemm<false, true>(map_a, map_b, *ep, (int)m, (int)n, (int)k, splits, kb_per_split, st);
+  return launch_gemm<false, false>(map_a, map_b, *ep, (int)m, (int)n, (int)k, splits, kb_per_split, st);
+}
+
+extern "C" int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                                  const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream) {
+  return pulse_gemm_bf16(a, lda, b, ldb, m, n, k, ep, split_k, 0u, stream);
 }

@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(256) sum_squares_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long count, const double* __restrict__ sumsq, float max_norm,
-                                                   float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr) {
+                                                   float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr,
+                                                   __nv_bfloat16* __restrict__ p_bf16) {
   const float step = static_cast<float>(*step_ptr);  // already incremented by bump_step_kernel
   const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
   float scale = 1.0f;
@@ -288,7 +289,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     m[i] = mi;
     v[i] = vi;
     // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    const float pn = p[i] - (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    p[i] = pn;
+    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16(pn);  // the GEMM operand copy shares the flat layout
   }
 }
 
@@ -411,12 +414,13 @@ extern "C" int pulse_sum_squares(const float* x, int64_t count, double* sumsq, v
 
 extern "C" int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                                const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step,
-                               void* stream) {
+                               pulse_bf16_t* params_bf16, void* stream) {
   PULSE_REQUIRE(params && grads && exp_avg && exp_avg_sq && count > 0 && step != nullptr, "pulse_adam_step: bad argument");
   bump_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step);
   PULSE_LAUNCH_OK("bump_step_kernel");
   adam_kernel<<<grid_for(count, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, count, grad_sumsq,
-                                                                                       max_norm, lr, beta1, beta2, eps, step);
+                                                                                       max_norm, lr, beta1, beta2, eps, step,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(params_bf16));
   PULSE_LAUNCH_OK("adam_kernel");
   return PULSE_OK;
 }

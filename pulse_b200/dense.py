@@ -22,16 +22,24 @@ def num_splits(k: int, split_k: int) -> int:
     return int(_lib.load().pulse_gemm_num_splits(k, split_k))
 
 
-def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act=None, gate: Optional[torch.Tensor] = None,
-            gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None, out_t: Optional[torch.Tensor] = None,
-            out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None, split_k: int = 1) -> None:
+def gemm_nt(a, b, **kw) -> None:
+    """a [M,K] . b [N,K]^T (both K-major)."""
+    gemm(a, b, **kw)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None, act=None,
+         gate: Optional[torch.Tensor] = None, gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
+         out_t: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
+         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1) -> None:
+    """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  a is [M,K] (K-major) or, with a_mn, [K,M] (MN-major: the reduction index
+    is the row); likewise b is [N,K] or, with b_mn, [K,N].  No operand is ever transposed in memory."""
     lib = _lib.load()
     _check_bf16(a, "a")
     _check_bf16(b, "b")
-    M, K = a.shape
-    N, Kb = b.shape
+    (K, M) = a.shape if a_mn else (a.shape[1], a.shape[0])
+    (Kb, N) = b.shape if b_mn else (b.shape[1], b.shape[0])
     if K != Kb:
-        raise _lib.PulseError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
+        raise _lib.PulseError(f"K mismatch: a {tuple(a.shape)} (mn={a_mn}) vs b {tuple(b.shape)} (mn={b_mn})")
     ep = _lib.GemmEpilogue()
     ep.alpha = alpha
     ep.act = ACT[act] if not isinstance(act, int) else act
@@ -64,10 +72,16 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = 
                 raise _lib.PulseError("out_f32 has fewer slabs than split-K needs")
             ep.split_stride, ep.ldf = out_f32.stride(0), out_f32.stride(1)
         else:
-            if split_k != 1:
-                raise _lib.PulseError("split_k > 1 needs a [splits, M, N] out_f32")
+            if split_k != 1 and not accumulate:
+                raise _lib.PulseError("split_k > 1 needs a [splits, M, N] out_f32 or accumulate=True")
             ep.ldf = out_f32.stride(0)
         ep.out_f32 = out_f32.data_ptr()
+        ep.accumulate = int(accumulate)
+    if colsum is not None:
+        if colsum.dtype != torch.float32 or colsum.numel() < N:
+            raise _lib.PulseError("colsum must be fp32 [N]")
+        ep.colsum = colsum.data_ptr()
+    flags = (_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0)
     with torch.cuda.device(a.device):
-        _lib.check(lib.pulse_gemm_bf16_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, C.byref(ep), split_k,
-                                          _lib.current_stream(a.device)), "pulse_gemm_bf16_nt")
+        _lib.check(lib.pulse_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, C.byref(ep), split_k, flags,
+                                       _lib.current_stream(a.device)), "pulse_gemm_bf16")

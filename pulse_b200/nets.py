@@ -3,12 +3,14 @@
 Mirrors what `phc.learning.network_builder.NetworkBuilder._build_mlp` + `AMPBuilder.Network`
 (network_builder.py:105-124, amp_network_builder.py:20-249) build -- Linear+activation stacks with a
 linear head -- but stores them for the tcgen05 GEMM: fp32 master weights in ONE flat buffer (so the
-gradient all-reduce, the norm clip and Adam are single launches), bf16 K-major operand copies of W
-and W^T refreshed after every optimizer step, activations (and their transposes, the operands of
-the weight-gradient GEMMs) written by the GEMM epilogues.
+gradient all-reduce, the norm clip and Adam are single launches) with a bf16 mirror in the same
+layout that the Adam kernel writes -- the GEMM operands.  Nothing is ever transposed in memory: the
+GEMM reads K-major or MN-major operands as they sit (forward: X, W K-major; dgrad: dY K-major, W
+MN-major; wgrad: dY, X MN-major).
 
-Forward / backward are explicit (no autograd): forward Y = act(X W^T + b); dgrad dX = (dY W) * act'(.);
-wgrad dW = dY^T X via split-K fp32 slabs; db = column sums of dY.
+Forward / backward are explicit (no autograd): forward Y = act(X W^T + b); dgrad dX = (dY W) * act'(.)
+with the bias gradient of the layer below (column sums of dX) fused into its epilogue; wgrad
+dW = dY^T X accumulated with fp32 atomics across split-K CTAs straight into the flat gradient buffer.
 """
 import ctypes as C
 import math
@@ -17,7 +19,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _lib
-from .dense import gemm_nt, num_splits
+from .dense import gemm, gemm_nt
 
 
 def pad8(n: int) -> int:
@@ -40,15 +42,20 @@ class FlatParams:
         n = 1
         for s in shape:
             n *= s
-        self._numel += (n + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self._numel += (n + 7) // 8 * 8  # every tensor 16-byte aligned in the fp32 AND the bf16 buffer
         self._shapes.append((off, tuple(shape)))
         return len(self._shapes) - 1
 
     def finalize(self):
         z = lambda: torch.zeros(self._numel, device=self.device, dtype=torch.float32)
         self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        self.params_bf16 = torch.zeros(self._numel, device=self.device, dtype=torch.bfloat16)
         self.sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
+
+    def sync_bf16(self):
+        """bf16 mirror <- fp32 masters (after init / checkpoint load; the Adam kernel keeps it current afterwards)."""
+        self.params_bf16.copy_(self.params)
 
     def view(self, idx: int, what: str = "params") -> torch.Tensor:
         off, shape = self._shapes[idx]
@@ -56,6 +63,11 @@ class FlatParams:
         for s in shape:
             n *= s
         return getattr(self, what)[off:off + n].view(*shape)
+
+    def view_padded(self, idx: int, what: str, n: int) -> torch.Tensor:
+        """first n elements of slot idx INCLUDING its alignment padding (slots are padded to multiples of 8)."""
+        off, _ = self._shapes[idx]
+        return getattr(self, what)[off:off + n]
 
     @property
     def numel(self):
@@ -75,7 +87,8 @@ class FlatParams:
                 _lib.check(lib.pulse_sum_squares(self.grads.data_ptr(), self._numel, self.sumsq.data_ptr(), st), "pulse_sum_squares")
                 sumsq_ptr = self.sumsq.data_ptr()
             _lib.check(lib.pulse_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                           self._numel, sumsq_ptr, float(max_norm or 0.0), lr, betas[0], betas[1], eps, self.step.data_ptr(), st),
+                                           self._numel, sumsq_ptr, float(max_norm or 0.0), lr, betas[0], betas[1], eps, self.step.data_ptr(),
+                                           self.params_bf16.data_ptr(), st),
                        "pulse_adam_step")
 
 
@@ -88,7 +101,6 @@ class Dense:
         self.flat = flat
         self.w_idx = flat.reserve(out_features, self.Kp)
         self.b_idx = flat.reserve(out_features)
-        self.w_bf16 = self.wt_bf16 = None
 
     # views (valid after flat.finalize())
     @property
@@ -98,6 +110,10 @@ class Dense:
     @property
     def bias(self):
         return self.flat.view(self.b_idx)
+
+    @property
+    def w_bf16(self):
+        return self.flat.view(self.w_idx, "params_bf16")
 
     @property
     def weight_grad(self):
@@ -121,15 +137,8 @@ class Dense:
         self.refresh()
 
     def refresh(self):
-        """bf16 operand copies: W [N, Kp] for forward, W^T [Kp, Np] for dgrad."""
-        lib = _lib.load()
-        dev = self.flat.device
-        if self.w_bf16 is None:
-            self.w_bf16 = torch.zeros(self.N, self.Kp, device=dev, dtype=torch.bfloat16)
-            self.wt_bf16 = torch.zeros(self.Kp, self.Np, device=dev, dtype=torch.bfloat16)
-        with torch.cuda.device(dev):
-            _lib.check(lib.pulse_refresh_weight_bf16(self.weight.data_ptr(), self.N, self.Kp, self.w_bf16.data_ptr(), self.Kp,
-                                                     self.wt_bf16.data_ptr(), self.Np, _lib.current_stream(dev)), "pulse_refresh_weight_bf16")
+        """bf16 operand copy of this layer (init / load path; Adam maintains it during training)."""
+        self.w_bf16.copy_(self.weight)
 
 
 class MLP:
@@ -158,27 +167,23 @@ class MLP:
         if key not in self._ws:
             dev = self.flat.device
             bf = lambda r, c: torch.zeros(r, c, device=dev, dtype=torch.bfloat16)
-            ws = {"act": [], "act_t": [], "pre": [], "dact": [], "dact_t": [], "slabs": []}
+            ws = {"act": [], "pre": [], "dact": [], "split": []}
             for i, l in enumerate(self.layers):
                 last = i == len(self.layers) - 1
                 ws["act"].append(None if last else bf(M, l.Np))
                 if train:
-                    ws["act_t"].append(None if last else bf(l.Np, M))
                     ws["pre"].append(bf(M, l.Np) if (l.act == "silu") else None)
                     ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
-                    ws["dact_t"].append(None if last else bf(l.Np, M))
                     tiles = ((l.N + 127) // 128) * ((l.Kp + 127) // 128)
-                    want = max(1, min(64, (2 * 148 + tiles - 1) // tiles))
-                    ns = num_splits(M, want)
-                    ws["slabs"].append((want, torch.zeros(ns, l.N, l.Kp, device=dev)))
+                    ws["split"].append(max(1, min(64, (2 * 148 + tiles - 1) // tiles)))  # wgrad split-K: ~2 CTAs per SM
             ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
             self._ws[key] = ws
         return self._ws[key]
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, train: bool = False, x_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, train: bool = False) -> torch.Tensor:
         """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer).
-        With train=True the activations / transposes needed by backward() are kept; x_t = x^T bf16 [Kp0, M]."""
+        With train=True the activations (and SiLU pre-activations) needed by backward() are kept."""
         M = x.shape[0]
         ws = self._workspace(M, train)
         h = x
@@ -187,41 +192,37 @@ class MLP:
             if last:
                 gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
             else:
-                gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], out_t=ws["act_t"][i] if train else None,
-                        preact=ws["pre"][i] if train else None)
+                gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)
                 h = ws["act"][i]
         if train:
-            ws["x"], ws["x_t"] = x, x_t
+            ws["x"] = x
         return ws["out"]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dout: torch.Tensor, dout_t: torch.Tensor, M: int) -> None:
-        """dout bf16 [M, pad8(head)], dout_t bf16 [head, M]: gradient of the loss w.r.t. the head output.
-        Accumulates dW, db of every layer into the flat gradient buffer (overwrites the layer's slots)."""
+    def backward(self, dout: torch.Tensor, M: int) -> None:
+        """dout bf16 [M, pad8(head)]: gradient of the loss w.r.t. the head output.  ADDS dW, db of every layer into the
+        flat gradient buffer (the caller zeroes it once per minibatch with flat.zero_grad())."""
         lib = _lib.load()
         ws = self._ws[(M, True)]
         dev = self.flat.device
-        dy, dy_t = dout, dout_t
+        dy = dout
+        head = self.layers[-1]
+        with torch.cuda.device(dev):  # bias gradient of the head: column sums of dout
+            _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
+                       "pulse_column_sum_bf16")
         for i in reversed(range(len(self.layers))):
             l = self.layers[i]
             x_in = ws["x"] if i == 0 else ws["act"][i - 1]
-            x_in_t = ws["x_t"] if i == 0 else ws["act_t"][i - 1]
-            want, slabs = ws["slabs"][i]
-            # wgrad: dW [N, Kp] = dY^T [N, M] . X [M, Kp]  (A = dY^T, B = X^T, reduction over M)
-            gemm_nt(dy_t[:l.N], x_in_t[:l.Kp], out_f32=slabs, split_k=want)
-            with torch.cuda.device(dev):
-                st = _lib.current_stream(dev)
-                _lib.check(lib.pulse_reduce_slabs(slabs.data_ptr(), slabs.stride(0), slabs.shape[0], l.N * l.Kp, l.weight_grad.data_ptr(), st),
-                           "pulse_reduce_slabs")
-                bg = l.bias_grad
-                bg.zero_()
-                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, l.N, bg.data_ptr(), st), "pulse_column_sum_bf16")
+            # wgrad: dW [N, Kp] += dY^T . X, both operands MN-major (reduction over the batch rows), fp32 atomics across split-K
+            gemm(dy[:, :l.N], x_in[:, :l.Kp], a_mn=True, b_mn=True, out_f32=l.weight_grad, accumulate=True, split_k=ws["split"][i])
             if i > 0:
                 prev = self.layers[i - 1]
-                # dgrad: dX [M, K] = dY [M, N] . W [N, K], gated by act'(.) of the previous layer
+                # dgrad: dX [M, K] = dY [M, N] . W [N, K] (W read MN-major), gated by act'(.) of the layer below; the epilogue
+                # also accumulates that layer's bias gradient (column sums of dX)
                 gate = ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1]
-                gemm_nt(dy[:, :l.N], l.wt_bf16[:, :l.N], gate=gate, gate_mode=prev.act, out=ws["dact"][i - 1], out_t=ws["dact_t"][i - 1])
-                dy, dy_t = ws["dact"][i - 1], ws["dact_t"][i - 1]
+                gemm(dy[:, :l.N], l.w_bf16, b_mn=True, gate=gate, gate_mode=prev.act, out=ws["dact"][i - 1],
+                     colsum=self.flat.view_padded(prev.b_idx, "grads", prev.Np))
+                dy = ws["dact"][i - 1]
 
     # ------------------------------------------------------------------ checkpoint names
     def state_dict(self, prefix: str, head_name: Optional[str] = None) -> Dict[str, torch.Tensor]:
@@ -247,7 +248,7 @@ class MLP:
 
 
 def normalize_to_bf16(x: torch.Tensor, mean: Optional[torch.Tensor], rstd: Optional[torch.Tensor], out: torch.Tensor,
-                      out_t: Optional[torch.Tensor] = None) -> None:
+                      out_t: Optional[torch.Tensor] = None) -> None:  # out_t: optional transposed copy (not used by the MLPs any more)
     """RunningMeanStd eval path (running_mean_std.py:69-95) fused with the bf16 cast / zero pad / transpose."""
     lib = _lib.load()
     rows, cols = x.shape

@@ -96,9 +96,7 @@ class PPOPolicy:
             b = {"x": torch.zeros(M, self.Kp, device=dev, dtype=torch.bfloat16)}
             if train:
                 Ap = pad8(self.A)
-                b.update(x_t=torch.zeros(self.Kp, M, device=dev, dtype=torch.bfloat16),
-                         dmu=torch.zeros(M, Ap, device=dev, dtype=torch.bfloat16), dmu_t=torch.zeros(Ap, M, device=dev, dtype=torch.bfloat16),
-                         dv=torch.zeros(M, 8, device=dev, dtype=torch.bfloat16), dv_t=torch.zeros(8, M, device=dev, dtype=torch.bfloat16))
+                b.update(dmu=torch.zeros(M, Ap, device=dev, dtype=torch.bfloat16), dv=torch.zeros(M, 8, device=dev, dtype=torch.bfloat16))
             else:
                 b.update(actions=torch.zeros(M, self.A, device=dev), neglogp=torch.zeros(M, device=dev))
             self._bufs[key] = b
@@ -139,30 +137,28 @@ class PPOPolicy:
         stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
         M = obs.shape[0]
         b = self._buf(M, True)
-        self.obs_rms.normalize_into(obs, b["x"], b["x_t"])  # normalise with the statistics BEFORE this batch's update
+        self.obs_rms.normalize_into(obs, b["x"])            # normalise with the statistics BEFORE this batch's update
         if update_obs_rms:
             self.obs_rms.update(obs)                         # running_mean_std.py:96-107 (train mode)
-        mu = self.actor.forward(b["x"], train=True, x_t=b["x_t"])
-        value = self.critic.forward(b["x"], train=True, x_t=b["x_t"])
+        mu = self.actor.forward(b["x"], train=True)
+        value = self.critic.forward(b["x"], train=True)
         a = _lib.PpoLossArgs(
             mu=mu.data_ptr(), ld_mu=mu.stride(0), value=value.data_ptr(), ld_value=value.stride(0), actions=actions.data_ptr(),
             old_neglogp=old_neglogp.data_ptr(), advantages=advantages.data_ptr(), returns=returns.data_ptr(),
             old_mu=old_mu.data_ptr() if old_mu is not None else None, logstd=self.logstd.data_ptr(), num_actions=self.A,
             e_clip=self.e_clip, critic_coef=self.critic_coef, bounds_coef=self.bounds_coef,
-            dmu=b["dmu"].data_ptr(), ld_dmu=b["dmu"].stride(0), dmu_t=b["dmu_t"].data_ptr(), ld_dmu_t=b["dmu_t"].stride(0),
-            dvalue=b["dv"].data_ptr(), ld_dv=b["dv"].stride(0), dvalue_t=b["dv_t"].data_ptr(), ld_dv_t=b["dv_t"].stride(0),
+            dmu=b["dmu"].data_ptr(), ld_dmu=b["dmu"].stride(0), dvalue=b["dv"].data_ptr(), ld_dv=b["dv"].stride(0),
             stats=self.stats.data_ptr())
         self.stats.zero_()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream(self.device)), "pulse_ppo_loss")
-        self.actor.backward(b["dmu"], b["dmu_t"], M)
-        self.critic.backward(b["dv"], b["dv_t"], M)
+        self.flat.zero_grad()                                # weight / bias gradients are accumulated with atomics
+        self.actor.backward(b["dmu"], M)
+        self.critic.backward(b["dv"], M)
         if world_size > 1:
             from .dist_utils import average_gradients
             average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)
-        self.flat.adam_step(self.lr, max_norm=self.grad_norm)
-        self.actor.refresh()
-        self.critic.refresh()
+        self.flat.adam_step(self.lr, max_norm=self.grad_norm)  # also writes the bf16 operand mirror
         return self.stats
 
     # ------------------------------------------------------------------ checkpoint keys (rl_games layout)

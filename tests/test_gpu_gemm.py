@@ -74,6 +74,35 @@ def test_gemm_split_k_slabs():
     torch.testing.assert_close(slabs.sum(0), _ref(a, b)[0], atol=3e-3, rtol=3e-3)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 384, 960), (300, 200, 136), (1024, 960, 16384), (69, 512, 4096)])
+def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
+    """dgrad / wgrad forms: operands consumed as they sit in memory (reduction index = row index)."""
+    from pulse_b200.dense import gemm
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + 3 * N + 7 * K + a_mn + 2 * b_mn)
+    pad = lambda n: (n + 7) // 8 * 8
+    A = torch.randn(M, K, device=dev, generator=g)
+    B = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
+    a = torch.zeros(K, pad(M), device=dev, dtype=torch.bfloat16)[:, :M] if a_mn else torch.zeros(M, pad(K), device=dev, dtype=torch.bfloat16)[:, :K]
+    b = torch.zeros(K, pad(N), device=dev, dtype=torch.bfloat16)[:, :N] if b_mn else torch.zeros(N, pad(K), device=dev, dtype=torch.bfloat16)[:, :K]
+    a.copy_(A.T if a_mn else A)
+    b.copy_(B.T if b_mn else B)
+    ref = (a.float().T if a_mn else a.float()) @ (b.float() if b_mn else b.float().T)
+    of = torch.zeros(M, N, device=dev)
+    gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=of)
+    torch.testing.assert_close(of, ref, atol=3e-3, rtol=3e-3)
+    # atomic accumulation across split-K + column sums of the result
+    acc = torch.ones(M, N, device=dev)
+    gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_f32=acc, accumulate=True, split_k=3)
+    torch.testing.assert_close(acc - 1.0, ref, atol=5e-3, rtol=5e-3)
+    cs = torch.zeros(N, device=dev)
+    ob = torch.zeros(M, pad(N), device=dev, dtype=torch.bfloat16)
+    gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=ob, colsum=cs)
+    torch.testing.assert_close(cs, ref.sum(0), atol=2e-2 * M ** 0.5, rtol=2e-2)
+    torch.testing.assert_close(ob[:, :N].float(), ref, atol=2e-2, rtol=2e-2)
+
+
 def test_gemm_rejects_bad_arguments():
     from pulse_b200 import PulseError
     from pulse_b200.dense import gemm_nt
