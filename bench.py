@@ -124,7 +124,8 @@ def cpu_port_rate(n_envs, n_iters, threads, gae=True):
     def mlp(i, o):
         return torch.nn.Sequential(torch.nn.Linear(i, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512), torch.nn.ReLU(), torch.nn.Linear(512, o))
     actor, critic, disc = mlp(934, 69), mlp(934, 1), mlp(1960, 1)
-    opt = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=2e-5, eps=1e-8)
+    params = list(actor.parameters()) + list(critic.parameters()) + list(disc.parameters())
+    opt = torch.optim.Adam(params, lr=2e-5, eps=1e-8)
     obs = torch.randn(n_envs, 934)
     ampx = torch.randn(n_envs, 1960)
     logstd = torch.full((69,), -2.9)
@@ -143,9 +144,12 @@ def cpu_port_rate(n_envs, n_iters, threads, gae=True):
     def update_minibatch(a_, nlp):
         x = torch.clamp(obs, -5, 5)
         out = po.ppo_total_loss(actor(x), critic(x).squeeze(1), nlp, adv_b, ret_b, a_, logstd)
+        q = max(1, n_envs // 4)            # amp_minibatch_size / minibatch_size = 4096 / 16384
+        ax = torch.clamp(ampx, -5, 5)
+        dl = po.disc_loss(disc, ax[:q], ax[q:2 * q], ax[2 * q:3 * q], disc[4].weight, [disc[0].weight, disc[2].weight, disc[4].weight])
         opt.zero_grad(set_to_none=True)
-        out["loss"].backward()
-        torch.nn.utils.clip_grad_norm_(list(actor.parameters()) + list(critic.parameters()), 50.0)
+        (out["loss"] + 5.0 * dl["disc_loss"]).backward()
+        torch.nn.utils.clip_grad_norm_(params, 50.0)
         opt.step()
 
     one_env_step()
@@ -211,9 +215,10 @@ def workload_config(a, world, envs_total):
                    "32x critic fwd on next obs (next_values)", "discriminator fwd + AMP reward over 32xN rows (K10)",
                    "GAE + returns + adv-norm (K11,K12)", "value/return normalisation (running stats)",
                    f"{MINI_EPOCHS} mini-epochs x minibatches: obs-RMS update, actor/critic fwd, PPO loss, bwd (dgrad+wgrad), "
-                   "NCCL grad all-reduce (N>1), grad-norm clip + Adam, bf16 weight refresh (K13,K15,K16)"],
-        "not_yet": ["discriminator UPDATE (BCE + logit reg + gradient penalty, K14) and AMP replay/demo buffers",
-                    "action -> PD target (K22)"],
+                   "discriminator loss on 3x4096 AMP rows: BCE + logit reg + weight decay + ANALYTIC gradient penalty (K14), "
+                   "NCCL grad all-reduce (N>1), grad-norm clip + Adam incl. bf16 operand mirror (K13,K15,K16)",
+                   "AMP demo fetch (MotionLib query + AMP obs), demo / replay ring updates and per-minibatch draws"],
+        "not_yet": ["action -> PD target (K22, four element-wise ops feeding Isaac Gym)"],
         "physics": "excluded (Isaac Gym not installable; simulator state tensors are synthetic, resident in HBM)",
         "l2": "256 MiB L2 flush write before every timed iteration; per-iteration working set (tables 3.9 GB + 6 GB rollout buffers at N=1) exceeds L2",
     }
@@ -228,7 +233,12 @@ def mlp_flops_per_env_step():
     # update: fwd + wgrad for every layer, dgrad for all but the first layer of each net
     dgrad_a = 1024 * 512 + 512 * 69
     dgrad_c = 1024 * 512 + 512 * 1
-    update = MINI_EPOCHS * (2 * (a + c) + dgrad_a + dgrad_c)
+    # discriminator update: 3 x 4096 rows per 16384-row minibatch (0.75 rows/row): fwd + wgrad + dgrad(2 upper layers),
+    # plus on the 4096 demo rows the analytic gradient penalty: 2 input-gradient GEMMs + 2 wgrad + 2 NT GEMMs
+    dg = 1024 * 512 + 512 * 1
+    gp = (512 * 1024 + 1024 * 1960) + (1024 * 1960 + 512 * 1024) + (1960 * 1024 + 1024 * 512)
+    disc_upd = MINI_EPOCHS * (0.75 * (2 * d + dg) + 0.25 * gp)
+    update = MINI_EPOCHS * (2 * (a + c) + dgrad_a + dgrad_c) + disc_upd
     return 2.0 * (rollout + update)
 
 
@@ -241,8 +251,8 @@ def main():
     from pulse_b200 import _lib
     from pulse_b200.humanoid_im import HumanoidImCompute
     from pulse_b200.motion_lib import MotionLibB200
-    from pulse_b200.nets import MLP, FlatParams, pad8
-    from pulse_b200.ppo import PPOPolicy, RunningMeanStdB200
+    from pulse_b200.nets import pad8
+    from pulse_b200.ppo import PPOPolicy
     from pulse_b200.rollout import discount_values
     from tools.synth import device_step_inputs, device_tables
 
@@ -266,13 +276,16 @@ def main():
     del tabs
     z = device_step_inputs(ml, n, seed=200 + rank)
     comp = HumanoidImCompute(ml)
-    policy = PPOPolicy(device=dev, seed=0)            # replicated: same seed on every rank (Horovod broadcast equivalent)
-    dflat = FlatParams(dev)
-    disc = MLP(dflat, 1960, (1024, 512), 1, "relu")   # discriminator, forward only here (amp_network_builder.py:230-249)
-    dflat.finalize()
-    disc.init_default(torch.Generator(device=dev).manual_seed(1))
-    amp_rms = RunningMeanStdB200(1960, dev)
+    policy = PPOPolicy(device=dev, seed=0, with_disc=True)   # replicated: same seed on every rank (Horovod broadcast equivalent)
+    disc = policy.disc
     amp_x = torch.zeros(T * n, pad8(1960), device=dev, dtype=torch.bfloat16)
+    AMP_MB = 4096                                        # amp_minibatch_size (im.yaml:81)
+    REPLAY = 200000                                      # amp_replay_buffer_size / amp_obs_demo_buffer_size (im.yaml:77-78)
+    replay_buf = torch.randn(REPLAY, 1960, device=dev)   # AMP replay ring (amp_agent.py:1043-1057), pre-filled
+    demo_buf = comp.fetch_amp_obs_demo(512).repeat((REPLAY + 511) // 512, 1)[:REPLAY].contiguous()   # demo ring (_init_amp_demo_buf)
+    replay_mb = torch.zeros(num_mb, AMP_MB, 1960, device=dev)
+    demo_mb = torch.zeros(num_mb, AMP_MB, 1960, device=dev)
+    ring_pos = [0]
 
     # experience buffers, ENV-MAJOR so a minibatch (512 envs x 32 steps) is a contiguous row range
     obses = torch.zeros(n, T, 934, device=dev)
@@ -280,7 +293,7 @@ def main():
     actions = torch.zeros(n, T, 69, device=dev)
     mus = torch.zeros(n, T, 69, device=dev)
     neglogp = torch.zeros(n, T, device=dev)
-    amp_obs = torch.zeros(T, n, 1960, device=dev)
+    amp_obs = torch.zeros(n, T, 1960, device=dev)      # env-major like the other experience tensors
     values = torch.zeros(T, n, 1, device=dev)
     next_values = torch.zeros(T, n, 1, device=dev)
     rewards = torch.zeros(T, n, device=dev)
@@ -332,7 +345,7 @@ def main():
     def post_step(t, e2e):
         nxt = obses[:, t + 1] if t + 1 < T else obs_carry
         comp.amp_obs(body_state=z["body_state"], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], amp_obs_buf=amp_buf)
-        amp_obs[t].copy_(amp_buf.view(n, 1960))
+        amp_obs[:, t].copy_(amp_buf.view(n, 1960))
         dones[t].copy_(reset_buf)
         nv = policy.critic_values(nxt)                       # _eval_critic on the next obs (amp_agent.py:396-398)
         next_values[t].copy_(nv * (1.0 - term_buf.unsqueeze(1).float()))
@@ -343,11 +356,19 @@ def main():
 
     def post_rollout():
         # discriminator reward over the whole horizon (amp_agent.py:422-424, :1027-1041)
-        amp_rms.normalize_into(amp_obs.view(T * n, 1960), amp_x)
-        logits = disc.forward(amp_x)
-        prob = 1.0 / (1.0 + torch.exp(-logits))
-        disc_r = -torch.log(torch.clamp(1.0 - prob, min=1e-4)) * 2.0
-        mb_rewards = 0.5 * rewards.unsqueeze(-1) + 0.5 * disc_r.view(T, n, 1)   # _combine_rewards, task_w = disc_w = 0.5
+        disc_r = disc.rewards(amp_obs.view(n * T, 1960), amp_x)                  # env-major [n*T, 1]
+        mb_rewards = 0.5 * rewards.unsqueeze(-1) + 0.5 * disc_r.view(n, T).t().unsqueeze(-1)   # _combine_rewards, task_w = disc_w = 0.5
+        # AMP demo / replay bookkeeping of train_epoch (amp_agent.py:476-483, :998-1001, :1043-1057): new demo samples into the
+        # demo ring, this rollout's AMP observations into the replay ring, one random draw per minibatch from each
+        new_demo = comp.fetch_amp_obs_demo(512)
+        p0 = ring_pos[0] % (REPLAY - 512)
+        demo_buf[p0:p0 + 512].copy_(new_demo)
+        idx = torch.randint(0, REPLAY, (num_mb * AMP_MB,), device=dev)
+        torch.index_select(replay_buf, 0, idx, out=replay_mb.view(-1, 1960))
+        idx2 = torch.randint(0, REPLAY, (num_mb * AMP_MB,), device=dev)
+        torch.index_select(demo_buf, 0, idx2, out=demo_mb.view(-1, 1960))
+        keep = torch.randint(0, n * T, (2048,), device=dev)                       # amp_replay_keep_prob 0.01 of the batch
+        replay_buf[p0:p0 + 2048].copy_(amp_obs.view(n * T, 1960)[keep])
         adv, ret = discount_values(dones, values, mb_rewards, next_values, normalize_advantage=True)
         # value / return normalisation in train mode (prepare_dataset, common_agent.py:372-374)
         policy.value_rms.update(values.view(T, n).t().reshape(T * n, 1))
@@ -357,7 +378,9 @@ def main():
 
     def update_mb(i):
         r0, r1 = i * MINIBATCH, (i + 1) * MINIBATCH
-        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], adv_buf[r0:r1], ret_buf[r0:r1], old_mu=mu_f[r0:r1], world_size=world)
+        amp_f = amp_obs.view(n * T, 1960)
+        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], adv_buf[r0:r1], ret_buf[r0:r1], old_mu=mu_f[r0:r1], world_size=world,
+                               amp=(amp_f[r0:r0 + AMP_MB], replay_mb[i], demo_mb[i]))   # amp_obs[0:amp_minibatch_size] (amp_agent.py:621-628)
 
     # ---- CUDA graphs: every launch sequence with fixed buffers is captured once and replayed -----------------
     use_graphs = os.environ.get("PULSE_NO_GRAPHS", "0") != "1"
@@ -454,8 +477,11 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (k_avg * 1e-3) / 1e9
     env_steps = T * a.envs
+    _d = 1960 * 1024 + 1024 * 512 + 512
+    _gp = 3 * (512 * 1024 + 1024 * 1960)
     upd_flops = 2.0 * MINI_EPOCHS * (2 * (960 * 1024 + 1024 * 512 + 512 * 69 + 960 * 1024 + 1024 * 512 + 512)
-                                     + 2 * 1024 * 512 + 512 * 69 + 512) * T * n
+                                     + 2 * 1024 * 512 + 512 * 69 + 512
+                                     + 0.75 * (2 * _d + 1024 * 512 + 512) + 0.25 * _gp) * T * n
     if rank == 0:
         line = {
             "metric": METRIC, "value": env_steps / (ms_dev * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": a.steps,

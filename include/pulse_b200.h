@@ -297,6 +297,19 @@ typedef struct {
 } pulse_ppo_loss_args_t;
 int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, void* stream);
 
+/* AMP discriminator loss pieces (AMPAgent._disc_loss, phc/learning/amp_agent.py:895-952):
+ *  - prediction loss 0.5*(BCE(agent U replay, 0) + BCE(demo, 1)) and its gradient w.r.t. the logits
+ *    (rows [0,n_agent) agent/replay, rows [n_agent, n_agent+n_demo) demo), scaled by `scale` (= disc_coef);
+ *    stats[0..3] += sum softplus(l) agent, sum softplus(-l) demo, #agent l<0, #demo l>0 (accuracies, :954-959);
+ *  - pulse_relu_mask_scale: out = (h > 0) * w, the first factor of the ANALYTIC input gradient of the ReLU
+ *    discriminator used for the gradient penalty (:910-929) instead of autograd's double backward;
+ *  - pulse_axpy: y += a*x (logit regulariser :905-908 and weight decay :932-937 gradients, 2*coef*w). */
+int pulse_disc_loss(const float* logits, int64_t ld, int64_t n_agent, int64_t n_demo, float scale, pulse_bf16_t* dlogit, int64_t ld_d,
+                    double* stats, void* stream);
+int pulse_relu_mask_scale(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int64_t cols, const float* w, pulse_bf16_t* out, int64_t ldo,
+                          void* stream);
+int pulse_axpy(float a, const float* x, float* y, int64_t count, void* stream);
+
 /* out[c] (+)= sum over rows of bf16 x[rows, ldx] (bias gradients). */
 int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);
 /* dst[i] = sum_s slabs[s*slab_stride + i]  (split-K weight-gradient slabs -> flat gradient buffer) */

@@ -573,3 +573,27 @@ def ppo_total_loss(mu, value, old_neglogp, advantage, returns, actions, logstd, 
     c = critic_loss(value, returns).mean()
     b = bound_loss(mu).mean()
     return {"a_loss": a, "c_loss": c, "b_loss": b, "loss": a + critic_coef * c + bounds_coef * b, "neglogp": neglogp}
+
+
+def disc_loss(disc_mlp, amp_agent, amp_replay, amp_demo, logit_weight, all_weights, logit_reg: float = 0.01,
+              grad_penalty: float = 5.0, weight_decay: float = 0.0001) -> Dict[str, torch.Tensor]:
+    """amp_agent.py:895-952 (_disc_loss) incl. the eval_disc calls of amp_models.py:33-41.
+
+    `disc_mlp` maps (already normalised) AMP observations to logits; `logit_weight` is `_disc_logits.weight`,
+    `all_weights` the weights of every discriminator Linear layer (get_disc_weights, amp_network_builder.py:221-228)."""
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    demo = amp_demo.detach().clone().requires_grad_(True)
+    agent_logit = torch.cat([disc_mlp(amp_agent), disc_mlp(amp_replay)], dim=0)
+    demo_logit = disc_mlp(demo)
+    loss = 0.5 * (bce(agent_logit, torch.zeros_like(agent_logit)) + bce(demo_logit, torch.ones_like(demo_logit)))
+    logit_loss = torch.sum(torch.square(torch.flatten(logit_weight)))
+    loss = loss + logit_reg * logit_loss
+    grad = torch.autograd.grad(demo_logit, demo, grad_outputs=torch.ones_like(demo_logit), create_graph=True, retain_graph=True,
+                               only_inputs=True)[0]
+    gp = torch.mean(torch.sum(torch.square(grad), dim=-1))
+    loss = loss + grad_penalty * gp
+    if weight_decay != 0:
+        wd = torch.sum(torch.square(torch.cat([torch.flatten(w) for w in all_weights], dim=-1)))
+        loss = loss + weight_decay * wd
+    return {"disc_loss": loss, "disc_grad_penalty": gp.detach(), "disc_logit_loss": logit_loss.detach(),
+            "disc_agent_acc": (agent_logit < 0).float().mean(), "disc_demo_acc": (demo_logit > 0).float().mean()}

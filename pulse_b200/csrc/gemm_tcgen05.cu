@@ -7,11 +7,11 @@
 //   wgrad     dW = dY^T X                    A = dY^T [N,M], B = X^T [K,M]  (transposed copies written by epilogues)
 // so both operands are always K-major and one TMA / UMMA configuration serves all three.
 //
-// Structure (one 128x128 output tile per CTA, 2 CTAs co-resident per SM so one tile's epilogue
-// overlaps the other's main loop):
+// Structure (persistent: one CTA per SM loops over 128x128 output tiles x split-K slices; the fp32 accumulator
+// is double-buffered in TMEM so one item's epilogue overlaps the next item's main loop):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 bf16 boxes (128B swizzle) into a
-//               3-stage shared-memory ring, completion on "full" mbarriers;
-//   warp 1      allocates 128 TMEM columns, then one elected lane issues tcgen05.mma (M128 N128 K16,
+//               6-stage shared-memory ring that runs continuously across work items, completion on "full" mbarriers;
+//   warp 1      allocates 256 TMEM columns, then one elected lane issues tcgen05.mma (M128 N128 K16,
 //               fp32 accumulate in TMEM) four times per stage and tcgen05.commit's the stage back to the
 //               producer ("empty") and, after the last k-block, the accumulator to the epilogue;
 //   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / activation / activation-
@@ -26,17 +26,19 @@ namespace pulse {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
-constexpr int kStagesG = 3;
+constexpr int kStagesG = 6;   // 6 x 32 KB ring (one CTA per SM)
 constexpr int kGemmThreads = 192;
 constexpr unsigned kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr unsigned kTmemCols = 128;
+constexpr unsigned kTmemCols = 256;  // two 128-column fp32 accumulators
 
 struct __align__(1024) GemmSmem {
   unsigned char a[kStagesG][kStageBytesA];
   unsigned char b[kStagesG][kStageBytesB];
   unsigned long long full[kStagesG];
   unsigned long long empty[kStagesG];
-  unsigned long long tmem_full;
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
+  float red[4][32 * 33];   // per-epilogue-warp transpose tile for coalesced fp32 atomics
   unsigned tmem_base;
 };
 
@@ -46,6 +48,9 @@ __device__ __forceinline__ void g_mbar_init(unsigned long long* bar, unsigned co
 }
 __device__ __forceinline__ void g_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool g_mbar_try(unsigned long long* bar, unsigned parity) {
   unsigned ok;
@@ -140,19 +145,22 @@ __device__ __forceinline__ float act_grad(float g, int mode) {
 }
 
 // A_MN / B_MN: operand is MN-major in global memory ([reduction rows, non-reduction cols] row-major) instead of K-major.
+// Persistent: one CTA per SM loops over (tile, split) work items.  The TMA ring runs continuously across
+// items; the accumulator is double-buffered in TMEM (2 x 128 columns) so the epilogue of item i overlaps the
+// main loop of item i+1.
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_b,
                                                                       const pulse_gemm_epilogue_t ep, int M, int N, int K,
-                                                                      int kb_per_split) {
+                                                                      int kb_per_split, int splits) {
   extern __shared__ unsigned char gsm_raw[];
   // the 128-byte swizzle atoms need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  const int tiles = tiles_m * tiles_n;
+  const int total = tiles * splits;
   const int num_kb_total = (K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int num_kb = min(kb_per_split, num_kb_total - kb0);
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -160,7 +168,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_kernel(const __grid
       g_mbar_init(&sm.full[s], 1);
       g_mbar_init(&sm.empty[s], 1);
     }
-    g_mbar_init(&sm.tmem_full, 1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      g_mbar_init(&sm.tmem_full[s], 1);
+      g_mbar_init(&sm.tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
@@ -173,205 +185,217 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_bf16_kernel(const __grid
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const unsigned tmem_d = sm.tmem_base;
+  const unsigned tmem_base = sm.tmem_base;
 
   if (warp == 0) {
     // ================================ TMA producer ======================================================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStagesG;
-        g_mbar_wait(&sm.empty[s], ((kb / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
-        g_mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
-        const int kk = (kb0 + kb) * BK;
-        if (A_MN) {  // box = [64 reduction rows][64 contiguous m]: two boxes cover the 128-wide tile
-          tma_load_2d(sm.a[s], &map_a, m0, kk, &sm.full[s]);
-          tma_load_2d(sm.a[s] + 8192, &map_a, m0 + 64, kk, &sm.full[s]);
-        } else {
-          tma_load_2d(sm.a[s], &map_a, kk, m0, &sm.full[s]);
-        }
-        if (B_MN) {
-          tma_load_2d(sm.b[s], &map_b, n0, kk, &sm.full[s]);
-          tma_load_2d(sm.b[s] + 8192, &map_b, n0 + 64, kk, &sm.full[s]);
-        } else {
-          tma_load_2d(sm.b[s], &map_b, kk, n0, &sm.full[s]);
+      int it = 0;  // running k-block counter across work items: stage = it % kStagesG
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = w / tiles, t = w - split * tiles;
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        const int kb0 = split * kb_per_split;
+        const int num_kb = min(kb_per_split, num_kb_total - kb0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStagesG;
+          g_mbar_wait(&sm.empty[s], ((it / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
+          g_mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
+          const int kk = (kb0 + kb) * BK;
+          if (A_MN) {  // box = [64 reduction rows][64 contiguous m]: two boxes cover the 128-wide tile
+            tma_load_2d(sm.a[s], &map_a, m0, kk, &sm.full[s]);
+            tma_load_2d(sm.a[s] + 8192, &map_a, m0 + 64, kk, &sm.full[s]);
+          } else {
+            tma_load_2d(sm.a[s], &map_a, kk, m0, &sm.full[s]);
+          }
+          if (B_MN) {
+            tma_load_2d(sm.b[s], &map_b, n0, kk, &sm.full[s]);
+            tma_load_2d(sm.b[s] + 8192, &map_b, n0 + 64, kk, &sm.full[s]);
+          } else {
+            tma_load_2d(sm.b[s], &map_b, kk, n0, &sm.full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ========================================================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStagesG;
-        g_mbar_wait(&sm.full[s], (kb / kStagesG) & 1);
+      int it = 0, lw = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
+        const int split = w / tiles;
+        const int kb0 = split * kb_per_split;
+        const int num_kb = min(kb_per_split, num_kb_total - kb0);
+        const int acc = lw & 1;
+        g_mbar_wait(&sm.tmem_empty[acc], ((lw >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
+        const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStagesG;
+          g_mbar_wait(&sm.full[s], (it / kStagesG) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: 16 bf16 = 32 bytes inside the 128-byte swizzle atom; MN-major: 16 reduction rows = two 1024-byte groups
-          const unsigned long long da = A_MN ? umma_desc_mn(a_addr + k * 2048) : umma_desc(a_addr + k * 32);
-          const unsigned long long db = B_MN ? umma_desc_mn(b_addr + k * 2048) : umma_desc(b_addr + k * 32);
-          umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 16 bf16 = 32 bytes inside the 128-byte swizzle atom; MN-major: 16 reduction rows = two 1024-byte groups
+            const unsigned long long da = A_MN ? umma_desc_mn(a_addr + k * 2048) : umma_desc(a_addr + k * 32);
+            const unsigned long long db = B_MN ? umma_desc_mn(b_addr + k * 2048) : umma_desc(b_addr + k * 32);
+            umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&sm.empty[s]);  // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
         }
-        umma_commit(&sm.empty[s]);  // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+        umma_commit(&sm.tmem_full[acc]);  // accumulator complete
       }
-      umma_commit(&sm.tmem_full);    // accumulator complete
     }
   } else {
     // ================================ epilogue warps (TMEM lane quarter = warp % 4) =======================
-    g_mbar_wait(&sm.tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
-    const int row = m0 + lrow;
-    const bool row_ok = row < M;
-    float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(blockIdx.z) * ep.split_stride : nullptr;
-    // The stage ring is idle once the accumulator is complete: its first 34 KB stage the TRANSPOSED tile
-    // ([col][row], pitch 136 bf16) so that out_t leaves in coalesced 16-byte segments.
-    __nv_bfloat16* tstage = reinterpret_cast<__nv_bfloat16*>(&sm.a[0][0]);
-    constexpr int TP = BM + 8;
-    static_assert(BN * TP * 2 <= kStagesG * (int)kStageBytesA, "transposed staging must fit in the A ring");
+    float* red_stage = sm.red[warp - 2];  // warp-private 32 x 33 fp32 tile for coalesced atomics
+    int lw = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
+      const int split = w / tiles, t = w - split * tiles;
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const int acc = lw & 1;
+      g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
+      const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
+      const int row = m0 + lrow;
+      const bool row_ok = row < M;
+      float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(ep.accumulate ? 0 : split) * ep.split_stride : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      unsigned r[32];
-      tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
-      const int col0 = n0 + c * 32;
-      const bool full = col0 + 32 <= N;
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
-      if (ep.bias != nullptr) {
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));  // bias is 16-byte aligned (flat buffer slots)
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+      for (int c = 0; c < BN / 32; ++c) {
+        unsigned r[32];
+        tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
+        if (c == BN / 32 - 1) {
+          // all of this warp's TMEM reads for the item are done: hand the accumulator back before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) g_mbar_arrive(&sm.tmem_empty[acc]);
         }
-      }
-      if (ep.preact != nullptr && row_ok) {
-        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
+        const int col0 = n0 + c * 32;
+        const bool full = col0 + 32 <= N;
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
-      }
-      if (ep.act != PULSE_ACT_NONE) {
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+        if (ep.bias != nullptr) {
+          if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ep.act);
-      }
-      if (ep.gate != nullptr && row_ok) {
-        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
-        if (full && (ep.ldg & 7) == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + i));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __bfloat1622float2(h[q]);
-              v[i + 2 * q] *= act_grad(f.x, ep.gate_mode);
-              v[i + 2 * q + 1] *= act_grad(f.y, ep.gate_mode);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));  // bias is 16-byte aligned (flat buffer slots)
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
-        }
-      }
-      if (ep.colsum != nullptr) {
-        // column sums of this warp's 32x32 block by a shuffle reduce-scatter (31 shuffles): lane l ends up with
-        // the sum over the warp's 32 rows of column l (bias gradients without a second pass over dY)
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = row_ok ? v[i] : 0.0f;
-#pragma unroll
-        for (int half = 16; half >= 1; half >>= 1) {
-          const bool upper = (lane & half) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float mine = upper ? w[i + half] : w[i];
-            const float send = upper ? w[i] : w[i + half];
-            w[i] = mine + __shfl_xor_sync(0xffffffffu, send, half);
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
           }
         }
-        // after the scatter, lane l holds column bitrev-free index: with this exchange pattern lane l owns column l
-        if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, w[0]);
-      }
-      if (outf != nullptr && row_ok && ep.accumulate) {
-        float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) atomicAdd(p + i, v[i]);
-      } else if (outf != nullptr && row_ok) {
-        float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
-        if (full && (ep.ldf & 3) == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) p[i] = v[i];
-        }
-      }
-      if (ep.out != nullptr && row_ok) {
-        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
-        if (full && (ep.ldo & 7) == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<unsigned*>(&h0);
-            u.y = *reinterpret_cast<unsigned*>(&h1);
-            u.z = *reinterpret_cast<unsigned*>(&h2);
-            u.w = *reinterpret_cast<unsigned*>(&h3);
-            *reinterpret_cast<uint4*>(p + i) = u;
-          }
-        } else {
+        if (ep.preact != nullptr && row_ok) {
+          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
         }
-      }
-      if (ep.out_t != nullptr) {
-        // lanes hold consecutive rows -> consecutive 2-byte addresses of tstage[col][row]: conflict-free
+        if (ep.act != PULSE_ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tstage[(c * 32 + i) * TP + lrow] = __float2bfloat16(v[i]);
-      }
-    }
-    if (ep.out_t != nullptr) {
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");  // the four epilogue warps only
-      const int t = threadIdx.x - 64;                    // 0..127
-      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(ep.out_t);
-      const bool vec_ok = (ep.ldot & 7) == 0;
-#pragma unroll 4
-      for (int it = 0; it < (BN * BM / 8) / 128; ++it) {
-        const int idx = it * 128 + t;
-        const int col = idx >> 4, seg = idx & 15;        // 16 segments of 8 rows per column
-        const int gcol = n0 + col, grow = m0 + seg * 8;
-        if (gcol < N && grow < M) {
-          const uint4 u = *reinterpret_cast<const uint4*>(tstage + col * TP + seg * 8);
-          __nv_bfloat16* dst = ot + static_cast<long long>(gcol) * ep.ldot + grow;
-          if (vec_ok && grow + 8 <= M) {
-            *reinterpret_cast<uint4*>(dst) = u;
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ep.act);
+        }
+        if (ep.gate != nullptr && row_ok) {
+          const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
+          if (full && (ep.ldg & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + i));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(h[q]);
+                v[i + 2 * q] *= act_grad(f.x, ep.gate_mode);
+                v[i + 2 * q + 1] *= act_grad(f.y, ep.gate_mode);
+              }
+            }
           } else {
-            const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
-            for (int q = 0; q < 8; ++q)
-              if (grow + q < M) dst[q] = e[q];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
           }
+        }
+        if (ep.colsum != nullptr) {
+          // column sums of this warp's 32x32 block by a shuffle reduce-scatter (31 shuffles): lane l ends up with
+          // the sum over the warp's 32 rows of column l (bias gradients without a second pass over dY)
+          float wv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) wv[i] = row_ok ? v[i] : 0.0f;
+#pragma unroll
+          for (int half = 16; half >= 1; half >>= 1) {
+            const bool upper = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float mine = upper ? wv[i + half] : wv[i];
+              const float send = upper ? wv[i] : wv[i + half];
+              wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, half);
+            }
+          }
+          if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, wv[0]);
+        }
+        if (outf != nullptr && ep.accumulate) {
+          // fp32 atomics, coalesced: transpose the warp's 32x32 block through its private shared tile so that one
+          // warp instruction adds 32 consecutive columns of ONE row (128 contiguous bytes)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) red_stage[lane * 33 + i] = v[i];
+          __syncwarp();
+          const int rows_here = min(32, M - (m0 + quarter * 32));
+          if (col0 + lane < N) {
+            float* p = outf + static_cast<long long>(m0 + quarter * 32) * ep.ldf + col0 + lane;
+            for (int rr = 0; rr < rows_here; ++rr) atomicAdd(p + static_cast<long long>(rr) * ep.ldf, red_stage[rr * 33 + lane]);
+          }
+          __syncwarp();
+        } else if (outf != nullptr && row_ok) {
+          float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
+          if (full && (ep.ldf & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) p[i] = v[i];
+          }
+        }
+        if (ep.out != nullptr && row_ok) {
+          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+          if (full && (ep.ldo & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<unsigned*>(&h0);
+              u.y = *reinterpret_cast<unsigned*>(&h1);
+              u.z = *reinterpret_cast<unsigned*>(&h2);
+              u.w = *reinterpret_cast<unsigned*>(&h3);
+              *reinterpret_cast<uint4*>(p + i) = u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+          }
+        }
+        if (ep.out_t != nullptr && row_ok) {
+          // transposed bf16 copy (not used by the MLP path any more; kept for API completeness): lanes hold consecutive
+          // rows -> consecutive 2-byte addresses of out_t[col][row]
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N)
+              reinterpret_cast<__nv_bfloat16*>(ep.out_t)[static_cast<long long>(col0 + i) * ep.ldot + row] = __float2bfloat16(v[i]);
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -412,8 +436,15 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
     PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(static_cast<unsigned>((n + BN - 1) / BN), static_cast<unsigned>((m + BM - 1) / BM), static_cast<unsigned>(splits));
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, smem, stream>>>(map_a, map_b, ep, m, n, k, kb_per_split);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PULSE_CUDA_OK(cudaGetDevice(&dev));
+    PULSE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long total = static_cast<long long>((n + BN - 1) / BN) * ((m + BM - 1) / BM) * splits;
+  const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);  // persistent: one CTA per SM
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, smem, stream>>>(map_a, map_b, ep, m, n, k, kb_per_split, splits);
   PULSE_LAUNCH_OK("gemm_bf16_kernel");
   return PULSE_OK;
 }

@@ -297,6 +297,57 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 __global__ void bump_step_kernel(int* step) { *step += 1; }
 
+// ---- AMP discriminator: BCE-with-logits gradients (amp_agent.py:895-920, :935-952) -------------------------------------
+// rows [0, n_agent) are agent / replay samples (target 0), rows [n_agent, n_agent + n_demo) demo samples (target 1).
+// dlogit = scale * 0.5 * d/dl mean BCE;  stats: [sum softplus(l) agent, sum softplus(-l) demo, #agent l<0, #demo l>0].
+__global__ void __launch_bounds__(256) disc_loss_kernel(const float* __restrict__ logits, long long ld, long long n_agent, long long n_demo,
+                                                        float scale, __nv_bfloat16* __restrict__ dlogit, long long ld_d,
+                                                        double* __restrict__ stats) {
+  double st[4] = {0, 0, 0, 0};
+  const long long n = n_agent + n_demo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float l = logits[i * ld];
+    const float sg = 1.0f / (1.0f + expf(-l));
+    const float sp = fmaxf(l, 0.0f) + log1pf(expf(-fabsf(l)));  // softplus(l), stable
+    float g;
+    if (i < n_agent) {
+      g = 0.5f * scale * sg / static_cast<float>(n_agent);
+      st[0] += sp;
+      st[2] += l < 0.0f ? 1.0 : 0.0;
+    } else {
+      g = 0.5f * scale * (sg - 1.0f) / static_cast<float>(n_demo);
+      st[1] += sp - l;  // softplus(-l)
+      st[3] += l > 0.0f ? 1.0 : 0.0;
+    }
+    dlogit[i * ld_d] = __float2bfloat16(g);
+  }
+  __shared__ double ws[8][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] = warp_sum_d(st[k]);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 4; ++k) ws[threadIdx.x >> 5][k] = st[k];
+  __syncthreads();
+  if (threadIdx.x < 4 && stats != nullptr) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w][threadIdx.x];
+    atomicAdd(stats + threadIdx.x, t);
+  }
+}
+
+// out[r, c] = h[r, c] > 0 ? w[c] : 0   (first step of the analytic input gradient of a ReLU MLP: m2 * w_logit)
+__global__ void __launch_bounds__(256) relu_mask_scale_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, long long rows, long long cols,
+                                                              const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long ldo) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    out[r * ldo + c] = __float2bfloat16(__bfloat162float(h[r * ldh + c]) > 0.0f ? w[c] : 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+
 __global__ void __launch_bounds__(256) refresh_weight_kernel(const float* __restrict__ w, long long n, long long k,
                                                              __nv_bfloat16* __restrict__ wb, long long ld_k,
                                                              __nv_bfloat16* __restrict__ wt, long long ld_n) {
@@ -422,6 +473,31 @@ extern "C" int pulse_adam_step(float* params, const float* grads, float* exp_avg
                                                                                        max_norm, lr, beta1, beta2, eps, step,
                                                                                        reinterpret_cast<__nv_bfloat16*>(params_bf16));
   PULSE_LAUNCH_OK("adam_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_disc_loss(const float* logits, int64_t ld, int64_t n_agent, int64_t n_demo, float scale, pulse_bf16_t* dlogit,
+                               int64_t ld_d, double* stats, void* stream) {
+  PULSE_REQUIRE(logits && dlogit && n_agent > 0 && n_demo > 0 && ld >= 1 && ld_d >= 1, "pulse_disc_loss: bad argument");
+  disc_loss_kernel<<<grid_for(n_agent + n_demo, 256, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ld, n_agent, n_demo, scale, reinterpret_cast<__nv_bfloat16*>(dlogit), ld_d, stats);
+  PULSE_LAUNCH_OK("disc_loss_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_relu_mask_scale(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int64_t cols, const float* w, pulse_bf16_t* out,
+                                     int64_t ldo, void* stream) {
+  PULSE_REQUIRE(h && w && out && rows > 0 && cols > 0, "pulse_relu_mask_scale: bad argument");
+  relu_mask_scale_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), ldh, rows, cols, w, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  PULSE_LAUNCH_OK("relu_mask_scale_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_axpy(float a, const float* x, float* y, int64_t count, void* stream) {
+  PULSE_REQUIRE(x && y && count > 0, "pulse_axpy: bad argument");
+  axpy_kernel<<<grid_for(count, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, x, y, count);
+  PULSE_LAUNCH_OK("axpy_kernel");
   return PULSE_OK;
 }
 

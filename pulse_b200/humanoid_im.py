@@ -160,6 +160,27 @@ class HumanoidImCompute:
             _lib.check(self.lib.pulse_amp_obs(C.byref(a), int(body_state.shape[0]), _lib.current_stream(self.device)), "pulse_amp_obs")
 
 
+    # ------------------------------------------------------------------------------------------
+    def build_amp_obs_demo(self, motion_ids: torch.Tensor, motion_times0: torch.Tensor, num_steps: Optional[int] = None) -> torch.Tensor:
+        """HumanoidAMP.build_amp_obs_demo (humanoid_amp.py:253-284): AMP observations of the reference motion at
+        t0 - k*dt, k = 0..steps-1, one MotionLib query (no offset) + one AMP-obs launch.  Returns [n, steps*196]."""
+        steps = int(num_steps or self.cfg.num_amp_obs_steps)
+        n = int(motion_ids.shape[0])
+        dev = self.device
+        ids = motion_ids.to(dev).unsqueeze(-1).repeat(1, steps).reshape(-1)
+        times = (motion_times0.to(dev).unsqueeze(-1) + (-self.cfg.dt) * torch.arange(0, steps, device=dev)).reshape(-1)
+        ms = self.motion_lib.get_motion_state(ids, times)
+        body = torch.cat([ms["rg_pos"], ms["rb_rot"], ms["body_vel"], ms["body_ang_vel"]], dim=-1).contiguous()   # [n*steps, 24, 13]
+        out = torch.empty(n * steps, 1, AMP_OBS, device=dev)
+        self.amp_obs(body_state=body, dof_pos=ms["dof_pos"], dof_vel=ms["dof_vel"], amp_obs_buf=out, shift_history=False)
+        return out.view(n, steps * AMP_OBS)
+
+    def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
+        """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230) with HumanoidIm's `_sample_time` = sample_time_interval."""
+        ids = self.motion_lib.sample_motions(num_samples)
+        return self.build_amp_obs_demo(ids, self.motion_lib.sample_time_interval(ids))
+
+
 class HumanoidImB200Mixin:
     """Overrides for `phc.env.tasks.humanoid_im.HumanoidIm` (method names and buffer names are the
     reference's).  Usage:

@@ -53,6 +53,7 @@ class MotionLibB200:
         self.num_bodies = 24
         self.motion_ids = torch.arange(M, dtype=torch.long, device=dev)
         self._sampling_batch_prob = torch.full((M,), 1.0 / M, device=dev)
+        self._time_step = torch.tensor(1 / 30, dtype=torch.float32, device=dev)  # cached: no H2D copy inside CUDA-graph capture
 
         # packed records (layout: include/pulse_b200.h PULSE_FRAME_REC / PULSE_AUX_REC)
         self.frame_rec = torch.empty(F, FRAME_REC, device=dev, dtype=torch.float32)
@@ -129,7 +130,7 @@ class MotionLibB200:
         if truncate_time is not None:
             assert truncate_time >= 0.0
             motion_len = motion_len - truncate_time
-        step = torch.tensor(1 / 30, dtype=torch.float32, device=self._device)
+        step = self._time_step
         return torch.div(phase * motion_len, step).long() * step
 
     def _query(self, motion_ids, motion_times, offset, want_full=True, diagnostics=False):

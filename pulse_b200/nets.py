@@ -26,6 +26,21 @@ def pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def pick_split(tiles: int, num_kb: int, sms: int = 148, epilogue_kb: int = 24) -> int:
+    """Split-K factor for a weight-gradient GEMM on the persistent kernel: minimise rounds x (k-blocks per item +
+    epilogue cost in k-block equivalents), where rounds = ceil(tiles * splits / SMs)."""
+    best, best_cost = 1, None
+    for s in range(1, min(64, num_kb) + 1):
+        per = -(-num_kb // s)
+        if -(-num_kb // per) != s:
+            continue  # not every slice would get a k-block
+        rounds = -(-(tiles * s) // sms)
+        cost = rounds * (per + epilogue_kb)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
 class FlatParams:
     """One flat fp32 buffer each for parameters, gradients and the two Adam moments."""
 
@@ -175,7 +190,7 @@ class MLP:
                     ws["pre"].append(bf(M, l.Np) if (l.act == "silu") else None)
                     ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
                     tiles = ((l.N + 127) // 128) * ((l.Kp + 127) // 128)
-                    ws["split"].append(max(1, min(64, (2 * 148 + tiles - 1) // tiles)))  # wgrad split-K: ~2 CTAs per SM
+                    ws["split"].append(pick_split(tiles, (M + 63) // 64))
             ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
             self._ws[key] = ws
         return self._ws[key]

@@ -7,8 +7,8 @@
   calc_gradients      amp_agent.py:605-760 (actor / critic / bound losses, grad-norm clip, Adam) -> PPOPolicy.train_minibatch
   _preproc_obs        amp_agent.py:586-603 + RunningMeanStd (running_mean_std.py:69-109)          -> RunningMeanStdB200
 
-The discriminator branch of calc_gradients (AMP style loss with gradient penalty, amp_agent.py:895-952) is not
-part of this class yet.  Multi-GPU: gradients are all-reduced (average) over torch.distributed's NCCL
+The discriminator branch of calc_gradients (AMP style loss with gradient penalty, amp_agent.py:895-952) lives in
+`pulse_b200/amp.py` and shares this class's flat parameter / gradient buffers (one optimizer, one norm clip).  Multi-GPU: gradients are all-reduced (average) over torch.distributed's NCCL
 communicator once per minibatch on the flat gradient buffer, replacing Horovod's DistributedOptimizer
 (amp_agent.py:735-742).
 """
@@ -69,17 +69,24 @@ class RunningMeanStdB200:
 class PPOPolicy:
     def __init__(self, obs_size: int = 934, num_actions: int = 69, units: Sequence[int] = (1024, 512), act: str = "relu",
                  logstd: float = -2.9, device="cuda:0", seed: int = 0, lr: float = 2e-5, e_clip: float = 0.2, critic_coef: float = 5.0,
-                 bounds_coef: float = 10.0, grad_norm: float = 50.0, normalize_value: bool = True):
+                 bounds_coef: float = 10.0, grad_norm: float = 50.0, normalize_value: bool = True, with_disc: bool = False,
+                 amp_obs_size: int = 1960, disc_units: Sequence[int] = (1024, 512)):
         self.device = torch.device(device)
         self.obs_size, self.A = obs_size, num_actions
         self.lr, self.e_clip, self.critic_coef, self.bounds_coef, self.grad_norm = lr, e_clip, critic_coef, bounds_coef, grad_norm
         self.flat = FlatParams(self.device)
         self.actor = MLP(self.flat, obs_size, units, num_actions, act)
         self.critic = MLP(self.flat, obs_size, units, 1, act)
+        self.disc = None
+        if with_disc:  # one optimizer / one grad-norm clip over actor + critic + discriminator, as in the reference
+            from .amp import AmpDiscriminator
+            self.disc = AmpDiscriminator(self.flat, amp_obs_size, disc_units)
         self.flat.finalize()
         gen = torch.Generator(device=self.device).manual_seed(seed)
         self.actor.init_default(gen)
         self.critic.init_default(gen)
+        if self.disc is not None:
+            self.disc.mlp.init_default(gen)
         self.logstd = torch.full((num_actions,), logstd, device=self.device)  # fixed_sigma, const_initializer (im.yaml:21-25)
         self.obs_rms = RunningMeanStdB200(obs_size, self.device)
         self.value_rms = RunningMeanStdB200(1, self.device) if normalize_value else None
@@ -131,7 +138,7 @@ class PPOPolicy:
 
     # ------------------------------------------------------------------ update side
     def train_minibatch(self, obs, actions, old_neglogp, advantages, returns, old_mu=None, update_obs_rms: bool = True,
-                        world_size: int = 1) -> torch.Tensor:
+                        world_size: int = 1, amp=None) -> torch.Tensor:
         """One calc_gradients step (amp_agent.py:605-760, PPO branch without the discriminator term).
         `returns` are already value-normalised (prepare_dataset, common_agent.py:372-374).  Returns the fp64
         stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
@@ -155,6 +162,8 @@ class PPOPolicy:
         self.flat.zero_grad()                                # weight / bias gradients are accumulated with atomics
         self.actor.backward(b["dmu"], M)
         self.critic.backward(b["dv"], M)
+        if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
+            self.disc.loss_backward(*amp)
         if world_size > 1:
             from .dist_utils import average_gradients
             average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)

@@ -279,7 +279,35 @@ def main():
     y2 = rms(x2)
     rms.eval()
     y3 = rms(x1)
+    # --- AMPAgent._disc_loss (amp_agent.py:895-952) on a small ReLU discriminator
+    dm = torch.nn.Sequential(torch.nn.Linear(40, 32), torch.nn.ReLU(), torch.nn.Linear(32, 16), torch.nn.ReLU())
+    dl = torch.nn.Linear(16, 1)
+    torch.manual_seed(11)
+    for m in list(dm) + [dl]:
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.normal_(m.weight, std=0.3)
+            torch.nn.init.normal_(m.bias, std=0.1)
+    net = types.SimpleNamespace(get_disc_logit_weights=lambda: torch.flatten(dl.weight),
+                                get_disc_weights=lambda: [torch.flatten(dm[0].weight), torch.flatten(dm[2].weight), torch.flatten(dl.weight)])
+    fake_disc = types.SimpleNamespace(model=types.SimpleNamespace(a2c_network=net), _disc_logit_reg=0.01, _disc_grad_penalty=5,
+                                      _disc_weight_decay=0.0001)
+    for name in ("_disc_loss_neg", "_disc_loss_pos", "_compute_disc_acc"):
+        setattr(fake_disc, name, types.MethodType(getattr(AA, name), fake_disc))
+    d_agent, d_replay = torch.randn(24, 40, generator=gen), torch.randn(24, 40, generator=gen)
+    d_demo = torch.randn(24, 40, generator=gen).requires_grad_(True)
+    ev = lambda x: dl(dm(x))
+    agent_cat = torch.cat([ev(d_agent), ev(d_replay)], dim=0)
+    demo_logit = ev(d_demo)
+    dinfo = AA._disc_loss(fake_disc, agent_cat, demo_logit, d_demo)
+    dparams = [dm[0].weight, dm[0].bias, dm[2].weight, dm[2].bias, dl.weight, dl.bias]
+    dgrads = torch.autograd.grad(dinfo["disc_loss"], dparams)
+
     ag = {
+        "disc_w0": dm[0].weight, "disc_b0": dm[0].bias, "disc_w1": dm[2].weight, "disc_b1": dm[2].bias, "disc_w2": dl.weight, "disc_b2": dl.bias,
+        "disc_agent": d_agent, "disc_replay": d_replay, "disc_demo": d_demo, "disc_loss": dinfo["disc_loss"],
+        "disc_grad_penalty": dinfo["disc_grad_penalty"], "disc_logit_loss": dinfo["disc_logit_loss"],
+        "disc_agent_acc": dinfo["disc_agent_acc"], "disc_demo_acc": dinfo["disc_demo_acc"],
+        "disc_gw0": dgrads[0], "disc_gb0": dgrads[1], "disc_gw1": dgrads[2], "disc_gb1": dgrads[3], "disc_gw2": dgrads[4], "disc_gb2": dgrads[5],
         "rewards": rewards, "values": values, "next_values": next_values, "fdones": fdones, "advs": advs, "returns": returns,
         "adv_norm": adv_norm, "old_neglogp": old_nlp, "new_neglogp": new_nlp, "adv_b": adv_b, "actor_loss": a_info["actor_loss"],
         "actor_clipped": a_info["actor_clipped"], "critic_values": values[:, 1, :], "critic_returns": returns[:, 0, :],

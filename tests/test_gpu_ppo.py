@@ -152,3 +152,37 @@ def test_policy_forward_and_update_match_fp32_reference():
               "a2c_network.value.bias", "a2c_network.sigma", "running_mean_std.running_mean"):
         assert k in sd
     assert sd["a2c_network.actor_mlp.0.weight"].shape == (1024, 934) and sd["a2c_network.mu.weight"].shape == (69, 512)
+
+
+def test_disc_loss_and_gradient_penalty_match_autograd():
+    """AMP discriminator: analytic gradient penalty (GEMM chain) vs the oracle's autograd double backward, im.yaml sizes."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.ppo import PPOPolicy
+    pol = PPOPolicy(device=DEV, seed=7, with_disc=True)
+    disc = pol.disc
+    B = 512
+    g = torch.Generator(device=DEV).manual_seed(8)
+    agent, replay, demo = (torch.randn(B, 1960, device=DEV, generator=g) for _ in range(3))
+    demo = demo * 0.7 + 0.3
+    ref_mlp = _torch_mlp(disc.mlp)
+    lins = [m for m in ref_mlp if isinstance(m, torch.nn.Linear)]
+    xn = lambda x: torch.clamp((x - disc.rms.mean_f32) * disc.rms.rstd_f32, -5, 5)
+    ref = po.disc_loss(ref_mlp, xn(agent), xn(replay), xn(demo), lins[-1].weight, [l.weight for l in lins])
+    (ref["disc_loss"] * 5.0).backward()
+    pol.flat.zero_grad()
+    stats = disc.loss_backward(agent, replay, demo, update_rms=False)
+    torch.cuda.synchronize()
+    out = disc.loss_from_stats(stats, B)
+    assert abs(out["disc_loss"] - ref["disc_loss"].item()) < 2e-3 * max(1.0, abs(ref["disc_loss"].item())), (out, ref["disc_loss"].item())
+    assert abs(out["disc_grad_penalty"] - ref["disc_grad_penalty"].item()) < 2e-2 * ref["disc_grad_penalty"].item() + 1e-6
+    assert abs(out["disc_agent_acc"] - ref["disc_agent_acc"].item()) < 0.02 and abs(out["disc_demo_acc"] - ref["disc_demo_acc"].item()) < 0.02
+    for l, lin in zip(disc.mlp.layers, lins):
+        gw = l.weight_grad[:, :l.K]
+        cos = torch.nn.functional.cosine_similarity(gw.flatten(), lin.weight.grad.flatten(), dim=0)
+        rel = (gw - lin.weight.grad).norm() / lin.weight.grad.norm()
+        assert cos > 0.99 and rel < 0.15, (l.N, l.K, cos.item(), rel.item())
+        cosb = torch.nn.functional.cosine_similarity(l.bias_grad, lin.bias.grad, dim=0)
+        assert cosb > 0.99, (l.N, cosb.item())
+    # rewards: -log(max(1 - sigmoid(D), 1e-4)) * 2
+    r = disc.rewards(agent)
+    torch.testing.assert_close(r, po.disc_reward(ref_mlp(xn(agent)).detach()), atol=3e-2, rtol=3e-2)

@@ -239,3 +239,22 @@ def test_full_size_properties():
     pr = _run_step(_mlib(tb), zp, with_ref=False)
     assert torch.equal(pr["obs_buf"], base["obs_buf"][perm])
     assert torch.equal(pr["reset_buf"], base["reset_buf"][perm])
+
+
+def test_build_amp_obs_demo_matches_oracle():
+    """humanoid_amp.py:253-284: demo AMP observations from the reference motion (MotionLib query + AMP obs)."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.humanoid_im import HumanoidImCompute
+    tb = oracle_tables()
+    comp = HumanoidImCompute(_mlib(tb))
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, tb.num_motions, (37,), generator=g)
+    t0 = po.sample_time_interval(tb, ids, torch.rand(37, generator=g))
+    out = comp.build_amp_obs_demo(ids.to(_dev()), t0.to(_dev())).cpu()
+    steps = 10
+    rid = ids.unsqueeze(-1).repeat(1, steps).reshape(-1)
+    rt = (t0.unsqueeze(-1) + (-po.STEP_DT) * torch.arange(0, steps)).reshape(-1)
+    ms = po.motion_state(tb, rid, rt, None)
+    ref = po.amp_obs_smpl(ms["root_pos"], ms["root_rot"], ms["root_vel"], ms["root_ang_vel"], ms["dof_pos"], ms["dof_vel"],
+                          ms["rg_pos"][:, list(po.KEY_BODY_IDS)], po.amp_dof_subset()).view(37, steps * 196)
+    torch.testing.assert_close(out, ref, atol=OBS_ATOL, rtol=0)

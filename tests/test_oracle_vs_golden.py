@@ -121,6 +121,18 @@ def test_agent_arithmetic():
     bce = torch.nn.functional.binary_cross_entropy_with_logits
     close(bce(z["disc_logits"], torch.zeros_like(z["disc_logits"])), z["bce_neg"])
     close(bce(z["disc_logits"], torch.ones_like(z["disc_logits"])), z["bce_pos"])
+    # discriminator loss incl. gradient penalty, and its parameter gradients through autograd
+    lin = lambda w, b: (lambda x: torch.nn.functional.linear(x, w, b))
+    ws = [z[k].clone().requires_grad_(True) for k in ("disc_w0", "disc_b0", "disc_w1", "disc_b1", "disc_w2", "disc_b2")]
+    dmlp = lambda x: lin(ws[4], ws[5])(torch.relu(lin(ws[2], ws[3])(torch.relu(lin(ws[0], ws[1])(x)))))
+    dinfo = po.disc_loss(dmlp, z["disc_agent"], z["disc_replay"], z["disc_demo"], ws[4], [ws[0], ws[2], ws[4]])
+    close(dinfo["disc_loss"], z["disc_loss"])
+    close(dinfo["disc_grad_penalty"], z["disc_grad_penalty"])
+    close(dinfo["disc_agent_acc"], z["disc_agent_acc"])
+    close(dinfo["disc_demo_acc"], z["disc_demo_acc"])
+    grads = torch.autograd.grad(dinfo["disc_loss"], ws)
+    for g_, k in zip(grads, ("disc_gw0", "disc_gb0", "disc_gw1", "disc_gb1", "disc_gw2", "disc_gb2")):
+        close(g_, z[k], atol=1e-5)
     rms = po.RunningMeanStd(7)
     y1 = rms.normalize(z["rms_x1"]); rms.update(z["rms_x1"])
     y2 = rms.normalize(z["rms_x2"]); rms.update(z["rms_x2"])
