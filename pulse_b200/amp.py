@@ -58,8 +58,8 @@ class AmpDiscriminator:
                 "g2": torch.zeros(B, L2.Np, device=dev, dtype=bf), "g1": torch.zeros(B, L1.Np, device=dev, dtype=bf),
                 "Gb": torch.zeros(B, self.Kp, device=dev, dtype=bf), "Gf": torch.zeros(B, self.Kp, device=dev),
                 "du": torch.zeros(B, L1.Np, device=dev, dtype=bf), "scratch": torch.zeros(B, L2.Np, device=dev, dtype=bf),
-                "split1": pick_split(((L1.N + 127) // 128) * ((L1.Kp + 127) // 128), (B + 63) // 64),
-                "split2": pick_split(((L2.N + 127) // 128) * ((L2.Kp + 127) // 128), (B + 63) // 64),
+                "split1": pick_split(((L1.N + 127) // 128) * ((L1.Kp + 255) // 256), (B + 63) // 64),
+                "split2": pick_split(((L2.N + 127) // 128) * ((L2.Kp + 255) // 256), (B + 63) // 64),
             }
         return self._bufs[B]
 

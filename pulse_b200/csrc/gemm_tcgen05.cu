@@ -7,14 +7,14 @@
 //   wgrad     dW = dY^T X                    A = dY^T [N,M], B = X^T [K,M]  (transposed copies written by epilogues)
 // so both operands are always K-major and one TMA / UMMA configuration serves all three.
 //
-// Structure (persistent: one CTA per SM loops over 128x128 output tiles x split-K slices; the fp32 accumulator
+// Structure (persistent: one CTA per SM loops over 128x256 output tiles x split-K slices; the fp32 accumulator
 // is double-buffered in TMEM so one item's epilogue overlaps the next item's main loop):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 bf16 boxes (128B swizzle) into a
 //               6-stage shared-memory ring that runs continuously across work items, completion on "full" mbarriers;
-//   warp 1      allocates 256 TMEM columns, then one elected lane issues tcgen05.mma (M128 N128 K16,
+//   warp 1      allocates 256 TMEM columns, then one elected lane issues tcgen05.mma (M128 N256 K16,
 //               fp32 accumulate in TMEM) four times per stage and tcgen05.commit's the stage back to the
 //               producer ("empty") and, after the last k-block, the accumulator to the epilogue;
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / activation / activation-
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 accumulator columns each): tcgen05.ld 32 lanes x 32 columns at a time -> bias / activation / activation-
 //               derivative gating -> bf16 row-major, bf16 transposed and/or fp32 outputs.
 // Split-K (blockIdx.z) writes fp32 partial slabs for the weight gradients.
 #include <cuda.h>
@@ -25,11 +25,12 @@
 namespace pulse {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
-constexpr int kStagesG = 6;   // 6 x 32 KB ring (one CTA per SM)
-constexpr int kGemmThreads = 192;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
+constexpr int kStagesG = 4;   // 4 x 48 KB ring (one CTA per SM)
+constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr unsigned kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr unsigned kTmemCols = 256;  // two 128-column fp32 accumulators
+constexpr unsigned kTmemCols = 512;  // two 256-column fp32 accumulators (all of TMEM)
 
 struct __align__(1024) GemmSmem {
   unsigned char a[kStagesG][kStageBytesA];
@@ -38,7 +39,7 @@ struct __align__(1024) GemmSmem {
   unsigned long long empty[kStagesG];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
-  float red[4][32 * 33];   // per-epilogue-warp transpose tile for coalesced fp32 atomics
+  float red[kEpiWarps][16 * 33];   // per-epilogue-warp transpose tile (16 rows at a time) for coalesced fp32 atomics
   unsigned tmem_base;
 };
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       g_mbar_init(&sm.tmem_full[s], 1);
-      g_mbar_init(&sm.tmem_empty[s], 4);  // one arrival per epilogue warp
+      g_mbar_init(&sm.tmem_empty[s], kEpiWarps);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             tma_load_2d(sm.a[s], &map_a, kk, m0, &sm.full[s]);
           }
           if (B_MN) {
-            tma_load_2d(sm.b[s], &map_b, n0, kk, &sm.full[s]);
-            tma_load_2d(sm.b[s] + 8192, &map_b, n0 + 64, kk, &sm.full[s]);
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h) tma_load_2d(sm.b[s] + h * 8192, &map_b, n0 + h * 64, kk, &sm.full[s]);
           } else {
             tma_load_2d(sm.b[s], &map_b, kk, n0, &sm.full[s]);
           }
@@ -247,8 +248,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     }
   } else {
     // ================================ epilogue warps (TMEM lane quarter = warp % 4) =======================
-    const int quarter = warp & 3;
-    float* red_stage = sm.red[warp - 2];  // warp-private 32 x 33 fp32 tile for coalesced atomics
+    const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
+    const int chalf = (warp - 2) >> 2;       // which 128-column half of the accumulator this warp drains
+    float* red_stage = sm.red[warp - 2];     // warp-private 16 x 33 fp32 tile for coalesced atomics
     int lw = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
       const int split = w / tiles, t = w - split * tiles;
@@ -262,10 +264,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       const bool row_ok = row < M;
       float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(ep.accumulate ? 0 : split) * ep.split_stride : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
         unsigned r[32];
         tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
-        if (c == BN / 32 - 1) {
+        if (c == chalf * 4 + 3) {
           // all of this warp's TMEM reads for the item are done: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
@@ -341,14 +343,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           // fp32 atomics, coalesced: transpose the warp's 32x32 block through its private shared tile so that one
           // warp instruction adds 32 consecutive columns of ONE row (128 contiguous bytes)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) red_stage[lane * 33 + i] = v[i];
-          __syncwarp();
-          const int rows_here = min(32, M - (m0 + quarter * 32));
-          if (col0 + lane < N) {
-            float* p = outf + static_cast<long long>(m0 + quarter * 32) * ep.ldf + col0 + lane;
-            for (int rr = 0; rr < rows_here; ++rr) atomicAdd(p + static_cast<long long>(rr) * ep.ldf, red_stage[rr * 33 + lane]);
+          for (int hr = 0; hr < 2; ++hr) {  // 16 rows at a time through the 16 x 33 tile
+            if ((lane >> 4) == hr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) red_stage[(lane & 15) * 33 + i] = v[i];
+            }
+            __syncwarp();
+            const int rbase = m0 + quarter * 32 + hr * 16;
+            const int rows_here = min(16, M - rbase);
+            if (col0 + lane < N) {
+              float* p = outf + static_cast<long long>(rbase) * ep.ldf + col0 + lane;
+              for (int rr = 0; rr < rows_here; ++rr) atomicAdd(p + static_cast<long long>(rr) * ep.ldf, red_stage[rr * 33 + lane]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         } else if (outf != nullptr && row_ok) {
           float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
           if (full && (ep.ldf & 3) == 0) {

@@ -189,7 +189,7 @@ class MLP:
                 if train:
                     ws["pre"].append(bf(M, l.Np) if (l.act == "silu") else None)
                     ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
-                    tiles = ((l.N + 127) // 128) * ((l.Kp + 127) // 128)
+                    tiles = ((l.N + 127) // 128) * ((l.Kp + 255) // 256)   # 128 x 256 output tiles
                     ws["split"].append(pick_split(tiles, (M + 63) // 64))
             ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
             self._ws[key] = ws
