@@ -263,10 +263,16 @@ int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t c
  * fp32 x [rows, cols] accumulated in fp64 into sums[2*cols] (caller zeroes). */
 int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, double* sums, void* stream);
 
+/* pulse_normalize_to_bf16 + pulse_column_moments in ONE pass over x: RunningMeanStd.forward in training mode
+ * (phc/utils/running_mean_std.py:91-107) normalises with the statistics from before the batch and merges the
+ * batch afterwards, so both read the same rows.  out [rows, ld_out] (padding columns zeroed), sums[2*cols] += . */
+int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
+                            pulse_bf16_t* out, int64_t ld_out, double* sums, void* stream);
+
 /* RunningMeanStd._update_mean_var_count_from_moments (:54-66) on the device: merges the batch sums of
  * pulse_column_moments (n rows) into the fp64 running mean / var / count and refreshes the fp32 mean / rstd
- * vectors pulse_normalize_to_bf16 reads.  One launch, no host round trip. */
-int pulse_rms_merge(const double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
+ * vectors pulse_normalize_to_bf16 reads, then zeroes `sums` for the next batch.  One launch, no host round trip. */
+int pulse_rms_merge(double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
                     float* mean_f32, float* rstd_f32, void* stream);
 
 /* Gaussian policy head (rl_games ModelA2CContinuousLogStd, fixed sigma: im.yaml:21-25):

@@ -75,9 +75,10 @@ class AmpDiscriminator:
         x = b["x"]
         # _preproc_amp_obs in train mode: normalise with the current statistics, then merge the batch (amp_agent.py:1004-1007)
         for k, src in enumerate((amp_agent, amp_replay, amp_demo)):
-            self.rms.normalize_into(src, x[k * B:(k + 1) * B])
             if update_rms:
-                self.rms.update(src)
+                self.rms.normalize_update(src, x[k * B:(k + 1) * B])
+            else:
+                self.rms.normalize_into(src, x[k * B:(k + 1) * B])
         logits = self.mlp.forward(x, train=True)                      # [3B, 1]: agent, replay, demo
         self.stats.zero_()
         with torch.cuda.device(dev):

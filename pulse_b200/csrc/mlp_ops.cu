@@ -82,6 +82,58 @@ __global__ void __launch_bounds__(256) column_moments_kernel(const float* __rest
   atomicAdd(sums + cols + c, q);
 }
 
+// ---- fused normalise + moments: ONE pass over x ---------------------------------------------------------------------
+// PHC's RunningMeanStd normalises with the statistics from BEFORE the batch and merges the batch moments afterwards
+// (running_mean_std.py:91-107), so both consume the same fp32 rows: each thread owns a column PAIR (8-byte load,
+// 4-byte bf16x2 store), walks a row chunk with 8 rows in flight, and finishes with four fp64 atomics.
+__global__ void __launch_bounds__(256) normalize_moments_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols,
+                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                __nv_bfloat16* __restrict__ out, long long ld_out,
+                                                                double* __restrict__ sums) {
+  const long long c = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= ld_out) return;
+  const bool live = c < cols;  // cols is even on this path: a pair is either fully inside or fully padding
+  const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  if (!live) {
+    for (long long r = r0; r < r1; ++r) *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = __floats2bfloat162_rn(0.0f, 0.0f);
+    return;
+  }
+  const float2 m = *reinterpret_cast<const float2*>(mean + c), rs = *reinterpret_cast<const float2*>(rstd + c);
+  double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+  long long r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldcs(reinterpret_cast<const float2*>(x + (r + i) * ldx + c));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y0 = fminf(fmaxf((v[i].x - m.x) * rs.x, -5.0f), 5.0f), y1 = fminf(fmaxf((v[i].y - m.y) * rs.y, -5.0f), 5.0f);
+      *reinterpret_cast<__nv_bfloat162*>(out + (r + i) * ld_out + c) = __floats2bfloat162_rn(y0, y1);
+      const double d0 = v[i].x, d1 = v[i].y;
+      s0 += d0;
+      s1 += d1;
+      q0 += d0 * d0;
+      q1 += d1 * d1;
+    }
+  }
+  for (; r < r1; ++r) {
+    const float2 v = *reinterpret_cast<const float2*>(x + r * ldx + c);
+    const float y0 = fminf(fmaxf((v.x - m.x) * rs.x, -5.0f), 5.0f), y1 = fminf(fmaxf((v.y - m.y) * rs.y, -5.0f), 5.0f);
+    *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = __floats2bfloat162_rn(y0, y1);
+    const double d0 = v.x, d1 = v.y;
+    s0 += d0;
+    s1 += d1;
+    q0 += d0 * d0;
+    q1 += d1 * d1;
+  }
+  if (sums == nullptr) return;  // normalise-only launch (rollout side)
+  atomicAdd(sums + c, s0);
+  atomicAdd(sums + c + 1, s1);
+  atomicAdd(sums + cols + c, q0);
+  atomicAdd(sums + cols + c + 1, q1);
+}
+
 // ---- Gaussian head ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gaussian_sample_kernel(const float* __restrict__ mu, long long ld_mu, const float* __restrict__ eps,
                                                               const float* __restrict__ logstd, long long rows, int A,
@@ -224,7 +276,7 @@ __global__ void __launch_bounds__(256) column_sum_bf16_kernel(const __nv_bfloat1
 }
 
 // ---- RunningMeanStd training-mode merge (running_mean_std.py:54-66, :96-107), one CTA ----------------------------------
-__global__ void __launch_bounds__(1024) rms_merge_kernel(const double* __restrict__ sums, long long n, int size, double* __restrict__ mean,
+__global__ void __launch_bounds__(1024) rms_merge_kernel(double* __restrict__ sums, long long n, int size, double* __restrict__ mean,
                                                          double* __restrict__ var, double* __restrict__ count, float eps,
                                                          float* __restrict__ mean_f32, float* __restrict__ rstd_f32) {
   const double cnt = *count;
@@ -240,6 +292,8 @@ __global__ void __launch_bounds__(1024) rms_merge_kernel(const double* __restric
     var[c] = nv;
     mean_f32[c] = (float)nm;
     rstd_f32[c] = 1.0f / sqrtf((float)nv + eps);
+    sums[c] = 0.0;  // consumed: the accumulator is left zeroed for the next batch (no separate memset launch)
+    sums[size + c] = 0.0;
   }
   __syncthreads();
   if (threadIdx.x == 0) *count = tot;
@@ -394,6 +448,19 @@ extern "C" int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows
   PULSE_REQUIRE(rows > 0 && cols > 0 && ld_out >= cols && ldx >= cols, "pulse_normalize_to_bf16: bad shape");
   PULSE_REQUIRE((mean == nullptr) == (rstd == nullptr), "pulse_normalize_to_bf16: mean and rstd go together");
   PULSE_REQUIRE(out_t == nullptr || ld_t >= rows, "pulse_normalize_to_bf16: ld_t < rows");
+  const bool paired = mean != nullptr && out != nullptr && out_t == nullptr && (cols % 2 == 0) && (ldx % 2 == 0) && (ld_out % 2 == 0) &&
+                      (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 4 == 0) &&
+                      (reinterpret_cast<uintptr_t>(mean) % 8 == 0) && (reinterpret_cast<uintptr_t>(rstd) % 8 == 0);
+  if (paired) {  // column-pair streaming kernel (8-byte loads, 8 rows in flight per thread)
+    const unsigned gx = static_cast<unsigned>((ld_out / 2 + 255) / 256);
+    unsigned gy = (2 * kSMs + gx - 1) / gx;
+    if (gy > rows / 8) gy = static_cast<unsigned>(rows / 8);
+    if (gy < 1) gy = 1;
+    normalize_moments_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, nullptr);
+    PULSE_LAUNCH_OK("normalize_moments_kernel");
+    return PULSE_OK;
+  }
   const long long tiles = ((ld_out + 31) / 32) * ((rows + 31) / 32);
   normalize_kernel<<<grid_for(tiles, 1, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, reinterpret_cast<__nv_bfloat16*>(out_t), ld_t);
@@ -406,6 +473,28 @@ extern "C" int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, i
   dim3 grid(static_cast<unsigned>((cols + 255) / 256), static_cast<unsigned>(rows >= 4096 ? 128 : 1));
   column_moments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, rows, cols, sums);
   PULSE_LAUNCH_OK("column_moments_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
+                                       pulse_bf16_t* out, int64_t ld_out, double* sums, void* stream) {
+  PULSE_REQUIRE(x && mean && rstd && out && sums, "pulse_normalize_moments: null buffer");
+  PULSE_REQUIRE(rows > 0 && cols > 0 && ld_out >= cols && ldx >= cols, "pulse_normalize_moments: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool paired = (cols % 2 == 0) && (ldx % 2 == 0) && (ld_out % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0) &&
+                      (reinterpret_cast<uintptr_t>(out) % 4 == 0) && (reinterpret_cast<uintptr_t>(mean) % 8 == 0) &&
+                      (reinterpret_cast<uintptr_t>(rstd) % 8 == 0);
+  if (!paired) {  // odd widths / unaligned views: the two single-purpose kernels (same results, two passes)
+    const int rc = pulse_normalize_to_bf16(x, ldx, rows, cols, mean, rstd, out, ld_out, nullptr, 0, stream);
+    if (rc != PULSE_OK) return rc;
+    return pulse_column_moments(x, ldx, rows, cols, sums, stream);
+  }
+  const unsigned gx = static_cast<unsigned>((ld_out / 2 + 255) / 256);
+  unsigned gy = (2 * kSMs + gx - 1) / gx;  // two 256-thread CTAs per SM, 8 x 8-byte loads in flight per thread
+  if (gy > rows / 8) gy = static_cast<unsigned>(rows / 8);
+  if (gy < 1) gy = 1;
+  normalize_moments_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, sums);
+  PULSE_LAUNCH_OK("normalize_moments_kernel");
   return PULSE_OK;
 }
 
@@ -431,7 +520,7 @@ extern "C" int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, v
 extern "C" int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream) {
   PULSE_REQUIRE(x && out && rows > 0 && cols > 0, "pulse_column_sum_bf16: bad argument");
   const unsigned gx = static_cast<unsigned>((cols + 127) / 128);
-  unsigned gy = static_cast<unsigned>((rows + 255) / 256);
+  unsigned gy = static_cast<unsigned>((rows + 31) / 32);  // >= 2 rows per lane: short chunks, many CTAs (latency-bound otherwise)
   const unsigned cap = (4 * kSMs + gx - 1) / gx;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
@@ -441,7 +530,7 @@ extern "C" int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t
   return PULSE_OK;
 }
 
-extern "C" int pulse_rms_merge(const double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
+extern "C" int pulse_rms_merge(double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
                                float* mean_f32, float* rstd_f32, void* stream) {
   PULSE_REQUIRE(sums && mean && var && count && mean_f32 && rstd_f32 && n >= 2 && size > 0, "pulse_rms_merge: bad argument");
   rms_merge_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(sums, n, size, mean, var, count, eps, mean_f32, rstd_f32);

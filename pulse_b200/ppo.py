@@ -41,19 +41,32 @@ class RunningMeanStdB200:
         self.mean_f32.copy_(self.running_mean)
         self.rstd_f32.copy_(1.0 / torch.sqrt(self.running_var.float() + self.eps))
 
+    def _merge(self, lib, n: int) -> None:
+        _lib.check(lib.pulse_rms_merge(self._sums.data_ptr(), n, self.size, self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                       self.count.data_ptr(), self.eps, self.mean_f32.data_ptr(), self.rstd_f32.data_ptr(),
+                                       _lib.current_stream(self.device)), "pulse_rms_merge")     # leaves _sums zeroed
+
     def update(self, x: torch.Tensor) -> None:
         """Training-mode statistics update (:96-107): Welford merge with the batch mean / unbiased variance."""
         if self.frozen:
             return
         lib = _lib.load()
-        n = x.shape[0]
-        self._sums.zero_()
         with torch.cuda.device(self.device):
-            _lib.check(lib.pulse_column_moments(x.data_ptr(), x.stride(0), n, self.size, self._sums.data_ptr(), _lib.current_stream(self.device)),
-                       "pulse_column_moments")
-            _lib.check(lib.pulse_rms_merge(self._sums.data_ptr(), n, self.size, self.running_mean.data_ptr(), self.running_var.data_ptr(),
-                                           self.count.data_ptr(), self.eps, self.mean_f32.data_ptr(), self.rstd_f32.data_ptr(),
-                                           _lib.current_stream(self.device)), "pulse_rms_merge")
+            _lib.check(lib.pulse_column_moments(x.data_ptr(), x.stride(0), x.shape[0], self.size, self._sums.data_ptr(),
+                                                _lib.current_stream(self.device)), "pulse_column_moments")
+            self._merge(lib, x.shape[0])
+
+    def normalize_update(self, x: torch.Tensor, out: torch.Tensor) -> None:
+        """forward() in training mode (:91-107): normalise with the CURRENT statistics, then merge this batch -- one
+        pass over x (pulse_normalize_moments) + the merge launch."""
+        if self.frozen:
+            return self.normalize_into(x, out)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pulse_normalize_moments(x.data_ptr(), x.stride(0), x.shape[0], self.size, self.mean_f32.data_ptr(),
+                                                   self.rstd_f32.data_ptr(), out.data_ptr(), out.stride(0), self._sums.data_ptr(),
+                                                   _lib.current_stream(self.device)), "pulse_normalize_moments")
+            self._merge(lib, x.shape[0])
 
     def normalize_into(self, x: torch.Tensor, out: torch.Tensor, out_t: Optional[torch.Tensor] = None) -> None:
         normalize_to_bf16(x, self.mean_f32, self.rstd_f32, out, out_t)
@@ -94,6 +107,7 @@ class PPOPolicy:
         self._bufs: Dict[tuple, dict] = {}
         self.stats = torch.zeros(6, dtype=torch.float64, device=self.device)
         self.lib = _lib.load()
+        self._side = None
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, M: int, train: bool):
@@ -144,11 +158,28 @@ class PPOPolicy:
         stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
         M = obs.shape[0]
         b = self._buf(M, True)
-        self.obs_rms.normalize_into(obs, b["x"])            # normalise with the statistics BEFORE this batch's update
-        if update_obs_rms:
-            self.obs_rms.update(obs)                         # running_mean_std.py:96-107 (train mode)
+        # Three independent chains -- actor, critic, discriminator -- run on three streams (fork/join with events, so
+        # the whole minibatch still captures into ONE CUDA graph): the persistent GEMMs of one chain fill the partial
+        # last wave of another, and the HBM-bound normalise / moments / loss kernels overlap with tensor-core work.
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_critic, s_disc = self._side
+        self.flat.zero_grad()                                # weight / bias gradients are accumulated with atomics
+        self.stats.zero_()
+        if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
+            s_disc.wait_stream(main)
+            with torch.cuda.stream(s_disc):
+                self.disc.loss_backward(*amp)
+        if update_obs_rms:                                   # normalise with the statistics BEFORE this batch, then merge it
+            self.obs_rms.normalize_update(obs, b["x"])       # (running_mean_std.py:91-107, train mode), one pass over obs
+        else:
+            self.obs_rms.normalize_into(obs, b["x"])
+        s_critic.wait_stream(main)
+        with torch.cuda.stream(s_critic):
+            value = self.critic.forward(b["x"], train=True)
         mu = self.actor.forward(b["x"], train=True)
-        value = self.critic.forward(b["x"], train=True)
+        main.wait_stream(s_critic)
         a = _lib.PpoLossArgs(
             mu=mu.data_ptr(), ld_mu=mu.stride(0), value=value.data_ptr(), ld_value=value.stride(0), actions=actions.data_ptr(),
             old_neglogp=old_neglogp.data_ptr(), advantages=advantages.data_ptr(), returns=returns.data_ptr(),
@@ -156,14 +187,15 @@ class PPOPolicy:
             e_clip=self.e_clip, critic_coef=self.critic_coef, bounds_coef=self.bounds_coef,
             dmu=b["dmu"].data_ptr(), ld_dmu=b["dmu"].stride(0), dvalue=b["dv"].data_ptr(), ld_dv=b["dv"].stride(0),
             stats=self.stats.data_ptr())
-        self.stats.zero_()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream(self.device)), "pulse_ppo_loss")
-        self.flat.zero_grad()                                # weight / bias gradients are accumulated with atomics
+        s_critic.wait_stream(main)
+        with torch.cuda.stream(s_critic):
+            self.critic.backward(b["dv"], M)
         self.actor.backward(b["dmu"], M)
-        self.critic.backward(b["dv"], M)
-        if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
-            self.disc.loss_backward(*amp)
+        main.wait_stream(s_critic)
+        if amp is not None:
+            main.wait_stream(s_disc)
         if world_size > 1:
             from .dist_utils import average_gradients
             average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)

@@ -94,6 +94,32 @@ def test_normalize_and_moments_match_reference_semantics():
     assert torch.equal(out_t.T.contiguous(), out)
 
 
+@pytest.mark.parametrize("rows,cols", [(300, 934), (4096, 1960), (37, 10), (64, 7)])
+def test_fused_normalize_moments_equals_two_pass(rows, cols):
+    """pulse_normalize_moments (one pass) == normalise with the OLD statistics, then merge (running_mean_std.py:91-107)."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.nets import pad8
+    from pulse_b200.ppo import RunningMeanStdB200
+    g = torch.Generator(device=DEV).manual_seed(rows + cols)
+    fused, two, ref = RunningMeanStdB200(cols, DEV), RunningMeanStdB200(cols, DEV), po.RunningMeanStd(cols)
+    for k in range(3):
+        x = torch.randn(rows, cols, device=DEV, generator=g) * (k + 1) + k
+        o1 = torch.full((rows, pad8(cols)), 7.0, device=DEV, dtype=torch.bfloat16)
+        o2 = torch.zeros_like(o1)
+        fused.normalize_update(x, o1)
+        two.normalize_into(x, o2)
+        two.update(x)
+        y = ref.normalize(x.cpu())
+        ref.update(x.cpu())
+        assert torch.equal(o1, o2)                       # same fp32 arithmetic, same bf16 rounding, padding zeroed
+        torch.testing.assert_close(o1[:, :cols].float().cpu(), y, atol=2e-2, rtol=1e-2)
+        torch.testing.assert_close(fused.running_mean, two.running_mean, atol=1e-12, rtol=1e-12)
+        torch.testing.assert_close(fused.running_var, two.running_var, atol=1e-10, rtol=1e-10)
+        torch.testing.assert_close(fused.running_mean.cpu(), ref.mean, atol=5e-6, rtol=5e-6)
+        assert float(fused.count) == float(two.count) == 1 + (k + 1) * rows
+    assert torch.all(fused._sums == 0)
+
+
 def test_policy_forward_and_update_match_fp32_reference():
     from oracle import pulse_oracle as po
     from pulse_b200.ppo import PPOPolicy
