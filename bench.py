@@ -251,7 +251,7 @@ def main():
     from pulse_b200 import _lib
     from pulse_b200.humanoid_im import HumanoidImCompute
     from pulse_b200.motion_lib import MotionLibB200
-    from pulse_b200.nets import pad8
+    from pulse_b200.nets import pad_k
     from pulse_b200.ppo import PPOPolicy
     from pulse_b200.rollout import discount_values
     from tools.synth import device_step_inputs, device_tables
@@ -278,7 +278,7 @@ def main():
     comp = HumanoidImCompute(ml)
     policy = PPOPolicy(device=dev, seed=0, with_disc=True)   # replicated: same seed on every rank (Horovod broadcast equivalent)
     disc = policy.disc
-    amp_x = torch.zeros(T * n, pad8(1960), device=dev, dtype=torch.bfloat16)
+    amp_x = torch.zeros(T * n, pad_k(1960), device=dev, dtype=torch.bfloat16)
     AMP_MB = 4096                                        # amp_minibatch_size (im.yaml:81)
     REPLAY = 200000                                      # amp_replay_buffer_size / amp_obs_demo_buffer_size (im.yaml:77-78)
     replay_buf = torch.randn(REPLAY, 1960, device=dev)   # AMP replay ring (amp_agent.py:1043-1057), pre-filled

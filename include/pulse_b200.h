@@ -275,6 +275,17 @@ int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows, int64_t c
 int pulse_rms_merge(double* sums, int64_t n, int32_t size, double* mean, double* var, double* count, float eps,
                     float* mean_f32, float* rstd_f32, void* stream);
 
+/* Single-output head (the critic's `value` Linear, network_builder.py:171; the discriminator's `_disc_logits`,
+ * amp_network_builder.py:245-249): out[m] = h[m,:] . w + bias.  h bf16 [rows, k] (row stride ldh), w bf16 [k]. */
+int pulse_head1_forward(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int32_t k, const pulse_bf16_t* w, const float* bias, float* out,
+                        int64_t ldo, void* stream);
+
+/* Backward of that head through the ReLU below it, ONE pass over h:  dh[m,j] = dv[m] w[j] (h[m,j] > 0) (bf16, may be
+ * NULL);  dw[j] += sum_m dv[m] h[m,j];  db += sum_m dv[m];  dbias_prev[j] += sum_m dh[m,j] (bias gradient of the layer
+ * that produced h; may be NULL).  k <= 2048, multiple of 8. */
+int pulse_head1_backward(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int32_t k, const pulse_bf16_t* dv, int64_t ld_dv,
+                         const pulse_bf16_t* w, pulse_bf16_t* dh, int64_t ld_dh, float* dw, float* db, float* dbias_prev, void* stream);
+
 /* Gaussian policy head (rl_games ModelA2CContinuousLogStd, fixed sigma: im.yaml:21-25):
  * actions = mu + exp(logstd)*eps;  neglogp = 0.5*sum(((a-mu)/sigma)^2) + 0.5*A*log(2*pi) + sum(logstd). */
 int pulse_gaussian_sample(const float* mu, int64_t ld_mu, const float* eps, const float* logstd, int64_t rows, int32_t num_actions,

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .dense import gemm
-from .nets import MLP, FlatParams, pad8, pick_split
+from .nets import MLP, FlatParams, pad_k, pick_split
 from .ppo import RunningMeanStdB200
 
 
@@ -27,7 +27,7 @@ class AmpDiscriminator:
     def __init__(self, flat: FlatParams, amp_obs_size: int = 1960, units: Sequence[int] = (1024, 512), disc_coef: float = 5.0,
                  logit_reg: float = 0.01, grad_penalty: float = 5.0, weight_decay: float = 0.0001, reward_scale: float = 2.0):
         self.flat, self.device = flat, flat.device
-        self.size, self.Kp = amp_obs_size, pad8(amp_obs_size)
+        self.size, self.Kp = amp_obs_size, pad_k(amp_obs_size)
         self.mlp = MLP(flat, amp_obs_size, units, 1, "relu")
         if len(units) != 2:
             raise _lib.PulseError("the analytic gradient penalty is written for the 2-hidden-layer discriminator of im.yaml")

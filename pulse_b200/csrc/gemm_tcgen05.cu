@@ -117,6 +117,7 @@ __device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
+// issue only: the registers are valid after tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -127,8 +128,8 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == PULSE_ACT_RELU) return fmaxf(x, 0.0f);
@@ -256,18 +257,49 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       const int split = w / tiles, t = w - split * tiles;
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
       const int acc = lw & 1;
-      g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
       const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
       const int row = m0 + lrow;
       const bool row_ok = row < M;
+      // ReLU-derivative gate: the saved activations do not depend on the accumulator, so this thread's 128 gate values
+      // (256 contiguous bytes of its row) are fetched BEFORE waiting for the MMAs -- their latency hides behind the main
+      // loop -- and folded to one bit each (4 registers) so nothing but the mask stays live across the wait.
+      const bool gate_fast = ep.gate != nullptr && ep.gate_mode == PULSE_ACT_RELU && (ep.ldg & 7) == 0 && n0 + chalf * 128 + 128 <= N;
+      unsigned gmask[4] = {0u, 0u, 0u, 0u};
+      if (gate_fast && row_ok) {
+        const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg +
+                                                        n0 + chalf * 128);
+        uint4 u[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = __ldg(g + i);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+          unsigned m8 = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h[q]);
+            m8 |= (f.x > 0.0f ? 1u : 0u) << (2 * q);
+            m8 |= (f.y > 0.0f ? 1u : 0u) << (2 * q + 1);
+          }
+          gmask[i >> 2] |= m8 << ((i & 3) * 8);
+        }
+      }
+      g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
+      const unsigned tmem_row = tmem_d + (static_cast<unsigned>(quarter * 32) << 16);
       float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(ep.accumulate ? 0 : split) * ep.split_stride : nullptr;
+      unsigned r[32];
+      tmem_ld32(tmem_row + static_cast<unsigned>(chalf * 4 * 32), r);
 #pragma unroll 1
       for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
-        unsigned r[32];
-        tmem_ld32(tmem_d + (static_cast<unsigned>(quarter * 32) << 16) + static_cast<unsigned>(c * 32), r);
-        if (c == chalf * 4 + 3) {
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+        if (c != chalf * 4 + 3) {
+          tmem_ld32(tmem_row + static_cast<unsigned>((c + 1) * 32), r);  // next 32 columns stream in under this chunk's math + stores
+        } else {
           // all of this warp's TMEM reads for the item are done: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
@@ -275,9 +307,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         }
         const int col0 = n0 + c * 32;
         const bool full = col0 + 32 <= N;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
         if (ep.bias != nullptr) {
           if (full) {
 #pragma unroll
@@ -301,7 +330,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ep.act);
         }
-        if (ep.gate != nullptr && row_ok) {
+        if (gate_fast) {
+          const int cc = c & 3;
+          const unsigned mk = cc == 0 ? gmask[0] : (cc == 1 ? gmask[1] : (cc == 2 ? gmask[2] : gmask[3]));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.0f;
+        } else if (ep.gate != nullptr && row_ok) {
           const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
           if (full && (ep.ldg & 7) == 0) {
 #pragma unroll

@@ -429,6 +429,110 @@ __global__ void __launch_bounds__(256) refresh_weight_kernel(const float* __rest
   }
 }
 
+// ---- single-output head (critic value, discriminator logit): GEMV forward and ONE fused backward pass ---------------
+// A [M,K] x [K,1] product has no tensor-core shape: the 128 x 256 MMA tile would be 255/256 padding and the three
+// backward GEMMs (K = 1 dgrad, M = 1 wgrad) are pure epilogue / pure reduction.  Both directions are HBM streams
+// over the last hidden activation h [M,K] bf16: forward reads it once; backward reads it once and writes dh once.
+__global__ void __launch_bounds__(256) head1_forward_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, long long rows, int K,
+                                                            const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ out, long long ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float b = bias != nullptr ? __ldg(bias) : 0.0f;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const __nv_bfloat16* hr = h + r * ldh;
+    float acc = 0.0f;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(hr + k));
+      const uint4 wu = __ldg(reinterpret_cast<const uint4*>(w + k));
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wu);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = __bfloat1622float2(a2[q]), ww = __bfloat1622float2(w2[q]);
+        acc = fmaf(a.x, ww.x, acc);
+        acc = fmaf(a.y, ww.y, acc);
+      }
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) out[r * ldo] = acc + b;
+  }
+}
+
+// dh[m,k] = dv[m] * w[k] * (h[m,k] > 0);  dw[k] += sum_m dv[m] h[m,k];  db += sum_m dv[m];  dbias_prev[k] += sum_m dh[m,k].
+// Thread = 8 columns (one 16-byte load / store); blockDim.x / (K/8) row lanes per CTA; fp32 atomics once per CTA.
+__global__ void __launch_bounds__(256) head1_backward_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, long long rows, int K,
+                                                             const __nv_bfloat16* __restrict__ dv, long long ld_dv,
+                                                             const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dh, long long ld_dh,
+                                                             float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dbias_prev) {
+  extern __shared__ float red[];  // [row lanes][2 * K + 1]
+  const int groups = K >> 3;                     // column groups of 8
+  const int lanes = blockDim.x / groups;         // row lanes per CTA (host guarantees >= 1)
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+  float aw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ac[8] = {0, 0, 0, 0, 0, 0, 0, 0}, adb = 0.0f;
+  if (rl < lanes) {
+    float wf[8];
+    {
+      const uint4 wu = __ldg(reinterpret_cast<const uint4*>(w + cg * 8));
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wu);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(w2[q]);
+        wf[2 * q] = f.x;
+        wf[2 * q + 1] = f.y;
+      }
+    }
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(h + r * ldh + cg * 8));
+      const float d = __bfloat162float(dv[r * ld_dv]);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = __bfloat1622float2(a2[q]);
+        aw[2 * q] = fmaf(d, a.x, aw[2 * q]);
+        aw[2 * q + 1] = fmaf(d, a.y, aw[2 * q + 1]);
+        o[2 * q] = a.x > 0.0f ? d * wf[2 * q] : 0.0f;
+        o[2 * q + 1] = a.y > 0.0f ? d * wf[2 * q + 1] : 0.0f;
+        ac[2 * q] += o[2 * q];
+        ac[2 * q + 1] += o[2 * q + 1];
+      }
+      if (dh != nullptr) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+        uint4 st;
+        st.x = *reinterpret_cast<unsigned*>(&p0);
+        st.y = *reinterpret_cast<unsigned*>(&p1);
+        st.z = *reinterpret_cast<unsigned*>(&p2);
+        st.w = *reinterpret_cast<unsigned*>(&p3);
+        *reinterpret_cast<uint4*>(dh + r * ld_dh + cg * 8) = st;
+      }
+      if (cg == 0) adb += d;
+    }
+    float* mine = red + (long long)rl * (2 * K + 1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      mine[cg * 8 + q] = aw[q];
+      mine[K + cg * 8 + q] = ac[q];
+    }
+    if (cg == 0) mine[2 * K] = adb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * K + 1; i += blockDim.x) {
+    float t = 0.0f;
+    for (int l = 0; l < lanes; ++l) t += red[(long long)l * (2 * K + 1) + i];
+    if (i < K) {
+      atomicAdd(dw + i, t);
+    } else if (i < 2 * K) {
+      if (dbias_prev != nullptr) atomicAdd(dbias_prev + (i - K), t);
+    } else if (db != nullptr) {
+      atomicAdd(db, t);
+    }
+  }
+}
+
 inline unsigned grid_for(long long work_items, int per_block, int waves = 8) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(kSMs) * waves;
@@ -495,6 +599,36 @@ extern "C" int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows
   if (gy < 1) gy = 1;
   normalize_moments_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, sums);
   PULSE_LAUNCH_OK("normalize_moments_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_head1_forward(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int32_t k, const pulse_bf16_t* w, const float* bias,
+                                   float* out, int64_t ldo, void* stream) {
+  PULSE_REQUIRE(h && w && out && rows > 0 && k > 0 && ldo >= 1, "pulse_head1_forward: bad argument");
+  PULSE_REQUIRE(k % 8 == 0 && ldh % 8 == 0 && reinterpret_cast<uintptr_t>(h) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0,
+                "pulse_head1_forward: K, ldh multiples of 8 and 16-byte aligned operands required");
+  head1_forward_kernel<<<grid_for(rows, 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), ldh, rows, k, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, ldo);
+  PULSE_LAUNCH_OK("head1_forward_kernel");
+  return PULSE_OK;
+}
+
+extern "C" int pulse_head1_backward(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int32_t k, const pulse_bf16_t* dv, int64_t ld_dv,
+                                    const pulse_bf16_t* w, pulse_bf16_t* dh, int64_t ld_dh, float* dw, float* db, float* dbias_prev,
+                                    void* stream) {
+  PULSE_REQUIRE(h && dv && w && dw && rows > 0 && k > 0 && ld_dv >= 1, "pulse_head1_backward: bad argument");
+  PULSE_REQUIRE(k % 8 == 0 && k <= 2048 && ldh % 8 == 0 && (dh == nullptr || ld_dh % 8 == 0), "pulse_head1_backward: K <= 2048, K and lds multiples of 8");
+  PULSE_REQUIRE(reinterpret_cast<uintptr_t>(h) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(dh) % 16 == 0,
+                "pulse_head1_backward: 16-byte aligned operands required");
+  const int groups = k / 8, lanes = 256 / groups;
+  const size_t smem = static_cast<size_t>(lanes) * (2 * k + 1) * sizeof(float);
+  long long blocks = (rows + 8LL * lanes - 1) / (8LL * lanes);  // >= 8 rows per row lane
+  if (blocks > 2 * kSMs) blocks = 2 * kSMs;
+  if (blocks < 1) blocks = 1;
+  head1_backward_kernel<<<static_cast<unsigned>(blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), ldh, rows, k, reinterpret_cast<const __nv_bfloat16*>(dv), ld_dv,
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(dh), ld_dh, dw, db, dbias_prev);
+  PULSE_LAUNCH_OK("head1_backward_kernel");
   return PULSE_OK;
 }
 

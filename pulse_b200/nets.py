@@ -26,6 +26,13 @@ def pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def pad_k(n: int) -> int:
+    """Leading dimension of a GEMM operand with n useful columns: a multiple of 64 bf16 (128 bytes) once n > 64, so every
+    64-column TMA box row starts on a 128-byte line (a 936-wide row makes each box row straddle an extra 32-byte sector:
+    measured 54.7 -> 39.7 us on the 16384 x 1024 x 934 layer)."""
+    return pad8(n) if n <= 64 else (n + 63) // 64 * 64
+
+
 def pick_split(tiles: int, num_kb: int, sms: int = 148, epilogue_kb: int = 24) -> int:
     """Split-K factor for a weight-gradient GEMM on the persistent kernel: minimise rounds x (k-blocks per item +
     epilogue cost in k-block equivalents), where rounds = ceil(tiles * splits / SMs)."""
@@ -57,7 +64,7 @@ class FlatParams:
         n = 1
         for s in shape:
             n *= s
-        self._numel += (n + 7) // 8 * 8  # every tensor 16-byte aligned in the fp32 AND the bf16 buffer
+        self._numel += (n + 63) // 64 * 64  # every tensor 128-byte aligned in the bf16 operand buffer (TMA box rows on line starts)
         self._shapes.append((off, tuple(shape)))
         return len(self._shapes) - 1
 
@@ -80,7 +87,7 @@ class FlatParams:
         return getattr(self, what)[off:off + n].view(*shape)
 
     def view_padded(self, idx: int, what: str, n: int) -> torch.Tensor:
-        """first n elements of slot idx INCLUDING its alignment padding (slots are padded to multiples of 8)."""
+        """first n elements of slot idx INCLUDING its alignment padding (slots are padded to multiples of 64)."""
         off, _ = self._shapes[idx]
         return getattr(self, what)[off:off + n]
 
@@ -108,11 +115,11 @@ class FlatParams:
 
 
 class Dense:
-    """One Linear layer: W [N, Kp] (K padded to a multiple of 8 with zero columns), b [N]."""
+    """One Linear layer: W [N, Kp] (K padded with zero columns, see pad_k), b [N]."""
 
     def __init__(self, flat: FlatParams, in_features: int, out_features: int, act: Optional[str]):
         self.K, self.N, self.act = in_features, out_features, act
-        self.Kp, self.Np = pad8(in_features), pad8(out_features)
+        self.Kp, self.Np = pad_k(in_features), pad_k(out_features)
         self.flat = flat
         self.w_idx = flat.reserve(out_features, self.Kp)
         self.b_idx = flat.reserve(out_features)
@@ -166,7 +173,7 @@ class MLP:
         self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], act) for i in range(len(units))]
         if head is not None:
             self.layers.append(Dense(flat, sizes[-1], head, None))
-        self.in_features, self.Kp0 = in_features, pad8(in_features)
+        self.in_features, self.Kp0 = in_features, pad_k(in_features)
         self._ws: Dict[int, dict] = {}
 
     def init_default(self, gen=None):
@@ -195,6 +202,11 @@ class MLP:
             self._ws[key] = ws
         return self._ws[key]
 
+    def _head1(self, i: int) -> bool:
+        """Layer i is a single-output head on top of a ReLU layer narrow enough for the fused GEMV kernels."""
+        l = self.layers[i]
+        return i == len(self.layers) - 1 and i > 0 and l.N == 1 and self.layers[i - 1].act == "relu" and l.Kp <= 2048
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, train: bool = False) -> torch.Tensor:
         """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer).
@@ -204,7 +216,13 @@ class MLP:
         h = x
         for i, l in enumerate(self.layers):
             last = i == len(self.layers) - 1
-            if last:
+            if last and self._head1(i):
+                # [M,K] x [K,1]: no tensor-core shape -- one HBM pass over h (pulse_head1_forward)
+                with torch.cuda.device(self.flat.device):
+                    _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), l.bias.data_ptr(),
+                                                               ws["out"].data_ptr(), ws["out"].stride(0),
+                                                               _lib.current_stream(self.flat.device)), "pulse_head1_forward")
+            elif last:
                 gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
             else:
                 gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)
@@ -222,10 +240,22 @@ class MLP:
         dev = self.flat.device
         dy = dout
         head = self.layers[-1]
-        with torch.cuda.device(dev):  # bias gradient of the head: column sums of dout
-            _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
-                       "pulse_column_sum_bf16")
-        for i in reversed(range(len(self.layers))):
+        top = len(self.layers) - 1
+        if self._head1(top):
+            # single-output head: bias gradient, weight gradient, gated input gradient and the bias gradient of the layer
+            # below in ONE pass over the last hidden activation (replaces a column sum and three degenerate GEMMs)
+            prev, h, dh = self.layers[top - 1], ws["act"][top - 1], ws["dact"][top - 1]
+            with torch.cuda.device(dev):
+                _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), M, head.Kp, dy.data_ptr(), dy.stride(0), head.w_bf16.data_ptr(),
+                                                    dh.data_ptr(), dh.stride(0), head.weight_grad.data_ptr(), head.bias_grad.data_ptr(),
+                                                    self.flat.view_padded(prev.b_idx, "grads", prev.Np).data_ptr(), _lib.current_stream(dev)),
+                           "pulse_head1_backward")
+            dy, top = dh, top - 1
+        else:
+            with torch.cuda.device(dev):  # bias gradient of the head: column sums of dout
+                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
+                           "pulse_column_sum_bf16")
+        for i in reversed(range(top + 1)):
             l = self.layers[i]
             x_in = ws["x"] if i == 0 else ws["act"][i - 1]
             # wgrad: dW [N, Kp] += dY^T . X, both operands MN-major (reduction over the batch rows), fp32 atomics across split-K

@@ -19,7 +19,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import _lib
-from .nets import MLP, FlatParams, normalize_to_bf16, pad8
+from .nets import MLP, FlatParams, normalize_to_bf16, pad8, pad_k
 
 
 class RunningMeanStdB200:
@@ -103,7 +103,7 @@ class PPOPolicy:
         self.logstd = torch.full((num_actions,), logstd, device=self.device)  # fixed_sigma, const_initializer (im.yaml:21-25)
         self.obs_rms = RunningMeanStdB200(obs_size, self.device)
         self.value_rms = RunningMeanStdB200(1, self.device) if normalize_value else None
-        self.Kp = pad8(obs_size)
+        self.Kp = pad_k(obs_size)
         self._bufs: Dict[tuple, dict] = {}
         self.stats = torch.zeros(6, dtype=torch.float64, device=self.device)
         self.lib = _lib.load()

@@ -212,3 +212,31 @@ def test_disc_loss_and_gradient_penalty_match_autograd():
     # rewards: -log(max(1 - sigmoid(D), 1e-4)) * 2
     r = disc.rewards(agent)
     torch.testing.assert_close(r, po.disc_reward(ref_mlp(xn(agent)).detach()), atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("rows,k", [(1000, 512), (37, 64), (4096, 2048), (5, 8)])
+def test_single_output_head_kernels(rows, k):
+    """pulse_head1_forward / pulse_head1_backward against fp32 torch on the same bf16 operands."""
+    from pulse_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(rows * 7 + k)
+    h = torch.relu(torch.randn(rows, k, device=DEV, generator=g)).bfloat16()
+    w = (torch.randn(k, device=DEV, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(1, device=DEV, generator=g)
+    dv = torch.zeros(rows, 8, device=DEV, dtype=torch.bfloat16)
+    dv[:, 0] = (torch.randn(rows, device=DEV, generator=g) * 0.01).bfloat16()
+    out = torch.zeros(rows, 1, device=DEV)
+    st = _lib.current_stream(DEV)
+    _lib.check(lib.pulse_head1_forward(h.data_ptr(), h.stride(0), rows, k, w.data_ptr(), bias.data_ptr(), out.data_ptr(), 1, st), "fwd")
+    ref = h.float() @ w.float() + bias
+    torch.testing.assert_close(out[:, 0], ref, atol=1e-4, rtol=1e-4)
+    dh = torch.full((rows, k), 3.0, device=DEV, dtype=torch.bfloat16)
+    dw, db, dbp = torch.ones(k, device=DEV), torch.ones(1, device=DEV), torch.ones(k, device=DEV)
+    _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), rows, k, dv.data_ptr(), dv.stride(0), w.data_ptr(), dh.data_ptr(), dh.stride(0),
+                                        dw.data_ptr(), db.data_ptr(), dbp.data_ptr(), st), "bwd")
+    d = dv[:, 0].float()
+    dh_ref = d[:, None] * w.float()[None, :] * (h.float() > 0)
+    assert torch.equal(dh, dh_ref.bfloat16())                          # single products: exact up to the bf16 rounding
+    torch.testing.assert_close(dw, 1 + (d[:, None] * h.float()).sum(0), atol=1e-4, rtol=1e-4)   # ADDS into the gradient buffers
+    torch.testing.assert_close(db, 1 + d.sum().reshape(1), atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(dbp, 1 + dh_ref.sum(0), atol=1e-4, rtol=1e-4)
