@@ -232,6 +232,7 @@ typedef struct {
   float* colsum;             /* [N] += column sums of the final values (bias gradient of the layer whose dY this GEMM writes), or NULL */
   int32_t accumulate;        /* 1: out_f32 += result with fp32 atomics (weight gradients; caller zeroes), 0: overwrite */
   int32_t reserved;
+  double* sumsq;             /* *sumsq += sum of squares of the final values over the valid [M,N] region (fp64 atomics), or NULL */
 } pulse_gemm_epilogue_t;
 
 #define PULSE_GEMM_A_MN 1u   /* A is given as [K, M] row-major (the reduction dimension is the ROW index) */

@@ -76,7 +76,7 @@ class GemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int32), ("gate_mode", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
         ("alpha", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int64), ("out_t", C.c_void_p), ("ldot", C.c_int64),
         ("out_f32", C.c_void_p), ("ldf", C.c_int64), ("split_stride", C.c_int64), ("preact", C.c_void_p), ("ldp", C.c_int64),
-        ("colsum", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+        ("colsum", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32), ("sumsq", C.c_void_p),
     ]
 
 

@@ -56,7 +56,7 @@ class AmpDiscriminator:
             self._bufs[B] = {
                 "x": torch.zeros(3 * B, self.Kp, device=dev, dtype=bf), "dlogit": torch.zeros(3 * B, 8, device=dev, dtype=bf),
                 "g2": torch.zeros(B, L2.Np, device=dev, dtype=bf), "g1": torch.zeros(B, L1.Np, device=dev, dtype=bf),
-                "Gb": torch.zeros(B, self.Kp, device=dev, dtype=bf), "Gf": torch.zeros(B, self.Kp, device=dev),
+                "Gb": torch.zeros(B, self.Kp, device=dev, dtype=bf),
                 "du": torch.zeros(B, L1.Np, device=dev, dtype=bf), "scratch": torch.zeros(B, L2.Np, device=dev, dtype=bf),
                 "split1": pick_split(((L1.N + 127) // 128) * ((L1.Kp + 255) // 256), (B + 63) // 64),
                 "split2": pick_split(((L2.N + 127) // 128) * ((L2.Kp + 255) // 256), (B + 63) // 64),
@@ -95,7 +95,7 @@ class AmpDiscriminator:
                                                  _lib.current_stream(dev)), "pulse_relu_mask_scale")
         gemm(b["g2"][:, :L2.N], L2.w_bf16, b_mn=True, gate=h1, gate_mode="relu", out=b["g1"])             # g1 = m1 * (g2 W2)
         c = 2.0 * self.disc_coef * self.grad_penalty / B
-        gemm(b["g1"][:, :L1.N], L1.w_bf16, b_mn=True, alpha=c, out=b["Gb"], out_f32=b["Gf"])              # G = c * g1 W1
+        gemm(b["g1"][:, :L1.N], L1.w_bf16, b_mn=True, alpha=c, out=b["Gb"], sumsq=self.stats[4:])         # G = c * g1 W1, stats[4] += sum G^2
         gemm(b["g1"][:, :L1.N], b["Gb"], a_mn=True, b_mn=True, out_f32=L1.weight_grad, accumulate=True, split_k=b["split1"])  # dW1 += g1^T G
         gemm(b["Gb"], L1.w_bf16, gate=h1, gate_mode="relu", out=b["du"])                                  # du = m1 * (G W1^T)
         gemm(b["g2"][:, :L2.N], b["du"][:, :L1.N], a_mn=True, b_mn=True, out_f32=L2.weight_grad, accumulate=True, split_k=b["split2"])  # dW2 += g2^T du
@@ -104,7 +104,6 @@ class AmpDiscriminator:
         # ---- logit regulariser and weight decay (amp_agent.py:905-908, :932-937): d/dw coef*sum(w^2) = 2*coef*w ------
         with torch.cuda.device(dev):
             st = _lib.current_stream(dev)
-            _lib.check(lib.pulse_sum_squares(b["Gf"].data_ptr(), b["Gf"].numel(), self.stats[4:].data_ptr(), st), "pulse_sum_squares")
             _lib.check(lib.pulse_sum_squares(L3.weight.data_ptr(), L3.weight.numel(), self.stats[5:].data_ptr(), st), "pulse_sum_squares")
             for l in (L1, L2, L3):
                 coef = 2.0 * self.disc_coef * (self.weight_decay + (self.logit_reg if l is L3 else 0.0))

@@ -30,7 +30,7 @@ def gemm_nt(a, b, **kw) -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None, act=None,
          gate: Optional[torch.Tensor] = None, gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
          out_t: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
-         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1) -> None:
+         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, sumsq: Optional[torch.Tensor] = None) -> None:
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  a is [M,K] (K-major) or, with a_mn, [K,M] (MN-major: the reduction index
     is the row); likewise b is [N,K] or, with b_mn, [K,N].  No operand is ever transposed in memory."""
     lib = _lib.load()
@@ -81,6 +81,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if colsum.dtype != torch.float32 or colsum.numel() < N:
             raise _lib.PulseError("colsum must be fp32 [N]")
         ep.colsum = colsum.data_ptr()
+    if sumsq is not None:
+        if sumsq.dtype != torch.float64 or sumsq.numel() < 1:
+            raise _lib.PulseError("sumsq must be an fp64 accumulator")
+        ep.sumsq = sumsq.data_ptr()
     flags = (_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0)
     with torch.cuda.device(a.device):
         _lib.check(lib.pulse_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, C.byref(ep), split_k, flags,

@@ -113,3 +113,28 @@ def test_gemm_rejects_bad_arguments():
         gemm_nt(a, b, out_f32=torch.zeros(128, 128, device=dev))  # lda = 70 not a multiple of 8
     with pytest.raises(PulseError):
         gemm_nt(a[:, :64].contiguous(), b[:, :64].contiguous())      # no output
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 128), (300, 1000, 72), (4096, 1960, 1024)])
+def test_gemm_relu_gate_mask_and_sumsq(M, N, K):
+    """Fast ReLU-gate path (128 gate values per thread folded to a bit mask before the accumulator wait) on full and ragged
+    128-column groups, including -0.0 / tiny / negative gate values, plus the fused sum-of-squares reduction."""
+    from pulse_b200.dense import gemm
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    b = (torch.randn(K, N + 8, device=dev, generator=g) / K ** 0.5).bfloat16()[:, :N]     # MN-major B, ld > N
+    gate = torch.randn(M, N + 8, device=dev, generator=g)
+    gate[::3] = torch.relu(gate[::3])                      # exact +0.0 entries
+    gate[1::7, ::5] = -0.0
+    gate[2::11, 1::4] = 1e-30                              # flushes to a tiny positive bf16 (still > 0)
+    gate = gate.bfloat16()[:, :N]
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    colsum = torch.zeros(N, device=dev)
+    sumsq = torch.zeros(2, device=dev, dtype=torch.float64)
+    gemm(a, b, b_mn=True, gate=gate, gate_mode="relu", alpha=0.25, out=out, colsum=colsum, sumsq=sumsq)
+    ref = 0.25 * (a.float() @ b.float()) * (gate.float() > 0)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(colsum, ref.sum(0), atol=5e-2, rtol=2e-3)
+    torch.testing.assert_close(sumsq[0], (ref.double() ** 2).sum(), atol=1e-3, rtol=1e-4)
+    assert float(sumsq[1]) == 0.0

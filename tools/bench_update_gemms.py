@@ -11,6 +11,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pulse_b200 import _lib  # noqa: E402
+if os.environ.get("PULSE_ALT_LIB"):      # A/B a differently built library on the same box
+    _lib.LIB_PATH = os.environ["PULSE_ALT_LIB"]
 from pulse_b200.dense import gemm  # noqa: E402
 from pulse_b200.nets import pad_k, pick_split  # noqa: E402
 
@@ -31,6 +34,7 @@ def timed(fn, iters=30, warm=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None, help="run just the cases whose name contains this (for ncu captures)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = {"bf16": 1514.7, "hbm": 6481.8}
@@ -43,6 +47,8 @@ def main():
 
     def case(name, M, N, K, kind, gate=False, colsum=False, f32=False, bf16_out=True, alpha=1.0):
         """kind: 'nt' (A [M,K], B [N,K]), 'dgrad' (A [M,K], B [K,N] MN-major), 'wgrad' (A [K,M], B [K,N], atomics into fp32)."""
+        if a.only and a.only not in name:
+            return
         Mp, Np, Kp = pad_k(M), pad_k(N), pad_k(K)
         kw = {}
         if kind == "nt":
