@@ -597,3 +597,149 @@ def disc_loss(disc_mlp, amp_agent, amp_replay, amp_demo, logit_weight, all_weigh
         loss = loss + weight_decay * wd
     return {"disc_loss": loss, "disc_grad_penalty": gp.detach(), "disc_logit_loss": logit_loss.detach(),
             "disc_agent_acc": (agent_logit < 0).float().mean(), "disc_demo_acc": (demo_logit > 0).float().mean()}
+
+
+# ------------------------------------------------------------------------------------------------
+# PULSE VAE distillation, Z-task decode (K20), reach task (K21), PD targets (K22)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class VaeNets:
+    """Weights of `AMPZBuilder.Network` (amp_network_z_builder.py:469-557) as (weights, biases) lists, reference layout.
+
+    enc: z_mlp = [Linear+SiLU]*len(task units) + Linear(units[-1], 5*E)  (:492-497);  enc_mu / enc_logvar: Linear(5E, E) (:510-512)
+    prior: z_prior = [Linear+SiLU]*len(task units) (:517);  prior_mu / prior_logvar: Linear(units[-1], E) (:518-519)
+    dec: actor_mlp = [Linear+SiLU]*len(mlp units) on [self_obs, z], then `mu` Linear (network_builder.py:246,261)
+    critic_z: critic_z_mlp (same shape as z_mlp but E outputs), critic: critic_mlp on [self_obs, critic_z] + `value`."""
+    enc: Tuple[list, list]
+    enc_mu: Tuple[torch.Tensor, torch.Tensor]
+    enc_logvar: Tuple[torch.Tensor, torch.Tensor]
+    prior: Tuple[list, list]
+    prior_mu: Tuple[torch.Tensor, torch.Tensor]
+    prior_logvar: Tuple[torch.Tensor, torch.Tensor]
+    dec: Tuple[list, list]
+    critic_z: Optional[Tuple[list, list]] = None
+    critic: Optional[Tuple[list, list]] = None
+    self_obs_size: int = SELF_OBS
+    clamp_lo: float = -5.0          # use_vae_clamped_prior (:86-87, :234-235)
+    clamp_hi: float = 2.0           # vae_var_clamp_max, env_im_vae.yaml:27
+
+    @staticmethod
+    def from_state_dict(sd: Dict[str, torch.Tensor], self_obs_size: int, prefix: str = "", clamp_hi: float = 2.0) -> "VaeNets":
+        def seq(name):
+            idx = sorted({int(k[len(prefix + name) + 1:].split(".")[0]) for k in sd if k.startswith(prefix + name + ".")})
+            return ([torch.as_tensor(sd[f"{prefix}{name}.{i}.weight"]) for i in idx], [torch.as_tensor(sd[f"{prefix}{name}.{i}.bias"]) for i in idx])
+
+        def lin(name):
+            return torch.as_tensor(sd[f"{prefix}{name}.weight"]), torch.as_tensor(sd[f"{prefix}{name}.bias"])
+
+        dec = seq("actor_mlp")
+        dec[0].append(lin("mu")[0]); dec[1].append(lin("mu")[1])
+        crit = None
+        if f"{prefix}critic_mlp.0.weight" in sd:
+            crit = seq("critic_mlp")
+            crit[0].append(lin("value")[0]); crit[1].append(lin("value")[1])
+        return VaeNets(enc=seq("z_mlp"), enc_mu=lin("z_mu"), enc_logvar=lin("z_logvar"), prior=seq("z_prior"), prior_mu=lin("z_prior_mu"),
+                       prior_logvar=lin("z_prior_logvar"), dec=dec, critic_z=seq("critic_z_mlp") if f"{prefix}critic_z_mlp.0.weight" in sd else None,
+                       critic=crit, self_obs_size=self_obs_size, clamp_hi=clamp_hi)
+
+
+def vae_encode(nets: VaeNets, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """z_mlp -> z_mu / clamped z_logvar (amp_network_z_builder.py:432, :82-87)."""
+    h = mlp_forward(obs, *nets.enc, activation="silu", last_linear=True)
+    mu = torch.nn.functional.linear(h, *nets.enc_mu)
+    lv = torch.clamp(torch.nn.functional.linear(h, *nets.enc_logvar), min=nets.clamp_lo, max=nets.clamp_hi)
+    return mu, lv
+
+
+def vae_prior(nets: VaeNets, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """compute_prior (amp_network_z_builder.py:226-241), use_vae_prior + use_vae_clamped_prior."""
+    h = mlp_forward(obs[:, :nets.self_obs_size], *nets.prior, activation="silu")
+    mu = torch.nn.functional.linear(h, *nets.prior_mu)
+    lv = torch.clamp(torch.nn.functional.linear(h, *nets.prior_logvar), min=nets.clamp_lo, max=nets.clamp_hi)
+    return mu, lv
+
+
+def vae_decode(nets: VaeNets, self_obs: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """actor_mlp([self_obs, z]) -> mu (amp_network_z_builder.py:445-462)."""
+    return mlp_forward(torch.cat([self_obs, z], dim=-1), *nets.dec, activation="silu", last_linear=True)
+
+
+def vae_eval_actor(nets: VaeNets, obs: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """eval_actor(return_extra=True) with the reparameterisation noise given (amp_network_z_builder.py:341-467, :89-90, :243-246)."""
+    mu, lv = vae_encode(nets, obs)
+    z = mu + torch.exp(0.5 * lv) * noise
+    return {"pred_action": vae_decode(nets, obs[:, :nets.self_obs_size], z), "vae_mu": mu, "vae_log_var": lv, "z": z}
+
+
+def vae_eval_critic(nets: VaeNets, obs: torch.Tensor) -> torch.Tensor:
+    """eval_critic, non-RNN branch for z_type 'vae' (amp_network_z_builder.py:325-339)."""
+    cz = mlp_forward(obs, *nets.critic_z, activation="silu", last_linear=True)
+    return mlp_forward(torch.cat([obs[:, :nets.self_obs_size], cz], dim=-1), *nets.critic, activation="silu", last_linear=True)
+
+
+def vae_kin_loss(nets: VaeNets, obs: torch.Tensor, noise: torch.Tensor, gt_action: torch.Tensor, progress: torch.Tensor, horizon: int,
+                 kld_coef: float = 0.01, ar1_coef: float = 0.005, use_ar1: bool = True, use_regu: bool = False, phi: float = 0.99) -> Dict[str, torch.Tensor]:
+    """AMPAgent._optimize_kin, z_type 'vae' + use_vae_prior (amp_agent.py:771-849).  rows are env-major [B/horizon, horizon]."""
+    out = vae_eval_actor(nets, obs, noise)
+    action_loss = torch.norm(out["pred_action"] - gt_action, dim=-1).mean()                       # :782
+    pm, plv = vae_prior(nets, obs)
+    kld = kl_multi(out["vae_mu"], out["vae_log_var"], pm, plv).mean()                             # :786-787
+    ar1 = torch.zeros(())
+    if use_ar1:                                                                                   # :792-808
+        B = obs.shape[0]
+        tz = out["vae_mu"].view(B // horizon, horizon, -1)
+        err = tz[:, 1:] - tz[:, :-1] * phi
+        idx = progress.view(B // horizon, horizon, -1)
+        not_consec = ((idx[:, 1:] - idx[:, :-1]) != 1).view(-1)
+        starters = ((idx <= 2)[:, 1:] + (idx <= 2)[:, :-1]).view(-1)
+        keep = (~(not_consec | starters)).to(err.dtype).view(-1, 1)
+        ar1 = torch.norm(err.reshape(-1, err.shape[-1]) * keep, dim=-1).mean()
+    regu = torch.zeros(())
+    if use_regu:                                                                                  # :810-814
+        regu = ((pm ** 2).mean() + (out["vae_mu"] ** 2).mean()) * 0.001 + ((plv ** 2).mean() + (out["vae_log_var"] ** 2).mean()) * 0.001
+    loss = action_loss + kld * kld_coef + ar1 * ar1_coef + regu * 0.005                           # :816
+    return {"kin_loss": loss, "kin_action_loss": action_loss, "kin_KLD": kld, "kin_ar1": ar1, "kin_prior_regu": regu, **out,
+            "prior_mu": pm, "prior_log_var": plv}
+
+
+def kld_anneal(epoch: int, kld_min: float = 0.001, start: int = 2500, end: int = 5000, base: float = 0.01) -> float:
+    """amp_agent.py:827-833: the coefficient used from `epoch` on (unchanged before `start`)."""
+    return (base - kld_min) * max((end - epoch) / (end - start), 0) + kld_min
+
+
+def teacher_action(raw_obs, mean, var, pnn_cols, composer, self_obs_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """HumanoidImDistill.step (humanoid_im_distill.py:167-198): normalise with the TEACHER's statistics, clamp +-5, three frozen
+    ReLU columns (PNN without lateral links, pnn.py:127-131) and the composer MLP as rebuilt by load_mcp_mlp (activation after
+    EVERY Linear including the last, network_loader.py:37-39); action = sum_k w_k a_k.
+    pnn_cols: list of (weights, biases); composer: (weights, biases)."""
+    so = (raw_obs[:, :self_obs_size] - mean.float()[:self_obs_size]) / torch.sqrt(var.float()[:self_obs_size] + 1e-05)
+    to = (raw_obs[:, self_obs_size:] - mean.float()[self_obs_size:]) / torch.sqrt(var.float()[self_obs_size:] + 1e-05)
+    x = torch.clamp(torch.cat([so, to], dim=-1), min=-5.0, max=5.0)
+    acts = torch.stack([mlp_forward(x, w, b, activation="relu", last_linear=True) for w, b in pnn_cols], dim=1)
+    wts = mlp_forward(x, *composer, activation="silu", last_linear=False)
+    return torch.sum(wts[:, :, None] * acts, dim=1), wts
+
+
+def z_decode_actions(nets: VaeNets, raw_obs: torch.Tensor, mean, var, action_z: torch.Tensor) -> torch.Tensor:
+    """HumanoidZ.compute_z_actions, 'vae' + use_vae_prior (humanoid_z.py:81-155): the prior sees the UNCLAMPED normalised self
+    observation, the decoder the clamped one; z = prior_mu + action_z (project_to_norm(.., 'none') is the identity)."""
+    S = nets.self_obs_size
+    so = (raw_obs[:, :S] - mean.float()[:S]) / torch.sqrt(var.float()[:S] + 1e-05)
+    pm = torch.nn.functional.linear(mlp_forward(so, *nets.prior, activation="silu"), *nets.prior_mu)
+    return vae_decode(nets, torch.clamp(so, min=-5.0, max=5.0), pm + action_z)
+
+
+def reach_obs(root_states: torch.Tensor, tar_pos: torch.Tensor) -> torch.Tensor:
+    """compute_location_observations (humanoid_reach.py:224-236)."""
+    return quat_rotate(heading_quat(root_states[:, 3:7], inverse=True), tar_pos - root_states[:, 0:3])
+
+
+def reach_reward(reach_body_pos: torch.Tensor, tar_pos: torch.Tensor) -> torch.Tensor:
+    """compute_reach_reward (humanoid_reach.py:238-250)."""
+    d = tar_pos - reach_body_pos
+    return torch.exp(-4.0 * torch.sum(d * d, dim=-1))
+
+
+def pd_targets(action: torch.Tensor, offset: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """Humanoid._action_to_pd_targets (humanoid.py:1392-1394)."""
+    return offset + scale * action

@@ -83,3 +83,27 @@ def synthetic_step_inputs(tb, n_envs, seed=0, dt=None):
         "dof_force": 30 * torch.randn(n_envs, 69, generator=g),
         "reset_buf_in": torch.zeros(n_envs, dtype=torch.long),
     }
+
+
+def vae_golden():
+    """tests/golden/vae.npz (reference-generated, make_golden_vae.py) + the oracle's view of its network weights."""
+    from oracle import pulse_oracle as po
+    g = load_npz("vae.npz")
+    S, Tk, A, E, T, NE = [int(x) for x in g["dims"]]
+    sd = {k[4:]: v for k, v in g.items() if k.startswith("net.")}
+    nets = po.VaeNets.from_state_dict(sd, S)
+    pnn_cols = [([g[f"pnn.actors.{c}.{i}.weight"] for i in (0, 2, 4)], [g[f"pnn.actors.{c}.{i}.bias"] for i in (0, 2, 4)]) for c in range(3)]
+    composer = ([g[f"composer.{i}.weight"] for i in (0, 2, 4)], [g[f"composer.{i}.bias"] for i in (0, 2, 4)])
+    return g, sd, nets, dict(S=S, Tk=Tk, A=A, E=E, T=T, NE=NE), pnn_cols, composer
+
+
+def vae_param_list(nets):
+    """Trainable tensors of the kin loss in reference naming order -> {reference parameter name: tensor}."""
+    out = {}
+    for name, (ws, bs) in (("z_mlp", nets.enc), ("z_prior", nets.prior), ("actor_mlp", (nets.dec[0][:-1], nets.dec[1][:-1]))):
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            out[f"{name}.{2 * i}.weight"], out[f"{name}.{2 * i}.bias"] = w, b
+    for name, (w, b) in (("z_mu", nets.enc_mu), ("z_logvar", nets.enc_logvar), ("z_prior_mu", nets.prior_mu),
+                         ("z_prior_logvar", nets.prior_logvar), ("mu", (nets.dec[0][-1], nets.dec[1][-1]))):
+        out[f"{name}.weight"], out[f"{name}.bias"] = w, b
+    return out

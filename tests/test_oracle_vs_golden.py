@@ -168,3 +168,35 @@ def test_oracle_against_live_reference():
     q0, q1 = unit(torch.randn(4000, 4, generator=g)), unit(torch.randn(4000, 4, generator=g))
     t = torch.rand(4000, 1, generator=g)
     close(po.slerp(q0, q1, t), ref.torch_utils.slerp(q0, q1, t))
+
+
+def test_vae_distillation_teacher_zdecode_reach_pd():
+    """the oracle's restatement of AMPZBuilder.Network + _optimize_kin, the PNN teacher,
+    HumanoidZ.compute_z_actions, the reach task functions and the PD target map against reference-generated vectors."""
+    from tests.helpers import vae_golden, vae_param_list
+    g, _, nets, d, pnn_cols, composer = vae_golden()
+    params = vae_param_list(nets)
+    for tag, regu in (("", False), ("regu_", True)):
+        for p in params.values():
+            p.requires_grad_(True)
+            p.grad = None
+        r = po.vae_kin_loss(nets, g["obs"], g[tag + "noise"], g["gt_action"], g["progress"], d["T"], use_regu=regu)
+        r["kin_loss"].backward()
+        for k in ("kin_loss", "kin_action_loss", "kin_KLD", "kin_ar1"):
+            close(r[k].detach(), torch.as_tensor(g[tag + "info." + k]))
+        if regu:
+            close(r["kin_prior_regu"].detach(), torch.as_tensor(g["regu_info.kin_prior_regu"]))
+        for name, p in params.items():
+            close(p.grad, g[tag + "grad." + name], atol=1e-6, rtol=1e-5)
+    with torch.no_grad():
+        for k in ("pred_action", "vae_mu", "vae_log_var", "prior_mu", "prior_log_var"):
+            close(r[k], g[k])
+        assert float((g["vae_log_var"] >= 2).float().mean()) > 0.05      # the clamp is exercised
+        close(po.vae_eval_critic(nets, g["obs"]), g["value"])
+        ta, w = po.teacher_action(g["teacher_raw_obs"], g["teacher_mean"], g["teacher_var"], pnn_cols, composer, d["S"])
+        close(ta, g["teacher_action"]); close(w, g["teacher_weights"])
+        close(po.z_decode_actions(nets, g["teacher_raw_obs"], g["teacher_mean"], g["teacher_var"], g["action_z"]), g["z_actions"])
+        close(po.reach_obs(g["reach_root_states"], g["reach_tar_pos"]), g["reach_obs"])
+        close(po.reach_reward(g["reach_body_pos"], g["reach_tar_pos"]), g["reach_reward"])
+        close(po.pd_targets(g["gt_action"], g["pd_offset"], g["pd_scale"]), g["pd_target"])
+    assert abs(po.kld_anneal(3750) - 0.0055) < 1e-9 and po.kld_anneal(6000) == 0.001
