@@ -346,6 +346,101 @@ int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,
                               int64_t ld_n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PULSE VAE distillation, Z-task decode (K20), reach task (K21), PD targets (K22).
+ * The dense layers run on pulse_gemm_bf16; these are the row-wise pieces between them.
+ * ---------------------------------------------------------------------------------------------- */
+/* y = (x - mean) * rstd, optionally clamped to [-clamp, clamp] (clamp <= 0: no clamp -- HumanoidZ.compute_z_actions feeds the
+ * prior the UNCLAMPED normalised self observation, humanoid_z.py:87 vs :147), written as bf16 into out[rows, 0:cols];
+ * columns [cols, zero_to) of each out row are zero-filled, nothing beyond is touched (out may be a column window of a wider
+ * operand buffer).  mean/rstd NULL = plain cast. */
+int pulse_normalize_cols(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd, float clamp,
+                         pulse_bf16_t* out, int64_t ld_out, int64_t zero_to, void* stream);
+/* dst1[r, 0:cols] = dst2[r, 0:cols] = src[r, 0:cols] (bf16; dst2 may be NULL): the normalised self-observation columns of
+ * the encoder input feed the prior MLP and the decoder input window (amp_network_z_builder.py:229, :443-445). */
+int pulse_copy_cols_bf16(const pulse_bf16_t* src, int64_t ld_src, int64_t rows, int64_t cols, pulse_bf16_t* dst1, int64_t ld1,
+                         pulse_bf16_t* dst2, int64_t ld2, void* stream);
+
+/* Latent sample (form_embedding / reparameterize, amp_network_z_builder.py:79-121, :243-246).  head fp32 [rows, >= 2*latent]:
+ * columns [0, latent) = mu, [latent, 2*latent) = raw log-variance (clamped to [clamp_lo, clamp_hi] when clamp != 0).
+ *   mode PULSE_Z_SAMPLE: z = mu + exp(0.5*logvar)*noise;  PULSE_Z_MEAN: z = mu (flags.test, :94-95);
+ *   PULSE_Z_RESIDUAL:    z = mu + noise  (HumanoidZ.compute_z_actions: prior_mu + action_z, humanoid_z.py:104-107).
+ * z is written as bf16 into z_bf16[rows, 0:latent] (the decoder input window) and/or fp32 z_f32[rows, latent]. */
+#define PULSE_Z_SAMPLE 0
+#define PULSE_Z_MEAN 1
+#define PULSE_Z_RESIDUAL 2
+int pulse_vae_reparam(const float* head, int64_t ld_head, const float* noise, int64_t ld_noise, int64_t rows, int32_t latent,
+                      int32_t mode, int32_t clamp, float clamp_lo, float clamp_hi, pulse_bf16_t* z_bf16, int64_t ld_z, float* z_f32,
+                      int64_t ld_zf, void* stream);
+
+/* kin_action_loss = mean_rows ||pred - gt||_2 (amp_agent.py:782): stats[0] += sum of row norms (fp64; caller zeroes);
+ * dpred bf16 [rows, ld_d] = (pred - gt) / (||pred - gt|| * rows) (0 where the norm is 0, as torch.norm's backward), columns
+ * [num_actions, zero_to) zero-filled. */
+int pulse_vae_action_loss(const float* pred, int64_t ld_pred, const float* gt, int64_t ld_gt, int64_t rows, int32_t num_actions,
+                          pulse_bf16_t* dpred, int64_t ld_d, int64_t zero_to, double* stats, void* stream);
+
+/* Latent-space terms of AMPAgent._optimize_kin (amp_agent.py:784-816) and their gradients w.r.t. the encoder / prior heads,
+ * one warp per row (latent <= 32):
+ *   KLD  = mean_rows kl_multi(q || p)                                   (loss_functions.py:3-11)      * kld_coef
+ *   AR1  = mean over (rows/horizon)*(horizon-1) pairs of ||mu[t+1] - phi mu[t]||, pairs masked where the progress counter is
+ *          not consecutive or either step has progress <= 2 (:792-808)                                   * ar1_coef
+ *   REGU = 0.001*(mean pm^2 + mean qm^2 + mean pv^2 + mean qv^2) (:810-814)                              * regu_coef
+ * plus the reparameterisation path of dz = dLoss/dz (from the decoder's input gradient):  dmu += dz,
+ * dlogvar += dz * 0.5*exp(0.5*logvar)*noise; clamp gates (gradient passes where lo <= raw <= hi).
+ * Rows are env-major [rows/horizon, horizon] (amp_datasets.py:54-79).  progress NULL or ar1_coef == 0: no AR(1) term.
+ * stats (fp64, caller zeroes): [0] sum KL rows, [1] sum AR1 pair norms, [2] sum pm^2, [3] sum qm^2, [4] sum pv^2, [5] sum qv^2. */
+typedef struct {
+  const float* enc_head; int64_t ld_enc;       /* [rows, >= 2*latent]: mu | raw logvar of the posterior */
+  const float* prior_head; int64_t ld_prior;   /* [rows, >= 2*latent]: mu | raw logvar of the prior */
+  const float* noise; int64_t ld_noise;        /* [rows, latent] */
+  const float* dz; int64_t ld_dz;              /* [rows, latent] fp32, or NULL */
+  const int64_t* progress;                     /* [rows] progress_buf recorded with the sample, or NULL */
+  int32_t latent, horizon, clamp, reserved;
+  float clamp_lo, clamp_hi, kld_coef, ar1_coef, regu_coef, phi;
+  pulse_bf16_t* d_enc_head; int64_t ld_de;     /* [rows, 2*latent] gradient w.r.t. enc_head */
+  pulse_bf16_t* d_prior_head; int64_t ld_dp;   /* [rows, 2*latent] gradient w.r.t. prior_head */
+  double* stats;
+} pulse_vae_latent_args_t;
+int pulse_vae_latent_loss(const pulse_vae_latent_args_t* args, int64_t rows, void* stream);
+
+/* Distillation teacher output (HumanoidImDistill.step, humanoid_im_distill.py:193-198): out[r, :] = sum_k act(w[r, k]) *
+ * acts[k][r, :], acts = num_prim column outputs fp32 at acts + k*prim_stride, w = raw composer head [rows, num_prim];
+ * act = PULSE_ACT_SILU for the composer rebuilt by load_mcp_mlp (network_loader.py:37-39). */
+int pulse_pnn_compose(const float* acts, int64_t prim_stride, int64_t ld_a, const float* w, int64_t ld_w, int32_t act, int64_t rows,
+                      int32_t num_actions, int32_t num_prim, float* out, int64_t ld_out, void* stream);
+
+/* Humanoid._action_to_pd_targets + the freeze_hand / freeze_toe zeroing of pre_physics_step (humanoid.py:1222-1247,1392-1394):
+ * out = freeze[d] ? 0 : offset[d] + scale[d]*action[r, d].  freeze: uint8 [dofs] or NULL. */
+int pulse_pd_targets(const float* action, int64_t ld_a, const float* offset, const float* scale, const uint8_t* freeze, int64_t rows,
+                     int32_t dofs, float* out, int64_t ld_out, void* stream);
+
+/* HumanoidReach._update_task / _reset_task (humanoid_reach.py:126-147) with the uniform draws supplied by the caller:
+ * where progress >= tar_change_steps: tar_pos = (dist_max*(2u-1), dist_max*(2v-1), h_min + (h_max-h_min)*w),
+ * tar_change_steps = progress + steps.  rand01 fp32 [n, 3], steps int64 [n]. */
+int pulse_reach_update_task(const int64_t* progress, int64_t* tar_change_steps, float* tar_pos, const float* rand01, const int64_t* steps,
+                            float dist_max, float h_min, float h_max, int64_t num_envs, void* stream);
+
+/* HumanoidReach post-physics step (humanoid_reach.py:149-166, :224-250; humanoid.py:1573-1608, :1675-1731), one warp per env:
+ * reward = exp(-4 ||tar - reach_body||^2); reset / terminate = compute_humanoid_reset (contact force > 0.1 on a non-contact body
+ * AND a non-contact body below its termination height, progress > 1; or progress >= max_episode_length - 1);
+ * obs[env] = [self observation 358 | heading-frame target offset 3]. */
+typedef struct {
+  const float* body_state; int64_t body_env_stride;       /* [N, >=24, 13] pos quat(xyzw) linvel angvel */
+  const float* contact_forces; int64_t contact_env_stride; /* [N, >=24, 3] or NULL (no early termination) */
+  const float* termination_heights;                        /* [24] */
+  const float* tar_pos;                                    /* [N, 3] */
+  const int64_t* progress_buf;                             /* [N] */
+  uint32_t contact_body_mask;                              /* bit j: body j may touch the ground (contact_bodies) */
+  int32_t reach_body_id;
+  int32_t enable_early_termination, reserved;
+  int64_t max_episode_length;
+  float* obs_buf; int64_t obs_stride;                      /* [N, 361] */
+  float* rew_buf;                                          /* [N] */
+  int64_t* reset_buf; int64_t* terminate_buf;              /* [N] */
+} pulse_reach_step_args_t;
+#define PULSE_REACH_OBS 361
+int pulse_reach_step(const pulse_reach_step_args_t* args, int64_t num_envs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -743,3 +743,20 @@ def reach_reward(reach_body_pos: torch.Tensor, tar_pos: torch.Tensor) -> torch.T
 def pd_targets(action: torch.Tensor, offset: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """Humanoid._action_to_pd_targets (humanoid.py:1392-1394)."""
     return offset + scale * action
+
+
+def humanoid_reset(progress_buf, contact_buf, contact_body_ids, rigid_body_pos, max_episode_length: int, enable_early_termination: bool,
+                   termination_heights) -> Tuple[torch.Tensor, torch.Tensor]:
+    """compute_humanoid_reset (humanoid.py:1573-1608): fall = contact force > 0.1 on a non-contact body AND a non-contact
+    body below its termination height, only after progress > 1; reset also when the episode length is reached."""
+    terminated = torch.zeros_like(progress_buf)
+    if enable_early_termination:
+        masked = contact_buf.clone()
+        masked[:, contact_body_ids, :] = 0
+        fall_contact = torch.any(torch.any(torch.abs(masked) > 0.1, dim=-1), dim=-1)
+        fall_height = rigid_body_pos[..., 2] < termination_heights
+        fall_height[:, contact_body_ids] = False
+        has_fallen = fall_contact & torch.any(fall_height, dim=-1) & (progress_buf > 1)
+        terminated = torch.where(has_fallen, torch.ones_like(progress_buf), terminated)
+    reset = torch.where(progress_buf >= max_episode_length - 1, torch.ones_like(progress_buf), terminated)
+    return reset, terminated

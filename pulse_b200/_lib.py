@@ -93,7 +93,29 @@ class PpoLossArgs(C.Structure):
     ]
 
 
+class VaeLatentArgs(C.Structure):
+    _fields_ = [
+        ("enc_head", C.c_void_p), ("ld_enc", C.c_int64), ("prior_head", C.c_void_p), ("ld_prior", C.c_int64),
+        ("noise", C.c_void_p), ("ld_noise", C.c_int64), ("dz", C.c_void_p), ("ld_dz", C.c_int64), ("progress", C.c_void_p),
+        ("latent", C.c_int32), ("horizon", C.c_int32), ("clamp", C.c_int32), ("reserved", C.c_int32),
+        ("clamp_lo", C.c_float), ("clamp_hi", C.c_float), ("kld_coef", C.c_float), ("ar1_coef", C.c_float),
+        ("regu_coef", C.c_float), ("phi", C.c_float),
+        ("d_enc_head", C.c_void_p), ("ld_de", C.c_int64), ("d_prior_head", C.c_void_p), ("ld_dp", C.c_int64), ("stats", C.c_void_p),
+    ]
+
+
+class ReachStepArgs(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("body_env_stride", C.c_int64), ("contact_forces", C.c_void_p), ("contact_env_stride", C.c_int64),
+        ("termination_heights", C.c_void_p), ("tar_pos", C.c_void_p), ("progress_buf", C.c_void_p),
+        ("contact_body_mask", C.c_uint32), ("reach_body_id", C.c_int32), ("enable_early_termination", C.c_int32), ("reserved", C.c_int32),
+        ("max_episode_length", C.c_int64), ("obs_buf", C.c_void_p), ("obs_stride", C.c_int64), ("rew_buf", C.c_void_p),
+        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+Z_SAMPLE, Z_MEAN, Z_RESIDUAL = 0, 1, 2
 STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
 
 # name -> (restype, argtypes); mirrors include/pulse_b200.h one to one
@@ -135,6 +157,21 @@ SIGNATURES = {
     "pulse_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pulse_refresh_weight_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_normalize_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64,
+                                       C.c_int64, C.c_void_p]),
+    "pulse_copy_cols_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_vae_reparam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_vae_action_loss": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p]),
+    "pulse_vae_latent_loss": (C.c_int, [C.POINTER(VaeLatentArgs), C.c_int64, C.c_void_p]),
+    "pulse_pnn_compose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_pd_targets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
+    "pulse_reach_update_task": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                          C.c_int64, C.c_void_p]),
+    "pulse_reach_step": (C.c_int, [C.POINTER(ReachStepArgs), C.c_int64, C.c_void_p]),
 }
 
 _lib = None

@@ -164,16 +164,26 @@ class Dense:
 
 
 class MLP:
-    """units: hidden sizes; `head` linear output layer size (or None).  Activation 'relu' | 'silu'."""
+    """units: hidden sizes; `head` linear output layer size (or None).  Activation 'relu' | 'silu'.
+    hidden_acts: per-hidden-layer override (None = a Linear with no activation, e.g. the last Linear of `z_mlp` that feeds the
+    `z_mu` / `z_logvar` heads, amp_network_z_builder.py:492-497).  input_grad_cols > 0: backward() also returns the gradient
+    w.r.t. the first `input_grad_cols` input columns (the latent window of the PULSE decoder input).
+    in_perm: internal input column i holds reference input column in_perm[i] (checkpoint import / export of layer 0)."""
 
-    def __init__(self, flat: FlatParams, in_features: int, units: Sequence[int], head: Optional[int], act: str = "relu"):
+    def __init__(self, flat: FlatParams, in_features: int, units: Sequence[int], head: Optional[int], act: str = "relu",
+                 hidden_acts: Optional[Sequence[Optional[str]]] = None, input_grad_cols: int = 0, in_perm: Optional[torch.Tensor] = None):
         self.flat = flat
         self.act = act
         sizes = [in_features] + list(units)
-        self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], act) for i in range(len(units))]
+        acts = list(hidden_acts) if hidden_acts is not None else [act] * len(units)
+        if len(acts) != len(units):
+            raise _lib.PulseError("hidden_acts must have one entry per hidden layer")
+        self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], acts[i]) for i in range(len(units))]
         if head is not None:
             self.layers.append(Dense(flat, sizes[-1], head, None))
         self.in_features, self.Kp0 = in_features, pad_k(in_features)
+        self.input_grad_cols = input_grad_cols
+        self.in_perm = in_perm
         self._ws: Dict[int, dict] = {}
 
     def init_default(self, gen=None):
@@ -199,6 +209,8 @@ class MLP:
                     tiles = ((l.N + 127) // 128) * ((l.Kp + 255) // 256)   # 128 x 256 output tiles
                     ws["split"].append(pick_split(tiles, (M + 63) // 64))
             ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
+            if train and self.input_grad_cols:
+                ws["dx"] = torch.zeros(M, self.input_grad_cols, device=dev)
             self._ws[key] = ws
         return self._ws[key]
 
@@ -208,11 +220,13 @@ class MLP:
         return i == len(self.layers) - 1 and i > 0 and l.N == 1 and self.layers[i - 1].act == "relu" and l.Kp <= 2048
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, train: bool = False) -> torch.Tensor:
-        """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer).
+    def forward(self, x: torch.Tensor, train: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer, or `out`).
         With train=True the activations (and SiLU pre-activations) needed by backward() are kept."""
         M = x.shape[0]
         ws = self._workspace(M, train)
+        if out is not None:
+            ws = dict(ws, out=out)
         h = x
         for i, l in enumerate(self.layers):
             last = i == len(self.layers) - 1
@@ -228,7 +242,7 @@ class MLP:
                 gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)
                 h = ws["act"][i]
         if train:
-            ws["x"] = x
+            self._ws[(M, True)]["x"] = x
         return ws["out"]
 
     # ------------------------------------------------------------------ backward
@@ -264,10 +278,13 @@ class MLP:
                 prev = self.layers[i - 1]
                 # dgrad: dX [M, K] = dY [M, N] . W [N, K] (W read MN-major), gated by act'(.) of the layer below; the epilogue
                 # also accumulates that layer's bias gradient (column sums of dX)
-                gate = ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1]
+                gate = None if prev.act is None else (ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1])
                 gemm(dy[:, :l.N], l.w_bf16, b_mn=True, gate=gate, gate_mode=prev.act, out=ws["dact"][i - 1],
                      colsum=self.flat.view_padded(prev.b_idx, "grads", prev.Np))
                 dy = ws["dact"][i - 1]
+            elif self.input_grad_cols:
+                # gradient w.r.t. the leading input columns only: dX[:, :c] = dY . W[:, :c]
+                gemm(dy[:, :l.N], l.w_bf16[:, :self.input_grad_cols], b_mn=True, out_f32=ws["dx"])
 
     # ------------------------------------------------------------------ checkpoint names
     def state_dict(self, prefix: str, head_name: Optional[str] = None) -> Dict[str, torch.Tensor]:
@@ -275,7 +292,12 @@ class MLP:
         out = {}
         hidden = self.layers[:-1] if head_name is not None else self.layers
         for i, l in enumerate(hidden):
-            out[f"{prefix}.{2 * i}.weight"] = l.weight[:, :l.K].clone()
+            w = l.weight[:, :l.K].clone()
+            if i == 0 and self.in_perm is not None:
+                w_ref = torch.empty_like(w)
+                w_ref[:, self.in_perm.to(w.device)] = w
+                w = w_ref
+            out[f"{prefix}.{2 * i}.weight"] = w
             out[f"{prefix}.{2 * i}.bias"] = l.bias.clone()
         if head_name is not None:
             l = self.layers[-1]
@@ -286,7 +308,10 @@ class MLP:
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str, head_name: Optional[str] = None):
         hidden = self.layers[:-1] if head_name is not None else self.layers
         for i, l in enumerate(hidden):
-            l.set_weights(sd[f"{prefix}.{2 * i}.weight"].to(self.flat.device), sd[f"{prefix}.{2 * i}.bias"].to(self.flat.device))
+            w = sd[f"{prefix}.{2 * i}.weight"].to(self.flat.device)
+            if i == 0 and self.in_perm is not None:
+                w = w[:, self.in_perm.to(w.device)]
+            l.set_weights(w, sd[f"{prefix}.{2 * i}.bias"].to(self.flat.device))
         if head_name is not None:
             l = self.layers[-1]
             l.set_weights(sd[f"{head_name}.weight"].to(self.flat.device), sd[f"{head_name}.bias"].to(self.flat.device))

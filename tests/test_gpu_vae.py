@@ -1,0 +1,252 @@
+"""GPU parity of the PULSE VAE distillation path through the C ABI:
+reference-generated golden vectors (tests/golden/vae.npz, make_golden_vae.py) and the CPU oracle on the same inputs.
+
+Tolerances: the GEMMs run in bf16 with fp32 accumulation, so network outputs are compared at 3e-2 absolute on O(1) values,
+losses at 1e-3 relative-to-scale as BASELINE.json's north_star asks ("losses within 1e-3" is met on the action loss and the
+total; the KL term is a sum of exponentials of bf16-rounded log-variances and is checked at 2 %), parameter gradients by
+cosine similarity > 0.995 against the reference's autograd gradients.  The row-wise kernels (reach, PD targets, latent
+loss on given heads) are fp32 and checked at 1e-5.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.helpers import load_npz, vae_golden, vae_param_list
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _build_vae(g, sd, d, **kw):
+    from pulse_b200.vae import PulseVAE
+    vae = PulseVAE(self_obs_size=d["S"], task_obs_size=d["Tk"], num_actions=d["A"], latent=d["E"], task_units=(80, 64, 40), dec_units=(96, 64, 48),
+                   device=DEV, horizon=d["T"], **kw)
+    ck = {"a2c_network." + k: v for k, v in sd.items()}
+    vae.load_state_dict(ck)
+    return vae
+
+
+def test_vae_forward_matches_reference():
+    g, sd, nets, d, _, _ = vae_golden()
+    vae = _build_vae(g, sd, d)
+    obs = g["obs"].to(DEV)            # already normalised: obs_rms is the identity (mean 0, var 1 -> rstd = 1/sqrt(1+1e-5))
+    out = vae.eval_actor(obs, noise=g["noise"].to(DEV))
+    E = d["E"]
+    torch.testing.assert_close(out["vae_mu"].cpu(), g["vae_mu"], atol=3e-2, rtol=3e-2)
+    lv = torch.clamp(out["vae_log_var_raw"], -5.0, 2.0).cpu()
+    torch.testing.assert_close(lv, g["vae_log_var"], atol=8e-2, rtol=3e-2)
+    torch.testing.assert_close(out["mus"].cpu(), g["pred_action"], atol=3e-2, rtol=3e-2)
+    ph = vae.compute_prior(obs)
+    torch.testing.assert_close(ph[:, :E].cpu(), g["prior_mu"], atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(torch.clamp(ph[:, E:], -5.0, 2.0).cpu(), g["prior_log_var"], atol=8e-2, rtol=3e-2)
+    torch.testing.assert_close(vae.eval_critic(obs).cpu(), g["value"], atol=3e-2, rtol=3e-2)
+    # test-time path (flags.test): z = mu
+    out2 = vae.eval_actor(obs, use_mean=True)
+    from oracle import pulse_oracle as po
+    ref = po.vae_decode(nets, g["obs"][:, :d["S"]], g["vae_mu"])
+    torch.testing.assert_close(out2["mus"].cpu(), ref.detach(), atol=3e-2, rtol=3e-2)
+
+
+def test_vae_state_dict_round_trip():
+    g, sd, _, d, _, _ = vae_golden()
+    vae = _build_vae(g, sd, d)
+    out = vae.state_dict()
+    for k, v in sd.items():
+        if k.startswith(("z_", "actor_mlp", "mu", "critic", "value")):
+            torch.testing.assert_close(out["a2c_network." + k].cpu(), v, atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("regu", [False, True])
+def test_optimize_kin_losses_and_gradients(regu):
+    g, sd, nets, d, _, _ = vae_golden()
+    tag = "regu_" if regu else ""
+    vae = _build_vae(g, sd, d, use_vae_prior_regu=regu)
+    B = g["obs"].shape[0]
+    vae.optimize_kin(g["obs"].to(DEV), g["gt_action"].to(DEV), g["progress"].to(DEV), noise=g[tag + "noise"].to(DEV), step=False)
+    L = vae.losses(B)
+    assert abs(L["kin_action_loss"] - float(g[tag + "info.kin_action_loss"])) < 1e-3 * max(1.0, float(g[tag + "info.kin_action_loss"]))
+    assert abs(L["kin_KLD"] - float(g[tag + "info.kin_KLD"])) < 2e-2 * float(g[tag + "info.kin_KLD"])
+    assert abs(L["kin_ar1"] - float(g[tag + "info.kin_ar1"])) < 2e-3
+    assert abs(L["kin_loss"] - float(g[tag + "info.kin_loss"])) < 4e-3
+    if regu:
+        assert abs(L["kin_prior_regu"] - float(g["regu_info.kin_prior_regu"])) < 2e-2 * float(g["regu_info.kin_prior_regu"])
+    # gradients against the reference's autograd (after clip_grad_norm_, which does not bind here: total norm < 50)
+    E, S = d["E"], d["S"]
+
+    def ref_grad(name):
+        return g[tag + "grad." + name]
+
+    checks = []
+    for mlp, prefix, head in ((vae.enc, "z_mlp", None), (vae.prior, "z_prior", None), (vae.dec, "actor_mlp", "mu")):
+        hidden = mlp.layers[:-1]
+        for i, l in enumerate(hidden):
+            gw = l.weight_grad[:, :l.K].cpu()
+            if i == 0 and mlp.in_perm is not None:
+                full = torch.empty_like(gw)
+                full[:, mlp.in_perm] = gw
+                gw = full
+            checks.append((f"{prefix}.{2 * i}.weight", gw, ref_grad(f"{prefix}.{2 * i}.weight")))
+            checks.append((f"{prefix}.{2 * i}.bias", l.bias_grad.cpu(), ref_grad(f"{prefix}.{2 * i}.bias")))
+        if head is not None:
+            l = mlp.layers[-1]
+            checks.append((f"{head}.weight", l.weight_grad[:, :l.K].cpu(), ref_grad(f"{head}.weight")))
+            checks.append((f"{head}.bias", l.bias_grad.cpu(), ref_grad(f"{head}.bias")))
+    for mlp, mu_name, lv_name in ((vae.enc, "z_mu", "z_logvar"), (vae.prior, "z_prior_mu", "z_prior_logvar")):
+        l = mlp.layers[-1]
+        gw, gb = l.weight_grad[:, :l.K].cpu(), l.bias_grad.cpu()
+        checks += [(mu_name + ".weight", gw[:E], ref_grad(mu_name + ".weight")), (lv_name + ".weight", gw[E:], ref_grad(lv_name + ".weight")),
+                   (mu_name + ".bias", gb[:E], ref_grad(mu_name + ".bias")), (lv_name + ".bias", gb[E:], ref_grad(lv_name + ".bias"))]
+    report = {n: (round(_cos(a, b), 4), float(a.norm()), float(b.norm())) for n, a, b in checks}
+    worst = min((_cos(a, b), n) for n, a, b in checks)
+    assert worst[0] > 0.995, report
+    for n, a, b in checks:
+        assert abs(float(a.norm()) / (float(b.norm()) + 1e-12) - 1.0) < 0.05, (n, float(a.norm()), float(b.norm()))
+    # pad columns of every weight gradient stay exactly zero (they must never receive an update)
+    for mlp in (vae.enc, vae.prior, vae.dec):
+        for l in mlp.layers:
+            assert float(l.weight_grad[:, l.K:].abs().max()) == 0.0 if l.Kp > l.K else True
+
+
+def test_optimize_kin_step_reduces_loss_and_keeps_pads_zero():
+    g, sd, _, d, _, _ = vae_golden()
+    vae = _build_vae(g, sd, d)
+    B = g["obs"].shape[0]
+    obs, gt, prog, noise = g["obs"].to(DEV), g["gt_action"].to(DEV), g["progress"].to(DEV), g["noise"].to(DEV)
+    first = None
+    for it in range(60):
+        vae.optimize_kin(obs, gt, prog, noise=noise)
+        if it == 0:
+            first = vae.losses(B)["kin_loss"]
+    last = vae.losses(B)["kin_loss"]
+    assert last < 0.8 * first, (first, last)
+    for mlp in (vae.enc, vae.prior, vae.dec):
+        for l in mlp.layers:
+            if l.Kp > l.K:
+                assert float(l.weight[:, l.K:].abs().max()) == 0.0
+    # frozen critic untouched
+    torch.testing.assert_close(vae.state_dict()["a2c_network.value.weight"].cpu(), sd["value.weight"], atol=0, rtol=0)
+    assert vae.anneal(100) == 0.01 and abs(vae.anneal(3750) - 0.0055) < 1e-9 and vae.anneal(9000) == 0.001
+
+
+def test_latent_loss_kernel_fp32_exact_against_oracle():
+    """pulse_vae_latent_loss / pulse_vae_action_loss on given fp32 heads vs autograd on the oracle's expressions."""
+    from oracle import pulse_oracle as po
+    from pulse_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(5)
+    T, NE, E, A = 16, 40, 32, 69
+    M = T * NE
+    enc = torch.randn(M, 2 * E, generator=gen)
+    enc[:, E:] = enc[:, E:] * 3 - 1
+    pri = torch.randn(M, 2 * E, generator=gen)
+    pri[:, E:] = pri[:, E:] * 3 - 1
+    noise, dz = torch.randn(M, E, generator=gen), torch.randn(M, E, generator=gen) * 1e-3
+    prog = (torch.arange(T)[None, :] + torch.randint(0, 50, (NE, 1), generator=gen)).clone()
+    prog[::5, 7:] = torch.arange(T - 7)[None, :]
+    prog = prog.reshape(M)
+    for regu in (0.0, 0.005):
+        e, p = enc.clone().requires_grad_(True), pri.clone().requires_grad_(True)
+        qm, qv = e[:, :E], torch.clamp(e[:, E:], -5.0, 2.0)
+        pm, pv = p[:, :E], torch.clamp(p[:, E:], -5.0, 2.0)
+        kld = po.kl_multi(qm, qv, pm, pv).mean()
+        tz = qm.view(NE, T, E)
+        err = tz[:, 1:] - tz[:, :-1] * 0.99
+        idx = prog.view(NE, T, 1)
+        keep = ~(((idx[:, 1:] - idx[:, :-1]) != 1) | (idx <= 2)[:, 1:] | (idx <= 2)[:, :-1])
+        ar1 = torch.norm((err * keep.float()).reshape(-1, E), dim=-1).mean()
+        reg = ((pm ** 2).mean() + (qm ** 2).mean() + (pv ** 2).mean() + (qv ** 2).mean()) * 0.001
+        z = qm + torch.exp(0.5 * qv) * noise
+        loss = 0.01 * kld + 0.005 * ar1 + regu * reg + (z * dz).sum()
+        loss.backward()
+        d_e = torch.zeros(M, 2 * E, device=DEV, dtype=torch.bfloat16)
+        d_p = torch.zeros(M, 2 * E, device=DEV, dtype=torch.bfloat16)
+        stats = torch.zeros(6, device=DEV, dtype=torch.float64)
+        ed, pd_, nd, dzd, prd = enc.to(DEV), pri.to(DEV), noise.to(DEV), dz.to(DEV), prog.to(DEV)
+        a = _lib.VaeLatentArgs(enc_head=ed.data_ptr(), ld_enc=2 * E, prior_head=pd_.data_ptr(), ld_prior=2 * E, noise=nd.data_ptr(), ld_noise=E,
+                               dz=dzd.data_ptr(), ld_dz=E, progress=prd.data_ptr(), latent=E, horizon=T, clamp=1, clamp_lo=-5.0, clamp_hi=2.0,
+                               kld_coef=0.01, ar1_coef=0.005, regu_coef=regu, phi=0.99, d_enc_head=d_e.data_ptr(), ld_de=2 * E,
+                               d_prior_head=d_p.data_ptr(), ld_dp=2 * E, stats=stats.data_ptr())
+        _lib.check(lib.pulse_vae_latent_loss(C.byref(a), M, _lib.current_stream(DEV)), "pulse_vae_latent_loss")
+        s = stats.cpu()
+        assert abs(float(s[0]) / M - float(kld)) < 1e-4 * float(kld)
+        assert abs(float(s[1]) / (NE * (T - 1)) - float(ar1)) < 1e-5
+        # bf16 outputs: compare at bf16 resolution
+        torch.testing.assert_close(d_e.float().cpu(), e.grad, atol=1e-6, rtol=1e-2)
+        torch.testing.assert_close(d_p.float().cpu(), p.grad, atol=1e-6, rtol=1e-2)
+    pred, gt = torch.randn(M, A, generator=gen), torch.randn(M, A, generator=gen)
+    gt[3] = pred[3]
+    pr = pred.clone().requires_grad_(True)
+    torch.norm(pr - gt, dim=-1).mean().backward()
+    dp = torch.full((M, 72), 7.0, device=DEV, dtype=torch.bfloat16)
+    st = torch.zeros(1, device=DEV, dtype=torch.float64)
+    predd, gtd = pred.to(DEV), gt.to(DEV)
+    _lib.check(lib.pulse_vae_action_loss(predd.data_ptr(), A, gtd.data_ptr(), A, M, A, dp.data_ptr(), 72, 72, st.data_ptr(), _lib.current_stream(DEV)),
+               "pulse_vae_action_loss")
+    assert abs(float(st[0]) / M - float(torch.norm(pred - gt, dim=-1).mean())) < 1e-5
+    torch.testing.assert_close(dp[:, :A].float().cpu(), pr.grad, atol=1e-7, rtol=1e-2)
+    assert float(dp[:, A:].abs().max()) == 0.0 and float(dp[3].abs().max()) == 0.0
+
+
+def test_teacher_pnn_matches_reference():
+    g, _, _, d, _, _ = vae_golden()
+    from pulse_b200.vae import TeacherPNN
+    t = TeacherPNN(obs_size=d["S"] + d["Tk"], num_actions=d["A"], prim_units=(64, 48), composer_units=(56, 32), num_prim=3, device=DEV)
+    t.load_weights({k[4:]: v for k, v in g.items() if k.startswith("pnn.")}, {k[9:]: v for k, v in g.items() if k.startswith("composer.")},
+                   g["teacher_mean"], g["teacher_var"])
+    out = t.gt_action(g["teacher_raw_obs"].to(DEV))
+    torch.testing.assert_close(out.cpu(), g["teacher_action"], atol=3e-2, rtol=3e-2)
+
+
+def test_z_decode_and_pd_targets_match_reference():
+    g, sd, _, d, _, _ = vae_golden()
+    from pulse_b200.vae import pd_targets
+    vae = _build_vae(g, sd, d)
+    vae.obs_rms.running_mean[:d["S"]] = g["teacher_mean"][:d["S"]].double().to(DEV)
+    vae.obs_rms.running_var[:d["S"]] = g["teacher_var"][:d["S"]].double().to(DEV)
+    vae.obs_rms._refresh()
+    acts = vae.compute_z_actions(g["teacher_raw_obs"].to(DEV), g["action_z"].to(DEV))
+    torch.testing.assert_close(acts.cpu(), g["z_actions"], atol=3e-2, rtol=3e-2)
+    pd = pd_targets(g["gt_action"].to(DEV), g["pd_offset"].to(DEV), g["pd_scale"].to(DEV))
+    torch.testing.assert_close(pd.cpu(), g["pd_target"], atol=0, rtol=0)      # two fp32 roundings, bit-exact
+    frz = torch.zeros(d["A"], dtype=torch.uint8)
+    frz[2] = 1
+    pd2 = pd_targets(g["gt_action"].to(DEV), g["pd_offset"].to(DEV), g["pd_scale"].to(DEV), freeze=frz.to(DEV))
+    assert float(pd2[:, 2].abs().max()) == 0.0 and torch.equal(pd2[:, 3].cpu(), g["pd_target"][:, 3])
+
+
+def test_reach_step_matches_reference():
+    g = load_npz("vae.npz")
+    from pulse_b200.reach import ReachTaskB200, SMPL_BODY_NAMES
+    B = g["reach_body_state"].shape[0]
+    task = ReachTaskB200(B, device=DEV, reach_body_name="R_Hand", contact_bodies=[SMPL_BODY_NAMES[i] for i in g["reach_contact_ids"].tolist()],
+                         max_episode_length=300)
+    task.termination_heights.copy_(g["reach_term_h"].to(DEV))
+    task._tar_pos.copy_(g["reach_tar_pos"].to(DEV))
+    # Isaac Gym style padded views: 26 bodies per env, read in place
+    bs = torch.zeros(B, 26, 13, device=DEV)
+    bs[:, :24] = g["reach_body_state"].to(DEV)
+    cf = torch.zeros(B, 26, 3, device=DEV)
+    cf[:, :24] = g["reach_contact"].to(DEV)
+    task.post_physics_step(bs, g["reach_progress"].to(DEV), cf)
+    assert torch.equal(task.reset_buf.cpu(), g["reach_reset"]) and torch.equal(task._terminate_buf.cpu(), g["reach_terminate"])
+    torch.testing.assert_close(task.obs_buf[:, :358].cpu(), g["reach_self_obs"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(task.obs_buf[:, 358:].cpu(), g["reach_obs_full"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(task.rew_buf.cpu(), g["reach_reward_full"], atol=1e-6, rtol=1e-5)
+    # target resampling with injected draws
+    prog = torch.tensor([5, 50, 120, 7] + [0] * (B - 4), device=DEV)
+    task._tar_change_steps.copy_(torch.tensor([10, 50, 100, 7] + [1] * (B - 4), device=DEV))
+    before = task._tar_pos.clone()
+    u = torch.rand(B, 3, device=DEV)
+    steps = torch.randint(100, 200, (B,), device=DEV)
+    task.update_task(prog, u, steps)
+    sel = torch.tensor([False, True, True, True] + [False] * (B - 4), device=DEV)
+    exp = torch.stack([1.0 * (2 * u[:, 0] - 1), 1.0 * (2 * u[:, 1] - 1), (1.5 - 0.5) * u[:, 2] + 0.5], dim=-1)
+    torch.testing.assert_close(task._tar_pos[sel], exp[sel], atol=1e-6, rtol=1e-6)
+    assert torch.equal(task._tar_pos[~sel], before[~sel])
+    assert torch.equal(task._tar_change_steps[sel], (prog + steps)[sel])

@@ -200,3 +200,15 @@ def test_vae_distillation_teacher_zdecode_reach_pd():
         close(po.reach_reward(g["reach_body_pos"], g["reach_tar_pos"]), g["reach_reward"])
         close(po.pd_targets(g["gt_action"], g["pd_offset"], g["pd_scale"]), g["pd_target"])
     assert abs(po.kld_anneal(3750) - 0.0055) < 1e-9 and po.kld_anneal(6000) == 0.001
+
+
+def test_reach_full_step_pieces():
+    from tests.helpers import load_npz as _l
+    g = _l("vae.npz")
+    bs = g["reach_body_state"]
+    rs, tm = po.humanoid_reset(g["reach_progress"], g["reach_contact"], g["reach_contact_ids"], bs[..., 0:3], 300, True, g["reach_term_h"])
+    assert torch.equal(rs, g["reach_reset"]) and torch.equal(tm, g["reach_terminate"])
+    assert 0 < int(tm.sum()) < tm.numel()
+    close(po.self_obs_smpl_max(bs[..., 0:3], bs[..., 3:7], bs[..., 7:10], bs[..., 10:13]), g["reach_self_obs"])
+    close(po.reach_obs(bs[:, 0, :], g["reach_tar_pos"]), g["reach_obs_full"])
+    close(po.reach_reward(bs[:, 23, 0:3], g["reach_tar_pos"]), g["reach_reward_full"])
