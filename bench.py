@@ -210,7 +210,7 @@ def workload_config(a, world, envs_total):
                     f"lognormal lengths, median {a.median_frames} frames @30fps), horizon 32, im.yaml nets (BASELINE configs[3])",
         "envs_total": envs_total, "envs_per_gpu": envs_total // world, "horizon": HORIZON, "minibatch": MINIBATCH,
         "mini_epochs": MINI_EPOCHS, "minibatches_per_epoch_per_gpu": mb, "parallelism": f"env-shard x{world}, grad all-reduce per minibatch",
-        "phases": ["32x [obs normalise + actor/critic MLP fwd (tcgen05) + Gaussian sample (K7-K9)]",
+        "phases": ["32x [obs normalise + actor/critic MLP fwd (tcgen05) + Gaussian sample (K7-K9) + action -> PD target (K22)]",
                    "32x fused reward+reset+obs kernel (K1-K5)", "32x AMP obs + history kernel (K6)",
                    "32x critic fwd on next obs (next_values)", "discriminator fwd + AMP reward over 32xN rows (K10)",
                    "GAE + returns + adv-norm (K11,K12)", "value/return normalisation (running stats)",
@@ -218,7 +218,7 @@ def workload_config(a, world, envs_total):
                    "discriminator loss on 3x4096 AMP rows: BCE + logit reg + weight decay + ANALYTIC gradient penalty (K14), "
                    "NCCL grad all-reduce (N>1), grad-norm clip + Adam incl. bf16 operand mirror (K13,K15,K16)",
                    "AMP demo fetch (MotionLib query + AMP obs), demo / replay ring updates and per-minibatch draws"],
-        "not_yet": ["action -> PD target (K22, four element-wise ops feeding Isaac Gym)"],
+        "not_yet": [],
         "physics": "excluded (Isaac Gym not installable; simulator state tensors are synthetic, resident in HBM)",
         "l2": "256 MiB L2 flush write before every timed iteration; per-iteration working set (tables 3.9 GB + 6 GB rollout buffers at N=1) exceeds L2",
     }
@@ -254,6 +254,7 @@ def main():
     from pulse_b200.nets import pad_k
     from pulse_b200.ppo import PPOPolicy
     from pulse_b200.rollout import discount_values
+    from pulse_b200.vae import pd_targets
     from tools.synth import device_step_inputs, device_tables
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,6 +304,8 @@ def main():
     term_buf = torch.zeros(n, dtype=torch.long, device=dev)
     amp_buf = torch.zeros(n, 10, 196, device=dev)
     progress0 = z["progress_buf"].clone()
+    pd_offset, pd_scale = torch.zeros(69, device=dev), torch.full((69,), 1.2, device=dev)   # _build_pd_action_offset_scale (humanoid.py:492-543)
+    pd_tar = torch.zeros(n, 69, device=dev)              # what gym.set_dof_position_target_tensor would receive
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # pinned host mirrors for the end-to-end arm
     h_body = z["body_state"].cpu().pin_memory()
@@ -336,6 +339,7 @@ def main():
         mus[:, t].copy_(res["mus"])
         neglogp[:, t].copy_(res["neglogpacs"])
         values[t].copy_(res["values"])
+        pd_targets(res["actions"], pd_offset, pd_scale, out=pd_tar)   # pre_physics_step -> _action_to_pd_targets (K22)
         z["progress_buf"] += 1                                # physics would run here (excluded); post_physics_step follows
 
     def env_step(t):
@@ -476,6 +480,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (k_avg * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one im_step_kernel launch at 16384 envs (ncu --set full, profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "im_step_traffic.json")))
+        if int(tr.get("envs", 0)) == n:
+            traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
+    except Exception:
+        pass
     env_steps = T * a.envs
     _d = 1960 * 1024 + 1024 * 512 + 512
     _gp = 3 * (512 * 1024 + 1024 * 1960)
@@ -492,7 +503,8 @@ def main():
                     "d2h_bytes_per_step": T * d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches_eager), "cuda_graphs": bool(use_graphs), "clocks": clocks,
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/im_step_traffic.json)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "avg_launch_ms": k_avg, "launches_timed": len(k_ms)},
             "roofline_update": {"kernels": "PPO update phase (tcgen05 GEMMs + loss/Adam/reduction kernels), per rank", "bound": "tensor",
