@@ -522,7 +522,15 @@ def main():
                                               "(oracle port of the reference PyTorch path, fp32), scaled to a 32-step iteration"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroy_process_group() was measured to hang at N=2 while CUDA graphs
+        # holding captured NCCL kernels are alive.  Everything is done and printed; a barrier keeps the ranks together, then
+        # every rank exits 0 directly.
+        graphs.clear()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
