@@ -264,6 +264,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL_DEBUG=VERSION prints a banner on STDOUT ahead of the JSON line
         dist.init_process_group("nccl", device_id=dev)
     n = a.envs // world
     lib = _lib.load()
