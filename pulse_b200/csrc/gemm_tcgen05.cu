@@ -18,6 +18,7 @@
 //               derivative gating -> bf16 row-major, bf16 transposed and/or fp32 outputs.
 // Split-K (blockIdx.z) writes fp32 partial slabs for the weight gradients.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "pulse_common.cuh"
@@ -25,6 +26,9 @@
 namespace pulse {
 namespace {
 
+#ifndef PULSE_GEMM_VARIANT
+#define PULSE_GEMM_VARIANT 0   // development experiments only (see tools/build_variant.sh); 0 = product
+#endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int kStagesG = 4;   // 4 x 48 KB ring (one CTA per SM)
 constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns
@@ -146,6 +150,37 @@ __device__ __forceinline__ float act_grad(float g, int mode) {
   return 1.0f;
 }
 
+
+// Coalesced bf16 store of one epilogue warp's 32-row x 32-column block.  A lane holds 32 columns (64 bytes) of ITS row, so
+// a direct 16-byte store instruction would touch 32 different rows (32 half-used sectors; measured 45.9 -> 41.6 us on the
+// 16384 x 1024 x 934 layer).  The block goes through the warp's private 2 KB shared tile instead (16-byte units,
+// XOR-swizzled so both the row-wise writes and the 8-rows-at-a-time reads are bank-conflict free) and leaves as
+// 8 rows x 64 contiguous bytes per instruction.  All 32 lanes must call it; rows >= rows_valid are not written.
+__device__ __forceinline__ void store_block_bf16(uint4* st, const float (&v)[32], __nv_bfloat16* base, long long ld, int rows_valid, int lane) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = 8 * q;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<unsigned*>(&h0);
+    u.y = *reinterpret_cast<unsigned*>(&h1);
+    u.z = *reinterpret_cast<unsigned*>(&h2);
+    u.w = *reinterpret_cast<unsigned*>(&h3);
+    st[lane * 4 + (q ^ sw)] = u;
+  }
+  __syncwarp();
+  __nv_bfloat16* obase = base + (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    const uint4 val = st[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+    if (rr < rows_valid) *reinterpret_cast<uint4*>(obase + static_cast<long long>(rr) * ld) = val;
+  }
+  __syncwarp();
+}
+
 // A_MN / B_MN: operand is MN-major in global memory ([reduction rows, non-reduction cols] row-major) instead of K-major.
 // Persistent: one CTA per SM loops over (tile, split) work items.  The TMA ring runs continuously across
 // items; the accumulator is double-buffered in TMEM (2 x 128 columns) so the epilogue of item i overlaps the
@@ -154,7 +189,7 @@ __device__ __forceinline__ float act_grad(float g, int mode) {
 // instance and the three warp roles run disjoint parts of it: measured, growing it by 260 instructions that never execute
 // slowed the forward layers from 39.6 to 54.6 us (instruction-cache misses).  Each specialisation carries only what its
 // caller can ask for; the host picks the smallest one that covers the request.
-enum : int { kModeGeneric = 0, kModeFwd = 1, kModeDgrad = 2, kModeWgrad = 3 };
+enum : int { kModeGeneric = 0, kModeFwd = 1, kModeDgrad = 2, kModeWgrad = 3, kModeDgradVec = 4 };
 
 template <bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -162,7 +197,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                                                                       const pulse_gemm_epilogue_t ep, int M, int N, int K,
                                                                       int kb_per_split, int splits) {
   constexpr bool kFwd = MODE == kModeGeneric || MODE == kModeFwd;      // bias, activation, pre-activation copy, transposed copy
-  constexpr bool kDgrad = MODE == kModeGeneric || MODE == kModeDgrad;  // activation-derivative gate, column sums, sum of squares
+  constexpr bool kDgrad = MODE == kModeGeneric || MODE == kModeDgrad || MODE == kModeDgradVec;  // activation-derivative gate, column sums, sum of squares
+  constexpr bool kGateVec = MODE == kModeGeneric || MODE == kModeDgradVec;  // prefetched general gate (SiLU); its 32 registers would spill kModeDgrad
   constexpr bool kAccum = MODE == kModeGeneric || MODE == kModeWgrad;  // fp32 atomic accumulation (weight gradients)
   constexpr bool kBf16Out = MODE != kModeWgrad;
   extern __shared__ unsigned char gsm_raw[];
@@ -198,10 +234,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const unsigned tmem_base = sm.tmem_base;
+  // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now -- its CTAs land on SMs as ours exit and
+  // run their own prologue (barrier init, TMEM allocation, tensor-map prefetch) under our tail -- while this kernel's first
+  // global-memory access waits (griddepcontrol.wait) until the PREVIOUS kernel has completed and flushed.  Roles that never
+  // touch global memory (the MMA issuer) do not wait.
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
   if (warp == 0) {
     // ================================ TMA producer ======================================================
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;\n" ::: "memory");
       int it = 0;  // running k-block counter across work items: stage = it % kStagesG
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int split = w / tiles, t = w - split * tiles;
@@ -262,6 +304,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
     const int chalf = (warp - 2) >> 2;       // which 128-column half of the accumulator this warp drains
     float* red_stage = sm.red[warp - 2];     // warp-private 16 x 33 fp32 tile for coalesced atomics
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     int lw = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
       const int split = w / tiles, t = w - split * tiles;
@@ -273,7 +316,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       // ReLU-derivative gate: the saved activations do not depend on the accumulator, so this thread's 128 gate values
       // (256 contiguous bytes of its row) are fetched BEFORE waiting for the MMAs -- their latency hides behind the main
       // loop -- and folded to one bit each (4 registers) so nothing but the mask stays live across the wait.
-      const bool gate_fast = kDgrad && ep.gate != nullptr && ep.gate_mode == PULSE_ACT_RELU && (ep.ldg & 7) == 0 && n0 + chalf * 128 + 128 <= N;
+      const bool gate_fast = (MODE == kModeGeneric || MODE == kModeDgrad) && ep.gate != nullptr && ep.gate_mode == PULSE_ACT_RELU && (ep.ldg & 7) == 0 && n0 + chalf * 128 + 128 <= N;
       unsigned gmask[4] = {0u, 0u, 0u, 0u};
       if (gate_fast && row_ok) {
         const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg +
@@ -294,6 +337,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           }
         }
       }
+      // General gate (SiLU pre-activations, or ReLU on a ragged column group): 64 bytes of this thread's row per 32-column
+      // chunk, fetched one chunk AHEAD -- the first before the accumulator wait, the next right after the current one is applied --
+      // so the load latency is never exposed (it was: 121 us on the 16384 x 1536 x 1024 SiLU dgrad).
+      const bool gate_vec = kGateVec && ep.gate != nullptr && !gate_fast && (ep.ldg & 7) == 0;
+      uint4 gq[4] = {};
+      auto gate_fetch = [&](int cc) {
+        const int c0 = n0 + cc * 32;
+        if (gate_vec && row_ok && c0 + 32 <= N) {
+          const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gq[q] = __ldg(g + q);
+        }
+      };
+      gate_fetch(chalf * 4);
       g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
@@ -336,11 +393,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
           }
         }
-        if (kFwd && ep.preact != nullptr && row_ok) {
-          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
+        if (kFwd && ep.preact != nullptr) {  // SiLU pre-activations for the backward pass (measured: scalar stores here made the layer 10x slower)
+          if (full && (ep.ldp & 7) == 0) {
+            store_block_bf16(reinterpret_cast<uint4*>(red_stage), v,
+                             reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(m0 + quarter * 32) * ep.ldp + col0, ep.ldp,
+                             M - (m0 + quarter * 32), lane);
+          } else if (row_ok) {
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+          }
         }
         if (kFwd && ep.act != PULSE_ACT_NONE) {
 #pragma unroll
@@ -353,10 +416,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           for (int i = 0; i < 32; ++i) v[i] = ((mk >> ((i >> 1) + 16 * (i & 1))) & 1u) ? v[i] : 0.0f;
         } else if (kDgrad && ep.gate != nullptr && row_ok) {
           const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
-          if (full && (ep.ldg & 7) == 0) {
+          if (full && (gate_vec || (ep.ldg & 7) == 0)) {
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + i));
+              const uint4 u = gate_vec ? gq[i >> 3] : __ldg(reinterpret_cast<const uint4*>(g + i));
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -371,6 +434,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
           }
         }
+        if (gate_vec && c != chalf * 4 + 3) gate_fetch(c + 1);  // consumed one chunk later: covered by the column sums + stores below
         if (kDgrad && ep.sumsq != nullptr && row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -423,6 +487,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) p[i] = v[i];
           }
         }
+#if PULSE_GEMM_VARIANT == 1   // experiment: no bf16 stores at all (keeps the math alive through an impossible condition)
+        if (kBf16Out && ep.out != nullptr && row_ok && v[0] == 1.2345678e30f) {
+          reinterpret_cast<__nv_bfloat16*>(ep.out)[row] = __float2bfloat16(v[1]);
+        }
+#elif PULSE_GEMM_VARIANT == 2   // experiment: the previous direct row-per-lane 16-byte stores
         if (kBf16Out && ep.out != nullptr && row_ok) {
           __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
           if (full && (ep.ldo & 7) == 0) {
@@ -443,6 +512,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
           }
         }
+#else
+        if (kBf16Out && ep.out != nullptr) {
+          if (full && (ep.ldo & 7) == 0) {
+            store_block_bf16(reinterpret_cast<uint4*>(red_stage), v,
+                             reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(m0 + quarter * 32) * ep.ldo + col0, ep.ldo,
+                             M - (m0 + quarter * 32), lane);
+          } else if (row_ok) {
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
+          }
+        }
+#endif
         if (kFwd && ep.out_t != nullptr && row_ok) {
           // transposed bf16 copy (not used by the MLP path any more; kept for API completeness): lanes hold consecutive
           // rows -> consecutive 2-byte addresses of out_t[col][row]
@@ -512,7 +595,22 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
   }
   const long long total = static_cast<long long>((n + BN - 1) / BN) * ((m + BM - 1) / BM) * splits;
   const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);  // persistent: one CTA per SM
-  gemm_bf16_kernel<A_MN, B_MN, MODE><<<grid, kGemmThreads, smem, stream>>>(map_a, map_b, ep, m, n, k, kb_per_split, splits);
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("PULSE_GEMM_PDL");
+    use_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE>, map_a, map_b, ep, m, n, k, kb_per_split, splits));
   PULSE_LAUNCH_OK("gemm_bf16_kernel");
   return PULSE_OK;
 }
@@ -562,7 +660,7 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   const bool want_accum = ep->accumulate != 0;
   int mode = kModeGeneric;
   if (!want_dgrad && !want_accum) mode = kModeFwd;
-  else if (!want_fwd && !want_accum) mode = kModeDgrad;
+  else if (!want_fwd && !want_accum) mode = (ep->gate && ep->gate_mode != PULSE_ACT_RELU) ? kModeDgradVec : kModeDgrad;
   else if (!want_fwd && !want_dgrad && !ep->out) mode = kModeWgrad;
   const int mi = (int)m, ni = (int)n, ki = (int)k;
 #define PULSE_GEMM_DISPATCH(AM, BM_)                                                                               \
@@ -570,6 +668,7 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
     case kModeFwd: return launch_gemm<AM, BM_, kModeFwd>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);     \
     case kModeDgrad: return launch_gemm<AM, BM_, kModeDgrad>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
     case kModeWgrad: return launch_gemm<AM, BM_, kModeWgrad>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
+    case kModeDgradVec: return launch_gemm<AM, BM_, kModeDgradVec>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
     default: return launch_gemm<AM, BM_, kModeGeneric>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);       \
   }
   if (a_mn && b_mn) { PULSE_GEMM_DISPATCH(true, true) }

@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None, help="run just the cases whose name contains this (for ncu captures)")
+    ap.add_argument("--vae", action="store_true", help="the SiLU stacks of the PULSE VAE (im_z_fit.yaml) instead of the PPO nets")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = {"bf16": 1514.7, "hbm": 6481.8}
@@ -45,7 +46,7 @@ def main():
     bf = lambda r, c: (torch.randn(r, c, device=dev) * 0.1).bfloat16()
     rows = []
 
-    def case(name, M, N, K, kind, gate=False, colsum=False, f32=False, bf16_out=True, alpha=1.0):
+    def case(name, M, N, K, kind, gate=False, colsum=False, f32=False, bf16_out=True, alpha=1.0, act="relu", preact=False):
         """kind: 'nt' (A [M,K], B [N,K]), 'dgrad' (A [M,K], B [K,N] MN-major), 'wgrad' (A [K,M], B [K,N], atomics into fp32)."""
         if a.only and a.only not in name:
             return
@@ -75,9 +76,12 @@ def main():
                 kw.update(out_f32=torch.zeros(M, Np, device=dev))
                 byt += M * N * 4
             if kind == "nt" and not gate:
-                kw.update(bias=torch.zeros(N, device=dev), act="relu" if bf16_out and not f32 else None)
+                kw.update(bias=torch.zeros(N, device=dev), act=act if bf16_out and not f32 else None)
+                if preact:
+                    kw.update(preact=torch.zeros(M, Np, device=dev, dtype=torch.bfloat16))
+                    byt += M * N * 2
         if gate:
-            kw.update(gate=bf(M, Np), gate_mode="relu")
+            kw.update(gate=bf(M, Np), gate_mode=act)
             byt += M * N * 2
         if colsum:
             kw.update(colsum=torch.zeros(Np, device=dev))
@@ -90,7 +94,15 @@ def main():
                      "gbs": round(byt / us / 1e3, 1), "floor_us": round(floor, 2), "eff": round(floor / us, 3)})
 
     B, Bd, Bg = 16384, 12288, 4096
-    for net, head in (("actor", 69), ("critic", 1)):
+    if a.vae:
+        for net, sizes in (("enc", [934, 1536, 1024, 512, 160]), ("prior", [358, 1536, 1024, 512]), ("dec", [390, 3096, 2048, 1024])):
+            for i in range(len(sizes) - 1):
+                k, n = sizes[i], sizes[i + 1]
+                case(f"{net}.fwd{i}", B, n, k, "nt", act="silu", preact=True)
+                case(f"{net}.wgrad{i}", n, k, B, "wgrad")
+                if i > 0:
+                    case(f"{net}.dgrad{i}", B, k, n, "dgrad", gate=True, colsum=True, act="silu")
+    for net, head in (() if a.vae else (("actor", 69), ("critic", 1))):
         case(f"{net}.fwd1", B, 1024, 934, "nt")
         case(f"{net}.fwd2", B, 512, 1024, "nt")
         case(f"{net}.head", B, head, 512, "nt", f32=True, bf16_out=False)
@@ -99,20 +111,23 @@ def main():
         case(f"{net}.wgrad2", 512, 1024, B, "wgrad")
         case(f"{net}.dgrad2", B, 1024, 512, "dgrad", gate=True, colsum=True)
         case(f"{net}.wgrad1", 1024, 934, B, "wgrad")
-    case("disc.fwd1", Bd, 1024, 1960, "nt")
-    case("disc.fwd2", Bd, 512, 1024, "nt")
-    case("disc.head", Bd, 1, 512, "nt", f32=True, bf16_out=False)
-    case("disc.wgrad_head", 1, 512, Bd, "wgrad")
-    case("disc.dgrad_head", Bd, 512, 1, "dgrad", gate=True, colsum=True)
-    case("disc.wgrad2", 512, 1024, Bd, "wgrad")
-    case("disc.dgrad2", Bd, 1024, 512, "dgrad", gate=True, colsum=True)
-    case("disc.wgrad1", 1024, 1960, Bd, "wgrad")
-    case("gp.g1", Bg, 1024, 512, "dgrad", gate=True)
-    case("gp.G", Bg, 1960, 1024, "dgrad", f32=True, alpha=0.01)
-    case("gp.dW1", 1024, 1960, Bg, "wgrad")
-    case("gp.du", Bg, 1024, 1960, "nt", gate=True)
-    case("gp.dW2", 512, 1024, Bg, "wgrad")
-    case("gp.dw3", Bg, 512, 1024, "nt", gate=True, colsum=True)
+    if a.vae:
+        Bd = Bg = 0
+    nonvae = lambda *args, **kw2: None if a.vae else case(*args, **kw2)
+    nonvae("disc.fwd1", Bd, 1024, 1960, "nt")
+    nonvae("disc.fwd2", Bd, 512, 1024, "nt")
+    nonvae("disc.head", Bd, 1, 512, "nt", f32=True, bf16_out=False)
+    nonvae("disc.wgrad_head", 1, 512, Bd, "wgrad")
+    nonvae("disc.dgrad_head", Bd, 512, 1, "dgrad", gate=True, colsum=True)
+    nonvae("disc.wgrad2", 512, 1024, Bd, "wgrad")
+    nonvae("disc.dgrad2", Bd, 1024, 512, "dgrad", gate=True, colsum=True)
+    nonvae("disc.wgrad1", 1024, 1960, Bd, "wgrad")
+    nonvae("gp.g1", Bg, 1024, 512, "dgrad", gate=True)
+    nonvae("gp.G", Bg, 1960, 1024, "dgrad", f32=True, alpha=0.01)
+    nonvae("gp.dW1", 1024, 1960, Bg, "wgrad")
+    nonvae("gp.du", Bg, 1024, 1960, "nt", gate=True)
+    nonvae("gp.dW2", 512, 1024, Bg, "wgrad")
+    nonvae("gp.dw3", Bg, 512, 1024, "nt", gate=True, colsum=True)
     tot, fl = sum(r["us"] for r in rows), sum(r["floor_us"] for r in rows)
     for r in rows:
         print(f"{r['name']:18s} {r['kind']:5s} M={r['M']:6d} N={r['N']:5d} K={r['K']:6d}  {r['us']:8.2f} us  {r['tflops']:7.1f} TF  "
