@@ -30,20 +30,27 @@ namespace {
 #define PULSE_GEMM_VARIANT 0   // development experiments only (see tools/build_variant.sh); 0 = product
 #endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int kStagesG = 4;   // 4 x 48 KB ring (one CTA per SM)
 constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
-constexpr unsigned kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr unsigned kStageBytesA = BM * BK * 2;
 constexpr unsigned kTmemCols = 512;  // two 256-column fp32 accumulators (all of TMEM)
 
-struct __align__(1024) GemmSmem {
-  unsigned char a[kStagesG][kStageBytesA];
-  unsigned char b[kStagesG][kStageBytesB];
-  unsigned long long full[kStagesG];
-  unsigned long long empty[kStagesG];
+// CTAS = 1: one CTA per 128 x 256 tile, 4 x 48 KB ring.  CTAS = 2: a CTA PAIR (cluster of two SMs, tcgen05 cta_group::2) per
+// 256 x 256 tile -- each CTA stages its own 128 rows of A and HALF of B (128 of the 256 columns), the leader's MMA reads both
+// halves, so the L2 -> SM operand traffic per MAC drops by a third (the single-CTA kernel was measured at the L2 delivery
+// limit: 8.9 TB/s of operand reads at 47 % tensor-pipe activity) and the 32 KB stages allow a 6-deep ring.
+template <int CTAS>
+struct __align__(1024) GemmSmemT {
+  static constexpr int kStages = CTAS == 2 ? 6 : 4;
+  static constexpr unsigned kStageBytesB = (BN / CTAS) * BK * 2;
+  unsigned char a[kStages][kStageBytesA];
+  unsigned char b[kStages][kStageBytesB];
+  unsigned long long full[kStages];
+  unsigned long long empty[kStages];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
-  float red[kEpiWarps][16 * 33];   // per-epilogue-warp transpose tile (16 rows at a time) for coalesced fp32 atomics
+  float red[kEpiWarps][16 * 33];   // per-epilogue-warp tile: fp32 transpose for coalesced atomics / bf16 store staging
+  float bias[kEpiWarps][128];      // per-epilogue-warp copy of the bias of its 128 columns (broadcast reads in the forward epilogue)
   unsigned tmem_base;
 };
 
@@ -121,6 +128,53 @@ __device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// The pair's barriers live in the LEADER (cluster rank 0): clearing bit 24 of a shared::cluster address turns the peer's
+// window address into the leader's (the offset inside the CTA is the same) -- the convention cta_group::2 TMA loads use.
+constexpr unsigned kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                   s_u32(smem_dst)),
+               "l"(map), "r"(s_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs of the pair when the preceding MMAs retire
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(s_u32(bar)),
+               "h"(static_cast<unsigned short>(3))
+               : "memory");
+}
+// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(unsigned long long* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(s_u32(bar))
+      : "memory");
+}
+template <int UM>
+__host__ __device__ constexpr unsigned instr_desc_m(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<unsigned>(BN >> 3) << 17) | (static_cast<unsigned>(UM >> 4) << 24);
+}
+
 // issue only: the registers are valid after tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
   asm volatile(
@@ -137,14 +191,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == PULSE_ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == PULSE_ACT_SILU) return x / (1.0f + __expf(-x));
+  if (act == PULSE_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));   // 2 MUFU ops; the IEEE division subroutine dominated the SiLU epilogue
   return x;
 }
 __device__ __forceinline__ float act_grad(float g, int mode) {
   // g: saved tensor -- ReLU: the layer's OUTPUT (>0 <=> active); SiLU: the layer's PRE-activation z
   if (mode == PULSE_ACT_RELU) return g > 0.0f ? 1.0f : 0.0f;
   if (mode == PULSE_ACT_SILU) {
-    const float s = 1.0f / (1.0f + __expf(-g));
+    const float s = __fdividef(1.0f, 1.0f + __expf(-g));
     return s * (1.0f + g * (1.0f - s));
   }
   return 1.0f;
@@ -181,6 +235,26 @@ __device__ __forceinline__ void store_block_bf16(uint4* st, const float (&v)[32]
   __syncwarp();
 }
 
+#if PULSE_GEMM_VARIANT == 3 || PULSE_GEMM_VARIANT == 1   // development: per-phase clock64 trace of CTA 0 (tools/gemm_trace.py)
+__device__ long long g_gemm_trace[32];
+#define PULSE_TRACE(slot)                                          \
+  do {                                                             \
+    if (blockIdx.x == 0) g_gemm_trace[slot] = clock64();           \
+  } while (0)
+#else
+#define PULSE_TRACE(slot) \
+  do {                    \
+  } while (0)
+#endif
+
+// silu(z) = z sigmoid(z) = 0.5 z (1 + tanh(z / 2)) on a bf16 pair: one MUFU (tanh.approx.bf16x2) per TWO elements
+__device__ __forceinline__ __nv_bfloat162 silu_bf16x2(__nv_bfloat162 z) {
+  const __nv_bfloat162 hz = __hmul2(z, __float2bfloat162_rn(0.5f));
+  unsigned t;
+  asm("tanh.approx.bf16x2 %0, %1;\n" : "=r"(t) : "r"(*reinterpret_cast<const unsigned*>(&hz)));
+  return __hfma2(hz, *reinterpret_cast<const __nv_bfloat162*>(&t), hz);
+}
+
 // A_MN / B_MN: operand is MN-major in global memory ([reduction rows, non-reduction cols] row-major) instead of K-major.
 // Persistent: one CTA per SM loops over (tile, split) work items.  The TMA ring runs continuously across
 // items; the accumulator is double-buffered in TMEM (2 x 128 columns) so the epilogue of item i overlaps the
@@ -191,7 +265,7 @@ __device__ __forceinline__ void store_block_bf16(uint4* st, const float (&v)[32]
 // caller can ask for; the host picks the smallest one that covers the request.
 enum : int { kModeGeneric = 0, kModeFwd = 1, kModeDgrad = 2, kModeWgrad = 3, kModeDgradVec = 4 };
 
-template <bool A_MN, bool B_MN, int MODE>
+template <bool A_MN, bool B_MN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_b,
                                                                       const pulse_gemm_epilogue_t ep, int M, int N, int K,
@@ -203,12 +277,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   constexpr bool kBf16Out = MODE != kModeWgrad;
   extern __shared__ unsigned char gsm_raw[];
   // the 128-byte swizzle atoms need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
-  GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  using Smem = GemmSmemT<CTAS>;
+  constexpr int kStagesG = Smem::kStages;
+  constexpr unsigned kStageBytesB = Smem::kStageBytesB;
+  constexpr int BMT = BM * CTAS;   // rows of the output tile one work item covers (the pair splits them 128 / 128)
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  const unsigned crank = CTAS == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs, owns the full / tmem_empty barriers)
+  const int work0 = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = CTAS == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BMT - 1) / BMT;
   const int tiles = tiles_m * tiles_n;
   const int total = tiles * splits;
   const int num_kb_total = (K + BK - 1) / BK;
+  if (threadIdx.x == 0) PULSE_TRACE(0);
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -219,21 +301,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       g_mbar_init(&sm.tmem_full[s], 1);
-      g_mbar_init(&sm.tmem_empty[s], kEpiWarps);  // one arrival per epilogue warp
+      g_mbar_init(&sm.tmem_empty[s], kEpiWarps * CTAS);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp deallocates
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers are initialised and its TMEM allocated before any cross-CTA traffic
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const unsigned tmem_base = sm.tmem_base;
+  if (threadIdx.x == 0) PULSE_TRACE(1);
   // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now -- its CTAs land on SMs as ours exit and
   // run their own prologue (barrier init, TMEM allocation, tensor-map prefetch) under our tail -- while this kernel's first
   // global-memory access waits (griddepcontrol.wait) until the PREVIOUS kernel has completed and flushed.  Roles that never
@@ -244,37 +334,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     // ================================ TMA producer ======================================================
     if (lane == 0) {
       asm volatile("griddepcontrol.wait;\n" ::: "memory");
+      PULSE_TRACE(2);
       int it = 0;  // running k-block counter across work items: stage = it % kStagesG
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = work0; w < total; w += work_stride) {
         const int split = w / tiles, t = w - split * tiles;
-        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        // this CTA's 128 rows of the tile and (pair mode) its half of the tile's 256 columns of B
+        const int m0 = (t / tiles_n) * BMT + static_cast<int>(crank) * BM, n0 = (t % tiles_n) * BN + static_cast<int>(crank) * (BN / 2) * (CTAS - 1);
         const int kb0 = split * kb_per_split;
         const int num_kb = min(kb_per_split, num_kb_total - kb0);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStagesG;
           g_mbar_wait(&sm.empty[s], ((it / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
-          g_mbar_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
+          // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+          if (CTAS == 1 || crank == 0) g_mbar_expect_tx(&sm.full[s], CTAS * (kStageBytesA + kStageBytesB));
           const int kk = (kb0 + kb) * BK;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (CTAS == 2) tma_load_2d_pair(dst, map, c0, c1, &sm.full[s]);
+            else tma_load_2d(dst, map, c0, c1, &sm.full[s]);
+          };
           if (A_MN) {  // box = [64 reduction rows][64 contiguous m]: two boxes cover the 128-wide tile
-            tma_load_2d(sm.a[s], &map_a, m0, kk, &sm.full[s]);
-            tma_load_2d(sm.a[s] + 8192, &map_a, m0 + 64, kk, &sm.full[s]);
+            load(sm.a[s], &map_a, m0, kk);
+            load(sm.a[s] + 8192, &map_a, m0 + 64, kk);
           } else {
-            tma_load_2d(sm.a[s], &map_a, kk, m0, &sm.full[s]);
+            load(sm.a[s], &map_a, kk, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int h = 0; h < BN / 64; ++h) tma_load_2d(sm.b[s] + h * 8192, &map_b, n0 + h * 64, kk, &sm.full[s]);
+            for (int h = 0; h < BN / CTAS / 64; ++h) load(sm.b[s] + h * 8192, &map_b, n0 + h * 64, kk);
           } else {
-            tma_load_2d(sm.b[s], &map_b, kk, n0, &sm.full[s]);
+            load(sm.b[s], &map_b, kk, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ========================================================
-    if (lane == 0) {
+    if (lane == 0 && crank == 0) {   // pair mode: only the leader issues (its MMAs read both CTAs' stages and write both TMEMs)
       int it = 0, lw = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
+      for (int w = work0; w < total; w += work_stride, ++lw) {
         const int split = w / tiles;
         const int kb0 = split * kb_per_split;
         const int num_kb = min(kb_per_split, num_kb_total - kb0);
@@ -285,6 +382,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStagesG;
           g_mbar_wait(&sm.full[s], (it / kStagesG) & 1);
+          if (it == 0) PULSE_TRACE(3);
+          if (kb == num_kb - 1 && lw < 3) PULSE_TRACE(12 + lw);   // last k-block of the item has landed
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
 #pragma unroll
@@ -292,11 +391,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             // K-major: 16 bf16 = 32 bytes inside the 128-byte swizzle atom; MN-major: 16 reduction rows = two 1024-byte groups
             const unsigned long long da = A_MN ? umma_desc_mn(a_addr + k * 2048) : umma_desc(a_addr + k * 32);
             const unsigned long long db = B_MN ? umma_desc_mn(b_addr + k * 2048) : umma_desc(b_addr + k * 32);
-            umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da, db, instr_desc_m<2 * BM>(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&sm.empty[s]);  // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+          // implies tcgen05.fence::before_thread_sync; frees the stage (in both CTAs of a pair) when the MMAs retire
+          if (CTAS == 2) umma_commit_pair(&sm.empty[s]);
+          else umma_commit(&sm.empty[s]);
         }
-        umma_commit(&sm.tmem_full[acc]);  // accumulator complete
+        if (CTAS == 2) umma_commit_pair(&sm.tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
+        else umma_commit(&sm.tmem_full[acc]);
+        if (lw < 3) PULSE_TRACE(4 + lw);
       }
     }
   } else {
@@ -306,9 +410,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     float* red_stage = sm.red[warp - 2];     // warp-private 16 x 33 fp32 tile for coalesced atomics
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     int lw = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
+    for (int w = work0; w < total; w += work_stride, ++lw) {
       const int split = w / tiles, t = w - split * tiles;
-      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const int m0 = (t / tiles_n) * BMT + static_cast<int>(crank) * BM, n0 = (t % tiles_n) * BN;   // this CTA's 128 rows, all 256 columns
       const int acc = lw & 1;
       const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
       const int row = m0 + lrow;
@@ -351,7 +455,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         }
       };
       gate_fetch(chalf * 4);
+      // Bias of this warp's 128 columns: lane l keeps columns l, 32+l, 64+l, 96+l (four coalesced 128-byte loads issued BEFORE
+      // the accumulator wait); the epilogue broadcasts them with shuffles.  The former eight 16-byte loads per chunk sat on
+      // the L1TEX path, which the TMA fills and the tensor core's operand reads keep busy: their latency was the largest
+      // stall of the forward epilogue (ncu: 36 % of the stall samples on the bias add and its first consumer).
+      float bias_l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // Forward fast path (MODE == kModeFwd, full 128-column group, bf16 output only): the activation is applied AFTER the
+      // shared-memory transpose, on packed bf16 pairs (4 packed max / tanh per 16-byte unit instead of 32-64 scalar ops; exact
+      // for ReLU since max commutes with the rounding), and the pre-activation / output leave straight from those registers in
+      // the coalesced layout.  The bias is added in fp32 before the pack from a per-warp shared vector.  Measured on the trace build:
+      // every LSU-path instruction of the epilogue (loads, shuffles, shared accesses) runs ~10x slower than nominal while the
+      // tensor core and the TMA own the shared-memory pipe, so the epilogue, not the main loop, set the tile time.
+      const bool fwd_fast = MODE == kModeFwd && ep.out != nullptr && (ep.ldo & 7) == 0 && ep.out_f32 == nullptr && ep.out_t == nullptr &&
+                            (ep.preact == nullptr || (ep.ldp & 7) == 0) && n0 + chalf * 128 + 128 <= N;
+      float* bias_s = sm.bias[warp - 2];
+      if (fwd_fast && ep.bias != nullptr) {
+        // fp32 bias of this warp's 128 columns into its private shared vector: 4 coalesced loads + 4 conflict-free stores per
+        // lane, BEFORE the accumulator wait; the chunk loop reads it back with 16-byte broadcast loads (8 per chunk instead of
+        // 32 shuffles) and adds it in fp32 -- adding it after the bf16 pack would double-round (PPO actor loss moved by 1.4e-3)
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) bias_s[cc * 32 + lane] = __ldg(ep.bias + n0 + (chalf * 4 + cc) * 32 + lane);
+        __syncwarp();
+      } else if (kFwd && ep.bias != nullptr) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col = n0 + (chalf * 4 + cc) * 32 + lane;
+          if (col < N) bias_l[cc] = __ldg(ep.bias + col);
+        }
+      }
       g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
+      if (warp == 2 && lane == 0 && lw < 3) PULSE_TRACE(16 + 2 * lw);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
       const unsigned tmem_row = tmem_d + (static_cast<unsigned>(quarter * 32) << 16);
@@ -361,7 +495,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       tmem_ld32(tmem_row + static_cast<unsigned>(chalf * 4 * 32), r);
 #pragma unroll 1
       for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
+        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(22 + 4 * c);
         tmem_ld_wait();
+        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(23 + 4 * c);
         float v[32];
         if (MODE != kModeWgrad && ep.alpha != 1.0f) {
 #pragma unroll
@@ -376,22 +512,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           // all of this warp's TMEM reads for the item are done: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
-          if (lane == 0) g_mbar_arrive(&sm.tmem_empty[acc]);
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_leader(&sm.tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs' epilogues
+            else g_mbar_arrive(&sm.tmem_empty[acc]);
+          }
         }
         const int col0 = n0 + c * 32;
         const bool full = col0 + 32 <= N;
-        if (kFwd && ep.bias != nullptr) {
-          if (full) {
+        if (fwd_fast) {
+          if (ep.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + (c & 3) * 32);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));  // bias is 16-byte aligned (flat buffer slots)
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              const float4 b = b4[i >> 2];   // same address in every lane: one broadcast wavefront
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
           }
+          uint4* st = reinterpret_cast<uint4*>(red_stage);
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = 8 * q;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<unsigned*>(&h0);
+            u.y = *reinterpret_cast<unsigned*>(&h1);
+            u.z = *reinterpret_cast<unsigned*>(&h2);
+            u.w = *reinterpret_cast<unsigned*>(&h3);
+            st[lane * 4 + (q ^ sw)] = u;
+          }
+          __syncwarp();
+          const long long coff = col0 + (lane & 3) * 8;
+          const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.0f);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            uint4 u = st[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            const long long grow = m0 + quarter * 32 + rr;
+            if (grow < M) {
+              if (ep.preact != nullptr) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.preact) + grow * ep.ldp + coff) = u;
+              if (ep.act == PULSE_ACT_RELU) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], zero2);
+              } else if (ep.act == PULSE_ACT_SILU) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = silu_bf16x2(h[q]);
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldo + coff) = u;
+            }
+          }
+          __syncwarp();
+          continue;   // everything this mode can ask for is done for the chunk
+        }
+        if (kFwd && ep.bias != nullptr) {
+          const int cc = c & 3;
+          const float bl = cc == 0 ? bias_l[0] : (cc == 1 ? bias_l[1] : (cc == 2 ? bias_l[2] : bias_l[3]));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, bl, i);   // columns >= N carry 0 and are never stored
         }
         if (kFwd && ep.preact != nullptr) {  // SiLU pre-activations for the backward pass (measured: scalar stores here made the layer 10x slower)
           if (full && (ep.ldp & 7) == 0) {
@@ -487,6 +666,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) p[i] = v[i];
           }
         }
+        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(24 + 4 * c);
 #if PULSE_GEMM_VARIANT == 1   // experiment: no bf16 stores at all (keeps the math alive through an impossible condition)
         if (kBf16Out && ep.out != nullptr && row_ok && v[0] == 1.2345678e30f) {
           reinterpret_cast<__nv_bfloat16*>(ep.out)[row] = __float2bfloat16(v[1]);
@@ -526,6 +706,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           }
         }
 #endif
+        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(25 + 4 * c);
         if (kFwd && ep.out_t != nullptr && row_ok) {
           // transposed bf16 copy (not used by the MLP path any more; kept for API completeness): lanes hold consecutive
           // rows -> consecutive 2-byte addresses of out_t[col][row]
@@ -540,13 +721,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) atomicAdd(ep.sumsq, static_cast<double>(sq));
       }
+      if (warp == 2 && lane == 0 && lw < 3) PULSE_TRACE(17 + 2 * lw);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) PULSE_TRACE(10);
+  if (CTAS == 2) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the leader's MMAs can still touch the peer
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -578,13 +763,13 @@ bool make_map(CUtensorMap* map, const void* base, long long rows, long long cols
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool A_MN, bool B_MN, int MODE>
+template <bool A_MN, bool B_MN, int MODE, int CTAS>
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_gemm_epilogue_t& ep, int m, int n, int k, int splits,
                 int kb_per_split, cudaStream_t stream) {
   static bool attr_set = false;
-  const size_t smem = sizeof(GemmSmem) + 1024;  // slack so the kernel can align the ring to 1024 B
+  const size_t smem = sizeof(GemmSmemT<CTAS>) + 1024;  // slack so the kernel can align the ring to 1024 B
   if (!attr_set) {
-    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -593,8 +778,10 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
     PULSE_CUDA_OK(cudaGetDevice(&dev));
     PULSE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long total = static_cast<long long>((n + BN - 1) / BN) * ((m + BM - 1) / BM) * splits;
-  const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);  // persistent: one CTA per SM
+  // persistent: one CTA (or CTA pair) per SM (pair of SMs) loops over the work items
+  const long long total = static_cast<long long>((n + BN - 1) / BN) * ((m + BM * CTAS - 1) / (BM * CTAS)) * splits;
+  const long long slots = num_sms / CTAS;
+  const unsigned grid = static_cast<unsigned>((total < slots ? total : slots) * CTAS);
   static int use_pdl = -1;
   if (use_pdl < 0) {
     const char* e = getenv("PULSE_GEMM_PDL");
@@ -605,18 +792,35 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE>, map_a, map_b, ep, m, n, k, kb_per_split, splits));
+  cfg.numAttrs = na;
+  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE, CTAS>, map_a, map_b, ep, m, n, k, kb_per_split, splits));
   PULSE_LAUNCH_OK("gemm_bf16_kernel");
   return PULSE_OK;
 }
 
 }  // namespace
 }  // namespace pulse
+
+#if PULSE_GEMM_VARIANT == 3 || PULSE_GEMM_VARIANT == 1
+extern "C" int pulse_debug_gemm_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, pulse::g_gemm_trace, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int pulse_gemm_num_splits(int64_t k, int32_t split_k) {
   const int num_kb = static_cast<int>((k + 63) / 64);
@@ -643,9 +847,16 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   PULSE_REQUIRE(split_k == 1 || (ep->out_f32 && !ep->out && !ep->out_t && !ep->bias && ep->act == PULSE_ACT_NONE && !ep->gate && !ep->preact && !ep->colsum),
                 "pulse_gemm_bf16: split-K only supports plain fp32 outputs (slabs or atomic accumulation)");
   PULSE_REQUIRE(ep->gate == nullptr || ep->gate_mode == PULSE_ACT_RELU || ep->gate_mode == PULSE_ACT_SILU, "pulse_gemm_bf16: bad gate_mode");
+  // CTA pairs (256 x 256 tiles, cta_group::2) for everything large enough to fill them; PULSE_GEMM_PAIR=0 forces single CTAs
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* e = getenv("PULSE_GEMM_PAIR");
+    use_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool pair = use_pair && m > 128 && n > 128;
   CUtensorMap map_a, map_b;
   const bool ok_a = a_mn ? make_map(&map_a, a, k, m, lda, 64) : make_map(&map_a, a, m, k, lda, BM);
-  const bool ok_b = b_mn ? make_map(&map_b, b, k, n, ldb, 64) : make_map(&map_b, b, n, k, ldb, BN);
+  const bool ok_b = b_mn ? make_map(&map_b, b, k, n, ldb, 64) : make_map(&map_b, b, n, k, ldb, pair ? BN / 2 : BN);
   if (!ok_a || !ok_b) {
     set_error("pulse_gemm_bf16: cuTensorMapEncodeTiled failed (driver entry point missing or bad strides)");
     return PULSE_ERR_CUDA;
@@ -663,13 +874,22 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   else if (!want_fwd && !want_accum) mode = (ep->gate && ep->gate_mode != PULSE_ACT_RELU) ? kModeDgradVec : kModeDgrad;
   else if (!want_fwd && !want_dgrad && !ep->out) mode = kModeWgrad;
   const int mi = (int)m, ni = (int)n, ki = (int)k;
-#define PULSE_GEMM_DISPATCH(AM, BM_)                                                                               \
-  switch (mode) {                                                                                                   \
-    case kModeFwd: return launch_gemm<AM, BM_, kModeFwd>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);     \
-    case kModeDgrad: return launch_gemm<AM, BM_, kModeDgrad>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
-    case kModeWgrad: return launch_gemm<AM, BM_, kModeWgrad>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
-    case kModeDgradVec: return launch_gemm<AM, BM_, kModeDgradVec>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
-    default: return launch_gemm<AM, BM_, kModeGeneric>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);       \
+#define PULSE_GEMM_DISPATCH(AM, BM_)                                                                                          \
+  if (pair) {                                                                                                                 \
+    switch (mode) {                                                                                                           \
+      case kModeFwd: return launch_gemm<AM, BM_, kModeFwd, 2>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);           \
+      case kModeDgrad: return launch_gemm<AM, BM_, kModeDgrad, 2>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);       \
+      case kModeWgrad: return launch_gemm<AM, BM_, kModeWgrad, 2>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);       \
+      case kModeDgradVec: return launch_gemm<AM, BM_, kModeDgradVec, 2>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st); \
+      default: return launch_gemm<AM, BM_, kModeGeneric, 2>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);             \
+    }                                                                                                                         \
+  }                                                                                                                           \
+  switch (mode) {                                                                                                             \
+    case kModeFwd: return launch_gemm<AM, BM_, kModeFwd, 1>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);             \
+    case kModeDgrad: return launch_gemm<AM, BM_, kModeDgrad, 1>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);         \
+    case kModeWgrad: return launch_gemm<AM, BM_, kModeWgrad, 1>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);         \
+    case kModeDgradVec: return launch_gemm<AM, BM_, kModeDgradVec, 1>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);   \
+    default: return launch_gemm<AM, BM_, kModeGeneric, 1>(map_a, map_b, *ep, mi, ni, ki, splits, kb_per_split, st);               \
   }
   if (a_mn && b_mn) { PULSE_GEMM_DISPATCH(true, true) }
   if (a_mn) { PULSE_GEMM_DISPATCH(true, false) }
