@@ -264,9 +264,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL_DEBUG=VERSION prints a banner on STDOUT ahead of the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT when the communicator is created (NCCL_DEBUG >= VERSION in the environment);
+        # stdout must carry exactly one JSON line, so fd 1 points at stderr until the communicator exists.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n = a.envs // world
     lib = _lib.load()
     T = HORIZON
