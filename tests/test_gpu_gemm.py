@@ -141,13 +141,13 @@ def test_gemm_relu_gate_mask_and_sumsq(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 512, 128), (300, 1000, 72), (16384, 1024, 512), (5000, 768, 256), (16384, 512, 69)])
-def test_gemm_relu_dgrad_transposed_epilogue(M, N, K):
-    """ReLU dgrad without sumsq: gate + column sums applied after the shared-memory transpose, per-lane column partials carried
-    across the tiles of a CTA (several tiles per CTA, column-tile counts that do and do not divide the grid, ragged edges)."""
+def test_gemm_relu_dgrad_gate_and_column_sums(M, N, K):
+    """ReLU dgrad as the MLP backward issues it (gate + bias-gradient column sums + bf16 output, no sumsq): several tiles per
+    CTA, column-tile counts that do and do not divide the grid, ragged edges, the K = 69 actor-head shape."""
     from pulse_b200.dense import gemm
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(7 * M + N + K)
-    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    a = torch.randn(M, (K + 7) // 8 * 8, device=dev, generator=g).bfloat16()[:, :K]      # 16-byte row pitch (K = 69 -> ld 72), as the MLP buffers
     b = (torch.randn(K, N + 8, device=dev, generator=g) / K ** 0.5).bfloat16()[:, :N]
     gate = torch.randn(M, N + 8, device=dev, generator=g)
     gate[::3] = torch.relu(gate[::3])
@@ -158,6 +158,5 @@ def test_gemm_relu_dgrad_transposed_epilogue(M, N, K):
     gemm(a, b, b_mn=True, gate=gate, gate_mode="relu", out=out, colsum=colsum)
     ref = (a.float() @ b.float()) * (gate.float() > 0)
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
-    # the column sums are taken over the bf16-rounded outputs on the fast path, over fp32 values on the ragged path
     torch.testing.assert_close(colsum, ref.sum(0), atol=0.25 + 4e-3 * M ** 0.5, rtol=5e-3)
     torch.testing.assert_close(colsum, out.float().sum(0), atol=0.25 + 4e-3 * M ** 0.5, rtol=5e-3)
