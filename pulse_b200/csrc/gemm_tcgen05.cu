@@ -1,22 +1,23 @@
-// bf16 NT GEMM on the 5th-generation tensor cores (sm_100a): D[M,N] = epilogue(A[M,K] . B[N,K]^T).
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a): D[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k)).
 //
 // This one kernel carries every dense contraction of the policy / value / discriminator / VAE MLPs
 // (network_builder.py:105-124, amp_network_builder.py:58-249, amp_network_z_builder.py:341-467):
-//   forward   Y  = act(X W^T + b)            A = X  [M,K],  B = W   [N,K]
-//   dgrad     dX = (dY W) * act'(.)          A = dY [M,N],  B = W^T [K,N]   (transposed bf16 copy kept by Adam)
-//   wgrad     dW = dY^T X                    A = dY^T [N,M], B = X^T [K,M]  (transposed copies written by epilogues)
-// so both operands are always K-major and one TMA / UMMA configuration serves all three.
+//   forward   Y  = act(X W^T + b)            A = X  [M,K] K-major,   B = W  [N,K] K-major
+//   dgrad     dX = (dY W) * act'(.)          A = dY [M,N] K-major,   B = W  [N,K] read MN-major
+//   wgrad     dW = dY^T X                    A = dY [M,N] MN-major,  B = X  [M,K] MN-major   (reduction over the batch rows)
+// Operands are read as they sit in memory: the UMMA descriptors' major bits select K-major or MN-major, nothing is transposed.
 //
-// Structure (persistent: one CTA per SM loops over 128x256 output tiles x split-K slices; the fp32 accumulator
-// is double-buffered in TMEM so one item's epilogue overlaps the next item's main loop):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x64 bf16 boxes (128B swizzle) into a
-//               6-stage shared-memory ring that runs continuously across work items, completion on "full" mbarriers;
-//   warp 1      allocates 256 TMEM columns, then one elected lane issues tcgen05.mma (M128 N256 K16,
-//               fp32 accumulate in TMEM) four times per stage and tcgen05.commit's the stage back to the
-//               producer ("empty") and, after the last k-block, the accumulator to the epilogue;
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 accumulator columns each): tcgen05.ld 32 lanes x 32 columns at a time -> bias / activation / activation-
-//               derivative gating -> bf16 row-major, bf16 transposed and/or fp32 outputs.
-// Split-K (blockIdx.z) writes fp32 partial slabs for the weight gradients.
+// Structure (persistent: one CTA -- or one CTA PAIR, see GemmSmemT -- per SM loops over output tiles x split-K slices; the
+// fp32 accumulator is double-buffered in TMEM so one item's epilogue overlaps the next item's main loop):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads (128B swizzle) into a shared-memory ring that runs
+//               continuously across work items, completion on "full" mbarriers;
+//   warp 1      allocates the 512 TMEM columns, then one elected lane issues tcgen05.mma (M128/M256 x N256 x K16, fp32
+//               accumulate in TMEM) four times per stage and tcgen05.commit's the stage back to the producer ("empty") and,
+//               after the last k-block, the accumulator to the epilogue;
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 accumulator columns each): tcgen05.ld 32 lanes x 32 columns at
+//               a time -> bias / activation / activation-derivative gate / column sums -> bf16 and/or fp32 outputs, or
+//               coalesced fp32 atomics into the weight-gradient buffer (split-K).
+// What bounds it and why the epilogue looks the way it does: DESIGN.md section 3.3 (measured with the phase-trace build).
 #include <cuda.h>
 #include <stdlib.h>
 #include <cuda_bf16.h>
@@ -27,7 +28,7 @@ namespace pulse {
 namespace {
 
 #ifndef PULSE_GEMM_VARIANT
-#define PULSE_GEMM_VARIANT 0   // development experiments only (see tools/build_variant.sh); 0 = product
+#define PULSE_GEMM_VARIANT 0   // 0 = product; 3 = phase-trace build for tools/gemm_trace.py (tools/build_variant.sh 3)
 #endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns
@@ -235,7 +236,7 @@ __device__ __forceinline__ void store_block_bf16(uint4* st, const float (&v)[32]
   __syncwarp();
 }
 
-#if PULSE_GEMM_VARIANT == 3 || PULSE_GEMM_VARIANT == 1   // development: per-phase clock64 trace of CTA 0 (tools/gemm_trace.py)
+#if PULSE_GEMM_VARIANT == 3   // development: per-phase clock64 trace of CTA 0 (tools/gemm_trace.py)
 __device__ long long g_gemm_trace[32];
 #define PULSE_TRACE(slot)                                          \
   do {                                                             \
@@ -667,32 +668,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           }
         }
         if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(24 + 4 * c);
-#if PULSE_GEMM_VARIANT == 1   // experiment: no bf16 stores at all (keeps the math alive through an impossible condition)
-        if (kBf16Out && ep.out != nullptr && row_ok && v[0] == 1.2345678e30f) {
-          reinterpret_cast<__nv_bfloat16*>(ep.out)[row] = __float2bfloat16(v[1]);
-        }
-#elif PULSE_GEMM_VARIANT == 2   // experiment: the previous direct row-per-lane 16-byte stores
-        if (kBf16Out && ep.out != nullptr && row_ok) {
-          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
-          if (full && (ep.ldo & 7) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<unsigned*>(&h0);
-              u.y = *reinterpret_cast<unsigned*>(&h1);
-              u.z = *reinterpret_cast<unsigned*>(&h2);
-              u.w = *reinterpret_cast<unsigned*>(&h3);
-              *reinterpret_cast<uint4*>(p + i) = u;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
-          }
-        }
-#else
         if (kBf16Out && ep.out != nullptr) {
           if (full && (ep.ldo & 7) == 0) {
             store_block_bf16(reinterpret_cast<uint4*>(red_stage), v,
@@ -705,7 +680,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
               if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
           }
         }
-#endif
         if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(25 + 4 * c);
         if (kFwd && ep.out_t != nullptr && row_ok) {
           // transposed bf16 copy (not used by the MLP path any more; kept for API completeness): lanes hold consecutive
@@ -816,7 +790,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
 }  // namespace
 }  // namespace pulse
 
-#if PULSE_GEMM_VARIANT == 3 || PULSE_GEMM_VARIANT == 1
+#if PULSE_GEMM_VARIANT == 3
 extern "C" int pulse_debug_gemm_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, pulse::g_gemm_trace, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
 }

@@ -325,14 +325,17 @@ class TeacherPNN:
     def load_weights(self, pnn_sd: Dict[str, torch.Tensor], composer_sd: Dict[str, torch.Tensor], running_mean: torch.Tensor,
                      running_var: torch.Tensor) -> None:
         """pnn_sd: keys `actors.<k>.<2i>.weight|bias` (PNN.state_dict()); composer_sd: `<2i>.weight|bias`."""
+        def seq_keys(sd, num_layers):
+            """nn.Sequential numbering (Linear at 0, 2, 4, ...) -> the prefix / head naming MLP.load_state_dict takes"""
+            last = 2 * (num_layers - 1)
+            out = {f"m.{k}": v for k, v in sd.items() if not k.startswith(f"{last}.")}
+            out["h.weight"], out["h.bias"] = sd[f"{last}.weight"], sd[f"{last}.bias"]
+            return out
+
         for k, col in enumerate(self.cols):
-            n = 2 * (len(col.layers) - 1)
             sub = {kk[len(f"actors.{k}."):]: v for kk, v in pnn_sd.items() if kk.startswith(f"actors.{k}.")}
-            sub["_h.weight"], sub["_h.bias"] = sub[f"{n}.weight"], sub[f"{n}.bias"]
-            col.load_state_dict({f"m.{kk}": v for kk, v in sub.items()} | {"h.weight": sub["_h.weight"], "h.bias": sub["_h.bias"]}, "m", "h")
-        n = 2 * (len(self.composer.layers) - 1)
-        self.composer.load_state_dict({f"m.{kk}": v for kk, v in composer_sd.items()} | {"h.weight": composer_sd[f"{n}.weight"], "h.bias": composer_sd[f"{n}.bias"]},
-                                      "m", "h")
+            col.load_state_dict(seq_keys(sub, len(col.layers)), "m", "h")
+        self.composer.load_state_dict(seq_keys(composer_sd, len(self.composer.layers)), "m", "h")
         self.rms.running_mean.copy_(running_mean.to(self.device).double())
         self.rms.running_var.copy_(running_var.to(self.device).double())
         self.rms._refresh()

@@ -80,3 +80,34 @@ def test_product_does_not_import_oracle():
     for f in glob.glob(os.path.join(ROOT, "pulse_b200", "**", "*.py"), recursive=True):
         src = open(f).read()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f"{f} references oracle/"
+
+
+def test_new_entry_points_validate_arguments_without_gpu(lib):
+    """Rows a14 / a19 / a20: the VAE / teacher / reach / PD entry points reject bad arguments before any launch."""
+    from pulse_b200 import _lib
+    assert lib.pulse_vae_latent_loss(None, 8, None) == -1 and b"null" in lib.pulse_last_error()
+    a = _lib.VaeLatentArgs()
+    assert lib.pulse_vae_latent_loss(C.byref(a), 8, None) == -1
+    buf = (C.c_float * 64)()
+    ptr = C.cast(buf, C.c_void_p)
+    a = _lib.VaeLatentArgs(enc_head=ptr, ld_enc=8, prior_head=ptr, ld_prior=8, noise=ptr, ld_noise=4, d_enc_head=ptr, ld_de=8,
+                           d_prior_head=ptr, ld_dp=8, stats=ptr, latent=64, horizon=4)
+    assert lib.pulse_vae_latent_loss(C.byref(a), 8, None) == -1 and b"latent" in lib.pulse_last_error()
+    a.latent, a.progress, a.ar1_coef, a.horizon = 4, ptr, 0.005, 3
+    assert lib.pulse_vae_latent_loss(C.byref(a), 8, None) == -1 and b"horizon" in lib.pulse_last_error()
+    assert lib.pulse_vae_reparam(ptr, 8, None, 0, 4, 4, _lib.Z_SAMPLE, 1, -5.0, 2.0, ptr, 8, None, 0, None) == -1   # noise required
+    assert lib.pulse_vae_reparam(ptr, 8, ptr, 4, 4, 4, 7, 1, -5.0, 2.0, ptr, 8, None, 0, None) == -1 and b"mode" in lib.pulse_last_error()
+    assert lib.pulse_vae_action_loss(ptr, 200, ptr, 200, 4, 200, ptr, 200, 0, ptr, None) == -1               # > 128 actions
+    assert lib.pulse_copy_cols_bf16(ptr, 7, 4, 6, ptr, 8, None, 0, None) == -1 and b"even" in lib.pulse_last_error()
+    assert lib.pulse_normalize_cols(ptr, 8, 4, 8, ptr, None, 0.0, ptr, 8, 8, None) == -1                     # mean without rstd
+    assert lib.pulse_pnn_compose(ptr, 64, 4, ptr, 2, _lib.ACT_SILU, 4, 8, 3, ptr, 8, None) == -1             # ld_a < num_actions
+    assert lib.pulse_pd_targets(ptr, 4, ptr, ptr, None, 4, 8, ptr, 8, None) == -1                            # ld_a < dofs
+    assert lib.pulse_reach_step(None, 4, None) == -1
+    r = _lib.ReachStepArgs(body_state=ptr, body_env_stride=24 * 13, tar_pos=ptr, progress_buf=ptr, obs_buf=ptr, obs_stride=300, rew_buf=ptr,
+                           reset_buf=ptr, terminate_buf=ptr, reach_body_id=23)
+    assert lib.pulse_reach_step(C.byref(r), 4, None) == -1 and b"stride" in lib.pulse_last_error()
+    r.obs_stride, r.reach_body_id = 361, 30
+    assert lib.pulse_reach_step(C.byref(r), 4, None) == -1 and b"reach_body_id" in lib.pulse_last_error()
+    r.reach_body_id, r.enable_early_termination = 23, 1
+    assert lib.pulse_reach_step(C.byref(r), 4, None) == -1 and b"termination_heights" in lib.pulse_last_error()
+    assert lib.pulse_reach_update_task(ptr, ptr, ptr, ptr, None, 1.0, 0.5, 1.5, 4, None) == -1
