@@ -760,3 +760,102 @@ def humanoid_reset(progress_buf, contact_buf, contact_body_ids, rigid_body_pos, 
         terminated = torch.where(has_fallen, torch.ones_like(progress_buf), terminated)
     reset = torch.where(progress_buf >= max_episode_length - 1, torch.ones_like(progress_buf), terminated)
     return reset, terminated
+
+
+# ------------------------------------------------------------------------------------------------
+# MotionLib loader: what `load_motions` computes per clip before concatenating the tables
+# ------------------------------------------------------------------------------------------------
+def _pl_quat_mul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """poselib rotation3d.quat_mul (:15-27), the 16-product Hamilton form (xyzw)."""
+    x1, y1, z1, w1 = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    x2, y2, z2, w2 = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2
+    x = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2
+    y = w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2
+    z = w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2
+    return torch.stack([x, y, z, w], dim=-1)
+
+
+def _pl_quat_normalize(q: torch.Tensor) -> torch.Tensor:
+    """rotation3d.quat_normalize (:93-98): real part made non-negative (quat_pos, float mask), then unit length."""
+    z = (q[..., 3:] < 0).float()
+    q = (1 - 2 * z) * q
+    return q / q.norm(p=2, dim=-1).unsqueeze(-1).clamp(min=1e-9)
+
+
+def _pl_quat_mul_norm(a, b):
+    return _pl_quat_normalize(_pl_quat_mul(a, b))
+
+
+def _pl_quat_conj(q):
+    return torch.cat([-q[..., :3], q[..., 3:]], dim=-1)
+
+
+def _pl_quat_rotate(rot, vec):
+    """rotation3d.quat_rotate (:206-211): imaginary part of rot (x) (vec, 0) (x) conj(rot)."""
+    other = torch.cat([vec, torch.zeros_like(vec[..., :1])], dim=-1)
+    return _pl_quat_mul(_pl_quat_mul(rot, other), _pl_quat_conj(rot))[..., :3]
+
+
+def loader_heading(pose_aa, pose_quat_global, trans: torch.Tensor, heading: float):
+    """Heading randomisation of motion_lib_smpl.py:131-140 for a given angle (the reference's own scipy calls)."""
+    from scipy.spatial.transform import Rotation as sRot
+    import numpy as np
+    B, J, N = pose_quat_global.shape
+    rot = sRot.from_euler("xyz", np.array([0.0, 0.0, heading]))
+    pose_aa = torch.as_tensor(pose_aa).clone()
+    pose_aa[:, :3] = torch.tensor((rot * sRot.from_rotvec(pose_aa[:, :3])).as_rotvec())
+    pose_quat_global = (rot * sRot.from_quat(np.asarray(pose_quat_global).reshape(-1, 4))).as_quat().reshape(B, J, N)
+    trans = torch.matmul(trans, torch.from_numpy(rot.as_matrix().T))
+    return pose_aa, pose_quat_global, trans
+
+
+def loader_clip(pose_quat_global, trans: torch.Tensor, fps: float, parents, local_translation) -> Dict[str, torch.Tensor]:
+    """One clip through `SkeletonState.from_rotation_and_root_translation(is_local=False)` ->
+    `SkeletonMotion.from_skeleton_state` -> `compute_motion_dof_vels` (motion_lib_smpl.py:147-150; poselib skeleton3d.py:389-462,
+    :1000-1022, :1100-1118; motion_lib_base.py:47-70) in the reference's own mix of precisions: global rotations and angular
+    velocities float64, local rotations / positions / linear and dof velocities float32; `load_motions` casts all to fp32 (:297-304).
+
+    pose_quat_global [T, J, 4] xyzw (after the heading step), trans [T, 3] float64, parents [J], local_translation [J, 3]."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter1d
+    g = torch.as_tensor(pose_quat_global, dtype=torch.float64)
+    T, J = g.shape[0], g.shape[1]
+    parents = [int(p) for p in parents]
+    dt = 1 / fps
+    # local rotations from the given global ones (skeleton3d.py:444-462): computed in float64 but ASSIGNED into a float32
+    # identity tensor (quat_identity_like builds float32), so everything downstream of them is float32
+    lr = torch.zeros(T, J, 4, dtype=torch.float32)
+    lr[..., 3] = 1.0
+    for j, p in enumerate(parents):
+        lr[:, j] = (g[:, j] if p == -1 else _pl_quat_mul_norm(_pl_quat_conj(g[:, p]), g[:, j])).float()
+    # forward kinematics for the joint positions (:389-407), float32: the skeleton's offsets and the root translation sit in
+    # a float32 tensor (:478-481) next to the float32 local rotations
+    loc = torch.as_tensor(local_translation).float()
+    root = trans.float()
+    rot_fk, pos = [None] * J, [None] * J
+    for j, p in enumerate(parents):
+        if p == -1:
+            rot_fk[j], pos[j] = lr[:, j], root
+        else:
+            rot_fk[j] = _pl_quat_mul_norm(rot_fk[p], lr[:, j])
+            pos[j] = _pl_quat_rotate(rot_fk[p], loc[j].expand(T, 3)) + pos[p]
+    gts = torch.stack(pos, dim=1)
+    # velocities: central differences + sigma = 2 gaussian along time (:1100-1107), float32 in / float32 out
+    vel = np.gradient(gts.numpy(), axis=-3) / dt
+    gvs = torch.from_numpy(gaussian_filter1d(vel, 2, axis=-3, mode="nearest")).to(gts)
+    # angular velocities from consecutive global rotations (:1110-1118); the last frame gets the identity difference
+    dq = torch.zeros_like(g)
+    dq[..., 3] = 1.0
+    dq[:-1] = _pl_quat_mul_norm(g[1:], _pl_quat_conj(g[:-1]))
+    angle = (2 * dq[..., 3] ** 2 - 1).clamp(-1, 1).arccos()
+    axis = dq[..., :3] / dq[..., :3].norm(p=2, dim=-1, keepdim=True).clamp(min=1e-9)
+    gavs = torch.from_numpy(gaussian_filter1d((axis * angle.unsqueeze(-1) / dt).numpy(), 2, axis=-3, mode="nearest"))
+    # dof velocities from consecutive LOCAL rotations, joints 1.. (motion_lib_base.py:47-70); the last frame repeats
+    rows = []
+    for f in range(T - 1):
+        d_ang, d_axis = quat_to_angle_axis(quat_mul(quat_conj(lr[f]), lr[f + 1]))
+        rows.append((d_axis * d_ang.unsqueeze(-1) / dt)[1:])
+    rows.append(rows[-1])
+    dvs = torch.stack(rows, dim=0)
+    return {"gts": gts, "grs": g, "lrs": lr, "gvs": gvs, "gavs": gavs, "dvs": dvs}

@@ -212,3 +212,22 @@ def test_reach_full_step_pieces():
     close(po.self_obs_smpl_max(bs[..., 0:3], bs[..., 3:7], bs[..., 7:10], bs[..., 10:13]), g["reach_self_obs"])
     close(po.reach_obs(bs[:, 0, :], g["reach_tar_pos"]), g["reach_obs_full"])
     close(po.reach_reward(bs[:, 23, 0:3], g["reach_tar_pos"]), g["reach_reward_full"])
+
+
+def test_motionlib_loader_per_clip_pipeline():
+    """SURVEY 8(f)-1 groundwork: the oracle's restatement of the per-clip loader (heading randomisation, local rotations, forward
+    kinematics, gaussian-filtered velocities, dof velocities) reproduces the reference's tables EXACTLY, including its mix of
+    float64 / float32 stages (tests/golden/loader.npz, make_golden_loader.py; the same rows as motionlib.npz)."""
+    from tests.helpers import load_npz as _l
+    z = _l("loader.npz")
+    tables = _l("motionlib.npz")
+    nf = z["num_frames"].tolist()
+    start = 0
+    for i, n in enumerate(nf):
+        a, b = start, start + n
+        start = b
+        _, q, tr = po.loader_heading(z["in_pose_aa"][a:b], z["in_pose_quat_global"][a:b].numpy(), z["in_root_trans"][a:b], float(z["headings"][i]))
+        out = po.loader_clip(q, tr, float(z["fps"][i]), z["parents"].tolist(), z["local_translation"])
+        for k, v in out.items():
+            assert torch.equal(v.double(), z[k][a:b]), (i, k)
+            assert torch.equal(v.float(), tables[k][a:b]), (i, k)      # what load_motions() concatenates (fp32)
