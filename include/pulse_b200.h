@@ -441,6 +441,28 @@ typedef struct {
 #define PULSE_REACH_OBS 361
 int pulse_reach_step(const pulse_reach_step_args_t* args, int64_t num_envs, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MotionLib loader on the device (EXPERIMENTAL in round 1: compiled, not yet validated on a GPU, nothing on the
+ * hot path calls it).  Per clip: optional heading rotation, local rotations, forward kinematics, gaussian-filtered linear /
+ * angular velocities and dof velocities (motion_lib_smpl.py:101-174, poselib skeleton3d.py:389-462, :1100-1118,
+ * motion_lib_base.py:47-70) from the on-disk clip arrays concatenated over clips; fills the six fp32 tables
+ * pulse_motionlib_create packs.  All pointers are device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const double* pose_quat_global;  /* [F, 24, 4] xyzw, as stored by convert_amass_isaac.py */
+  const double* root_trans;        /* [F, 3] root_trans_offset */
+  const int32_t* frame_clip;       /* [F] clip index of every frame */
+  const int64_t* clip_start;       /* [M + 1] first frame of every clip, clip_start[M] = F */
+  const float* fps;                /* [M] */
+  const double* headings;          /* [M] heading angle drawn per clip (motion_lib_smpl.py:134-135), or NULL (im_eval / test) */
+  const int32_t* parents;          /* [24] skeleton parent indices (-1 = root) */
+  const float* local_translation;  /* [24, 3] skeleton offsets */
+  int64_t total_frames, num_clips;
+  float* gts; float* grs; float* lrs; float* gvs; float* gavs; float* dvs;   /* outputs, shapes as in pulse_motionlib_desc_t */
+  float* tmp_vel; float* tmp_ang;  /* workspaces [F, 24, 3] */
+} pulse_loader_args_t;
+int pulse_motionlib_load_clips(const pulse_loader_args_t* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,16 @@ class ReachStepArgs(C.Structure):
     ]
 
 
+class LoaderArgs(C.Structure):
+    _fields_ = [
+        ("pose_quat_global", C.c_void_p), ("root_trans", C.c_void_p), ("frame_clip", C.c_void_p), ("clip_start", C.c_void_p),
+        ("fps", C.c_void_p), ("headings", C.c_void_p), ("parents", C.c_void_p), ("local_translation", C.c_void_p),
+        ("total_frames", C.c_int64), ("num_clips", C.c_int64),
+        ("gts", C.c_void_p), ("grs", C.c_void_p), ("lrs", C.c_void_p), ("gvs", C.c_void_p), ("gavs", C.c_void_p), ("dvs", C.c_void_p),
+        ("tmp_vel", C.c_void_p), ("tmp_ang", C.c_void_p),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 Z_SAMPLE, Z_MEAN, Z_RESIDUAL = 0, 1, 2
 STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
@@ -172,6 +182,7 @@ SIGNATURES = {
     "pulse_reach_update_task": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                           C.c_int64, C.c_void_p]),
     "pulse_reach_step": (C.c_int, [C.POINTER(ReachStepArgs), C.c_int64, C.c_void_p]),
+    "pulse_motionlib_load_clips": (C.c_int, [C.POINTER(LoaderArgs), C.c_void_p]),
 }
 
 _lib = None

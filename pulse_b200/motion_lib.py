@@ -9,7 +9,8 @@ Same method names, argument meaning and return keys as the reference:
   sample_time / get_motion_length / num_motions / get_motion_num_steps
 The clip loader (load_motions: FK, heading randomisation, velocity filters) stays with the
 reference for now: build this object from the tables it produced with
-`MotionLibB200.from_reference(motion_lib)` or from raw tables with `from_tables(...)`.
+`MotionLibB200.from_reference(motion_lib)` or from raw tables with `from_tables(...)`.  `from_clips(...)` is the
+device-side loader: written in round 1, not yet validated on a GPU (its test is opt-in).
 """
 import ctypes as C
 from typing import Dict, Optional
@@ -83,6 +84,44 @@ class MotionLibB200:
                  dt=ref_lib._motion_dt, length_starts=ref_lib.length_starts, fps=ref_lib._motion_fps,
                  motion_bodies=ref_lib._motion_bodies, motion_limb_weights=ref_lib._motion_limb_weights)
         return cls(t, device=device)
+
+    @classmethod
+    def from_clips(cls, clips, parents, local_translation, device, headings=None):
+        """EXPERIMENTAL (compiled in round 1, not yet validated on a GPU): build the tables ON THE DEVICE from
+        clips in the on-disk schema (`pose_quat_global` f64 [T,24,4], `root_trans_offset` f64 [T,3], `pose_aa` [T,72], `fps`;
+        convert_amass_isaac.py:127-136) instead of MotionLibBase.load_motions' per-frame Python loops
+        (motion_lib_base.py:179-323).  `headings`: the per-clip heading angles the reference draws with
+        `np.pi * (2 * np.random.random() - 1)` (motion_lib_smpl.py:134-135), or None for the im_eval / test path."""
+        import numpy as np
+        lib = _lib.load()
+        dev = torch.device(device)
+        nf = [int(np.asarray(c["pose_quat_global"]).shape[0]) for c in clips]
+        M, F = len(clips), int(sum(nf))
+        f64 = lambda arrs: torch.from_numpy(np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in arrs], axis=0))).to(dev)
+        quat = f64([c["pose_quat_global"] for c in clips])
+        trans = f64([c["root_trans_offset"].numpy() if torch.is_tensor(c["root_trans_offset"]) else c["root_trans_offset"] for c in clips])
+        starts = torch.tensor(np.concatenate([[0], np.cumsum(nf)]), dtype=torch.int64, device=dev)
+        frame_clip = torch.repeat_interleave(torch.arange(M, dtype=torch.int32, device=dev), torch.tensor(nf, device=dev))
+        fps = torch.tensor([float(c.get("fps", 30)) for c in clips], dtype=torch.float32, device=dev)
+        hd = torch.as_tensor(np.asarray(headings, dtype=np.float64)).to(dev) if headings is not None else None
+        par = torch.as_tensor(np.asarray(parents, dtype=np.int32)).to(dev)
+        loc = torch.as_tensor(np.asarray(local_translation, dtype=np.float32)).to(dev).contiguous()
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        t = {"gts": z(F, 24, 3), "grs": z(F, 24, 4), "lrs": z(F, 24, 4), "gvs": z(F, 24, 3), "gavs": z(F, 24, 3), "dvs": z(F, 23, 3)}
+        tmp_v, tmp_w = z(F, 24, 3), z(F, 24, 3)
+        a = _lib.LoaderArgs(pose_quat_global=quat.data_ptr(), root_trans=trans.data_ptr(), frame_clip=frame_clip.data_ptr(),
+                            clip_start=starts.data_ptr(), fps=fps.data_ptr(), headings=_lib.ptr(hd), parents=par.data_ptr(),
+                            local_translation=loc.data_ptr(), total_frames=F, num_clips=M, gts=t["gts"].data_ptr(), grs=t["grs"].data_ptr(),
+                            lrs=t["lrs"].data_ptr(), gvs=t["gvs"].data_ptr(), gavs=t["gavs"].data_ptr(), dvs=t["dvs"].data_ptr(),
+                            tmp_vel=tmp_v.data_ptr(), tmp_ang=tmp_w.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(lib.pulse_motionlib_load_clips(C.byref(a), _lib.current_stream(dev)), "pulse_motionlib_load_clips")
+        nf_t = torch.tensor(nf, dtype=torch.int64, device=dev)
+        fps64 = [float(c.get("fps", 30)) for c in clips]
+        t.update(motion_aa=torch.from_numpy(np.concatenate([np.asarray(c["pose_aa"]).reshape(-1, 72) for c in clips])).float(),
+                 lengths=torch.tensor([1.0 / f * (n - 1) for f, n in zip(fps64, nf)], dtype=torch.float32),   # motion_lib_base.py:262-263
+                 num_frames=nf_t, dt=torch.tensor([1.0 / f for f in fps64], dtype=torch.float32), length_starts=starts[:-1].clone(), fps=fps)
+        return cls(t, device=dev)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
