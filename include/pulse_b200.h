@@ -442,8 +442,7 @@ typedef struct {
 int pulse_reach_step(const pulse_reach_step_args_t* args, int64_t num_envs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * MotionLib loader on the device (EXPERIMENTAL in round 1: compiled, not yet validated on a GPU, nothing on the
- * hot path calls it).  Per clip: optional heading rotation, local rotations, forward kinematics, gaussian-filtered linear /
+ * MotionLib loader on the device (parity green against the reference's tables, not yet timed).  Per clip: optional heading rotation, local rotations, forward kinematics, gaussian-filtered linear /
  * angular velocities and dof velocities (motion_lib_smpl.py:101-174, poselib skeleton3d.py:389-462, :1100-1118,
  * motion_lib_base.py:47-70) from the on-disk clip arrays concatenated over clips; fills the six fp32 tables
  * pulse_motionlib_create packs.  All pointers are device pointers.

@@ -8,8 +8,8 @@
 // Precision follows the reference stage by stage (oracle.pulse_oracle.loader_clip): heading rotation, local rotations and
 // the consecutive-frame rotation differences in float64; forward kinematics, linear and dof velocities in float32.
 //
-// STATUS: written and compiled in round 1 after the GPU budget was spent; not yet validated on a device.  Nothing on the
-// hot path calls it; its GPU test is opt-in (PULSE_EXPERIMENTAL_LOADER=1) until it has been.
+// STATUS (round 1): parity green against the reference's tables on a B200 (tests/test_gpu_loader.py); not yet timed, and the
+// bench still builds its synthetic tables directly.
 #include "pulse_common.cuh"
 #include "quat_math.cuh"
 

@@ -10,7 +10,7 @@ Same method names, argument meaning and return keys as the reference:
 The clip loader (load_motions: FK, heading randomisation, velocity filters) stays with the
 reference for now: build this object from the tables it produced with
 `MotionLibB200.from_reference(motion_lib)` or from raw tables with `from_tables(...)`.  `from_clips(...)` is the
-device-side loader: written in round 1, not yet validated on a GPU (its test is opt-in).
+device-side loader: parity green against the reference's tables (tests/test_gpu_loader.py).
 """
 import ctypes as C
 from typing import Dict, Optional
@@ -87,7 +87,7 @@ class MotionLibB200:
 
     @classmethod
     def from_clips(cls, clips, parents, local_translation, device, headings=None):
-        """EXPERIMENTAL (compiled in round 1, not yet validated on a GPU): build the tables ON THE DEVICE from
+        """Device-side loader: build the tables ON THE DEVICE from
         clips in the on-disk schema (`pose_quat_global` f64 [T,24,4], `root_trans_offset` f64 [T,3], `pose_aa` [T,72], `fps`;
         convert_amass_isaac.py:127-136) instead of MotionLibBase.load_motions' per-frame Python loops
         (motion_lib_base.py:179-323).  `headings`: the per-clip heading angles the reference draws with

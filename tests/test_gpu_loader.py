@@ -1,19 +1,14 @@
-"""EXPERIMENTAL device-side MotionLib loader against the reference-generated tables (tests/golden/loader.npz).
-
-Opt-in: the kernels were written after round 1's GPU budget was spent and have not run on a device yet; set
-PULSE_EXPERIMENTAL_LOADER=1 to run this test.  Tolerances: rotations / positions 1e-5; velocities 2e-4 (gaussian of finite
+"""Device-side MotionLib loader against the reference-generated tables (tests/golden/loader.npz): eight clips of
+2 to 150 frames with the reference's heading randomisation.  Tolerances: rotations / positions 1e-5; velocities 2e-4 (gaussian of finite
 differences); dof velocities 1e-3 -- the reference computes them from float32 local rotations with an acos near 1, so two
 float32 implementations differ by ~2e-4 on slow joints.
 """
-import os
-
 import pytest
 import torch
 
 from tests.helpers import load_npz
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PULSE_EXPERIMENTAL_LOADER") != "1",
-                                                  reason="device loader not yet validated on a GPU (opt in with PULSE_EXPERIMENTAL_LOADER=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_device_loader_matches_reference_tables():
