@@ -16,3 +16,10 @@ def im_eval_mean_reset(task) -> bool:
     if fl is None:
         return bool(getattr(task, "_pulse_im_eval", False)) and not bool(getattr(task, "strict_eval", False))
     return bool(getattr(fl, "im_eval", False)) and not bool(getattr(task, "strict_eval", False))
+
+
+def flags_test() -> bool:
+    """`flags.test` (evaluation run: the distillation teacher is skipped, humanoid_im_distill.py:151; the VAE uses z = mu,
+    amp_network_z_builder.py:94-95)."""
+    fl = reference_flags()
+    return bool(getattr(fl, "test", False)) if fl is not None else False
