@@ -65,6 +65,8 @@ class AMPAgentB200Mixin:
     def get_action_values(self, obs):
         pol = self._pulse_policy()
         res = pol.act(obs["obs"])
+        # PulseVAE.act (only_kin_loss): the env is stepped with `mus` (amp_agent.py:244-246, :367-369); no PPO statistics are used,
+        # so `actions` = `mus` and `neglogpacs` = 0 stand in for the sampled action and its likelihood
         out = {"actions": res.get("actions", res["mus"]), "mus": res["mus"], "sigmas": res["sigmas"], "values": res["values"],
                "neglogpacs": res.get("neglogpacs", torch.zeros(res["mus"].shape[0], device=res["mus"].device)), "rnn_states": None}
         return out
@@ -77,6 +79,9 @@ class AMPAgentB200Mixin:
 
     def _calc_amp_rewards(self, amp_obs):
         pol = self._pulse_policy()
+        if not hasattr(pol, "disc") or pol.disc is None:
+            # distillation (only_kin_loss): the AMP reward is logged but does not enter the kin loss; the reference path keeps it
+            return super()._calc_amp_rewards(amp_obs)
         return {"disc_rewards": pol.disc.rewards(amp_obs.reshape(-1, amp_obs.shape[-1])).reshape(*amp_obs.shape[:-1], 1)}
 
     def discount_values(self, mb_fdones, mb_values, mb_rewards, mb_next_values):
