@@ -266,448 +266,26 @@ __device__ __forceinline__ __nv_bfloat162 silu_bf16x2(__nv_bfloat162 z) {
 // caller can ask for; the host picks the smallest one that covers the request.
 enum : int { kModeGeneric = 0, kModeFwd = 1, kModeDgrad = 2, kModeWgrad = 3, kModeDgradVec = 4 };
 
-template <bool A_MN, bool B_MN, int MODE, int CTAS>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                      const __grid_constant__ CUtensorMap map_b,
-                                                                      const pulse_gemm_epilogue_t ep, int M, int N, int K,
-                                                                      int kb_per_split, int splits) {
-  constexpr bool kFwd = MODE == kModeGeneric || MODE == kModeFwd;      // bias, activation, pre-activation copy, transposed copy
-  constexpr bool kDgrad = MODE == kModeGeneric || MODE == kModeDgrad || MODE == kModeDgradVec;  // activation-derivative gate, column sums, sum of squares
-  constexpr bool kGateVec = MODE == kModeGeneric || MODE == kModeDgradVec;  // prefetched general gate (SiLU); its 32 registers would spill kModeDgrad
-  constexpr bool kAccum = MODE == kModeGeneric || MODE == kModeWgrad;  // fp32 atomic accumulation (weight gradients)
-  constexpr bool kBf16Out = MODE != kModeWgrad;
-  extern __shared__ unsigned char gsm_raw[];
-  // the 128-byte swizzle atoms need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
-  using Smem = GemmSmemT<CTAS>;
-  constexpr int kStagesG = Smem::kStages;
-  constexpr unsigned kStageBytesB = Smem::kStageBytesB;
-  constexpr int BMT = BM * CTAS;   // rows of the output tile one work item covers (the pair splits them 128 / 128)
-  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned crank = CTAS == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs, owns the full / tmem_empty barriers)
-  const int work0 = CTAS == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int work_stride = CTAS == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BMT - 1) / BMT;
-  const int tiles = tiles_m * tiles_n;
-  const int total = tiles * splits;
-  const int num_kb_total = (K + BK - 1) / BK;
-  if (threadIdx.x == 0) PULSE_TRACE(0);
+// ---- grouped launch: several problems of the same operand majors / epilogue mode in ONE persistent launch ------------------
+constexpr int kMaxGroup = 4;
+struct GemmProblem {
+  CUtensorMap map_a, map_b;
+  pulse_gemm_epilogue_t ep;
+  int M, N, K, kb_per_split;
+  int item_end;   // cumulative work items (tiles x split-K slices) up to and including this problem
+  int pad[3];
+};
+struct GemmGroup {
+  GemmProblem p[kMaxGroup];
+  int count, total_items;
+};
 
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kStagesG; ++s) {
-      g_mbar_init(&sm.full[s], 1);
-      g_mbar_init(&sm.empty[s], 1);
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      g_mbar_init(&sm.tmem_full[s], 1);
-      g_mbar_init(&sm.tmem_empty[s], kEpiWarps * CTAS);  // one arrival per epilogue warp (of both CTAs of a pair)
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
-  }
-  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp deallocates
-    if (CTAS == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&sm.tmem_base)), "n"(kTmemCols)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (CTAS == 2) cluster_sync_all();   // the peer's barriers are initialised and its TMEM allocated before any cross-CTA traffic
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const unsigned tmem_base = sm.tmem_base;
-  if (threadIdx.x == 0) PULSE_TRACE(1);
-  // Programmatic dependent launch: the NEXT kernel in the stream may be scheduled now -- its CTAs land on SMs as ours exit and
-  // run their own prologue (barrier init, TMEM allocation, tensor-map prefetch) under our tail -- while this kernel's first
-  // global-memory access waits (griddepcontrol.wait) until the PREVIOUS kernel has completed and flushed.  Roles that never
-  // touch global memory (the MMA issuer) do not wait.
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-
-  if (warp == 0) {
-    // ================================ TMA producer ======================================================
-    if (lane == 0) {
-      asm volatile("griddepcontrol.wait;\n" ::: "memory");
-      PULSE_TRACE(2);
-      int it = 0;  // running k-block counter across work items: stage = it % kStagesG
-      for (int w = work0; w < total; w += work_stride) {
-        const int split = w / tiles, t = w - split * tiles;
-        // this CTA's 128 rows of the tile and (pair mode) its half of the tile's 256 columns of B
-        const int m0 = (t / tiles_n) * BMT + static_cast<int>(crank) * BM, n0 = (t % tiles_n) * BN + static_cast<int>(crank) * (BN / 2) * (CTAS - 1);
-        const int kb0 = split * kb_per_split;
-        const int num_kb = min(kb_per_split, num_kb_total - kb0);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kStagesG;
-          g_mbar_wait(&sm.empty[s], ((it / kStagesG) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
-          // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
-          if (CTAS == 1 || crank == 0) g_mbar_expect_tx(&sm.full[s], CTAS * (kStageBytesA + kStageBytesB));
-          const int kk = (kb0 + kb) * BK;
-          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
-            if (CTAS == 2) tma_load_2d_pair(dst, map, c0, c1, &sm.full[s]);
-            else tma_load_2d(dst, map, c0, c1, &sm.full[s]);
-          };
-          if (A_MN) {  // box = [64 reduction rows][64 contiguous m]: two boxes cover the 128-wide tile
-            load(sm.a[s], &map_a, m0, kk);
-            load(sm.a[s] + 8192, &map_a, m0 + 64, kk);
-          } else {
-            load(sm.a[s], &map_a, kk, m0);
-          }
-          if (B_MN) {
-#pragma unroll
-            for (int h = 0; h < BN / CTAS / 64; ++h) load(sm.b[s] + h * 8192, &map_b, n0 + h * 64, kk);
-          } else {
-            load(sm.b[s], &map_b, kk, n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ========================================================
-    if (lane == 0 && crank == 0) {   // pair mode: only the leader issues (its MMAs read both CTAs' stages and write both TMEMs)
-      int it = 0, lw = 0;
-      for (int w = work0; w < total; w += work_stride, ++lw) {
-        const int split = w / tiles;
-        const int kb0 = split * kb_per_split;
-        const int num_kb = min(kb_per_split, num_kb_total - kb0);
-        const int acc = lw & 1;
-        g_mbar_wait(&sm.tmem_empty[acc], ((lw >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kStagesG;
-          g_mbar_wait(&sm.full[s], (it / kStagesG) & 1);
-          if (it == 0) PULSE_TRACE(3);
-          if (kb == num_kb - 1 && lw < 3) PULSE_TRACE(12 + lw);   // last k-block of the item has landed
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const unsigned a_addr = s_u32(sm.a[s]), b_addr = s_u32(sm.b[s]);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: 16 bf16 = 32 bytes inside the 128-byte swizzle atom; MN-major: 16 reduction rows = two 1024-byte groups
-            const unsigned long long da = A_MN ? umma_desc_mn(a_addr + k * 2048) : umma_desc(a_addr + k * 32);
-            const unsigned long long db = B_MN ? umma_desc_mn(b_addr + k * 2048) : umma_desc(b_addr + k * 32);
-            if (CTAS == 2) umma_bf16_pair(tmem_d, da, db, instr_desc_m<2 * BM>(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, da, db, instr_desc(A_MN, B_MN), (kb | k) != 0 ? 1u : 0u);
-          }
-          // implies tcgen05.fence::before_thread_sync; frees the stage (in both CTAs of a pair) when the MMAs retire
-          if (CTAS == 2) umma_commit_pair(&sm.empty[s]);
-          else umma_commit(&sm.empty[s]);
-        }
-        if (CTAS == 2) umma_commit_pair(&sm.tmem_full[acc]);  // accumulator complete (both CTAs' epilogues)
-        else umma_commit(&sm.tmem_full[acc]);
-        if (lw < 3) PULSE_TRACE(4 + lw);
-      }
-    }
-  } else {
-    // ================================ epilogue warps (TMEM lane quarter = warp % 4) =======================
-    const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
-    const int chalf = (warp - 2) >> 2;       // which 128-column half of the accumulator this warp drains
-    float* red_stage = sm.red[warp - 2];     // warp-private 16 x 33 fp32 tile for coalesced atomics
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    int lw = 0;
-    for (int w = work0; w < total; w += work_stride, ++lw) {
-      const int split = w / tiles, t = w - split * tiles;
-      const int m0 = (t / tiles_n) * BMT + static_cast<int>(crank) * BM, n0 = (t % tiles_n) * BN;   // this CTA's 128 rows, all 256 columns
-      const int acc = lw & 1;
-      const int lrow = quarter * 32 + lane;  // row inside the tile == TMEM lane
-      const int row = m0 + lrow;
-      const bool row_ok = row < M;
-      // ReLU-derivative gate: the saved activations do not depend on the accumulator, so this thread's 128 gate values
-      // (256 contiguous bytes of its row) are fetched BEFORE waiting for the MMAs -- their latency hides behind the main
-      // loop -- and folded to one bit each (4 registers) so nothing but the mask stays live across the wait.
-      const bool gate_fast = (MODE == kModeGeneric || MODE == kModeDgrad) && ep.gate != nullptr && ep.gate_mode == PULSE_ACT_RELU && (ep.ldg & 7) == 0 && n0 + chalf * 128 + 128 <= N;
-      unsigned gmask[4] = {0u, 0u, 0u, 0u};
-      if (gate_fast && row_ok) {
-        const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg +
-                                                        n0 + chalf * 128);
-        uint4 u[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) u[i] = __ldg(g + i);
-        // bf16 x > 0  <=>  sign clear and magnitude bits non-zero; two halfwords per word with integer ops:
-        // ((w & 0x7fff7fff) + 0x7fff7fff) has bit 15 / 31 set iff that halfword's magnitude is non-zero (no carry across).
-        // Mask layout per 32-column chunk: bit j = column 2j, bit 16+j = column 2j+1.
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const unsigned wds[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const unsigned pos = (((wds[q] & 0x7fff7fffu) + 0x7fff7fffu) & ~wds[q]) & 0x80008000u;
-            gmask[i >> 2] |= (pos >> 15) << ((i & 3) * 4 + q);
-          }
-        }
-      }
-      // General gate (SiLU pre-activations, or ReLU on a ragged column group): 64 bytes of this thread's row per 32-column
-      // chunk, fetched one chunk AHEAD -- the first before the accumulator wait, the next right after the current one is applied --
-      // so the load latency is never exposed (it was: 121 us on the 16384 x 1536 x 1024 SiLU dgrad).
-      const bool gate_vec = kGateVec && ep.gate != nullptr && !gate_fast && (ep.ldg & 7) == 0;
-      uint4 gq[4] = {};
-      auto gate_fetch = [&](int cc) {
-        const int c0 = n0 + cc * 32;
-        if (gate_vec && row_ok && c0 + 32 <= N) {
-          const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) gq[q] = __ldg(g + q);
-        }
-      };
-      gate_fetch(chalf * 4);
-      // Bias of this warp's 128 columns: lane l keeps columns l, 32+l, 64+l, 96+l (four coalesced 128-byte loads issued BEFORE
-      // the accumulator wait); the epilogue broadcasts them with shuffles.  The former eight 16-byte loads per chunk sat on
-      // the L1TEX path, which the TMA fills and the tensor core's operand reads keep busy: their latency was the largest
-      // stall of the forward epilogue (ncu: 36 % of the stall samples on the bias add and its first consumer).
-      float bias_l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      // Forward fast path (MODE == kModeFwd, full 128-column group, bf16 output only): the activation is applied AFTER the
-      // shared-memory transpose, on packed bf16 pairs (4 packed max / tanh per 16-byte unit instead of 32-64 scalar ops; exact
-      // for ReLU since max commutes with the rounding), and the pre-activation / output leave straight from those registers in
-      // the coalesced layout.  The bias is added in fp32 before the pack from a per-warp shared vector.  Measured on the trace build:
-      // every LSU-path instruction of the epilogue (loads, shuffles, shared accesses) runs ~10x slower than nominal while the
-      // tensor core and the TMA own the shared-memory pipe, so the epilogue, not the main loop, set the tile time.
-      const bool fwd_fast = MODE == kModeFwd && ep.out != nullptr && (ep.ldo & 7) == 0 && ep.out_f32 == nullptr && ep.out_t == nullptr &&
-                            (ep.preact == nullptr || (ep.ldp & 7) == 0) && n0 + chalf * 128 + 128 <= N;
-      float* bias_s = sm.bias[warp - 2];
-      if (fwd_fast && ep.bias != nullptr) {
-        // fp32 bias of this warp's 128 columns into its private shared vector: 4 coalesced loads + 4 conflict-free stores per
-        // lane, BEFORE the accumulator wait; the chunk loop reads it back with 16-byte broadcast loads (8 per chunk instead of
-        // 32 shuffles) and adds it in fp32 -- adding it after the bf16 pack would double-round (PPO actor loss moved by 1.4e-3)
-        __syncwarp();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) bias_s[cc * 32 + lane] = __ldg(ep.bias + n0 + (chalf * 4 + cc) * 32 + lane);
-        __syncwarp();
-      } else if (kFwd && ep.bias != nullptr) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col = n0 + (chalf * 4 + cc) * 32 + lane;
-          if (col < N) bias_l[cc] = __ldg(ep.bias + col);
-        }
-      }
-      g_mbar_wait(&sm.tmem_full[acc], (lw >> 1) & 1);
-      if (warp == 2 && lane == 0 && lw < 3) PULSE_TRACE(16 + 2 * lw);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const unsigned tmem_d = tmem_base + static_cast<unsigned>(acc * BN);
-      const unsigned tmem_row = tmem_d + (static_cast<unsigned>(quarter * 32) << 16);
-      float* outf = ep.out_f32 != nullptr ? ep.out_f32 + static_cast<long long>(ep.accumulate ? 0 : split) * ep.split_stride : nullptr;
-      unsigned r[32];
-      float sq = 0.0f;  // this thread's share of sum(v^2) for the item (ep.sumsq)
-      tmem_ld32(tmem_row + static_cast<unsigned>(chalf * 4 * 32), r);
-#pragma unroll 1
-      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
-        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(22 + 4 * c);
-        tmem_ld_wait();
-        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(23 + 4 * c);
-        float v[32];
-        if (MODE != kModeWgrad && ep.alpha != 1.0f) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        }
-        if (c != chalf * 4 + 3) {
-          tmem_ld32(tmem_row + static_cast<unsigned>((c + 1) * 32), r);  // next 32 columns stream in under this chunk's math + stores
-        } else {
-          // all of this warp's TMEM reads for the item are done: hand the accumulator back before the stores
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (CTAS == 2) mbar_arrive_leader(&sm.tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs' epilogues
-            else g_mbar_arrive(&sm.tmem_empty[acc]);
-          }
-        }
-        const int col0 = n0 + c * 32;
-        const bool full = col0 + 32 <= N;
-        if (fwd_fast) {
-          if (ep.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + (c & 3) * 32);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = b4[i >> 2];   // same address in every lane: one broadcast wavefront
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
-          }
-          uint4* st = reinterpret_cast<uint4*>(red_stage);
-          const int sw = (lane >> 1) & 3;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int i = 8 * q;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<unsigned*>(&h0);
-            u.y = *reinterpret_cast<unsigned*>(&h1);
-            u.z = *reinterpret_cast<unsigned*>(&h2);
-            u.w = *reinterpret_cast<unsigned*>(&h3);
-            st[lane * 4 + (q ^ sw)] = u;
-          }
-          __syncwarp();
-          const long long coff = col0 + (lane & 3) * 8;
-          const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.0f);
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2);
-            uint4 u = st[rr * 4 + ((lane & 3) ^ ((rr >> 1) & 3))];
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            const long long grow = m0 + quarter * 32 + rr;
-            if (grow < M) {
-              if (ep.preact != nullptr) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.preact) + grow * ep.ldp + coff) = u;
-              if (ep.act == PULSE_ACT_RELU) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], zero2);
-              } else if (ep.act == PULSE_ACT_SILU) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = silu_bf16x2(h[q]);
-              }
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + grow * ep.ldo + coff) = u;
-            }
-          }
-          __syncwarp();
-          continue;   // everything this mode can ask for is done for the chunk
-        }
-        if (kFwd && ep.bias != nullptr) {
-          const int cc = c & 3;
-          const float bl = cc == 0 ? bias_l[0] : (cc == 1 ? bias_l[1] : (cc == 2 ? bias_l[2] : bias_l[3]));
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, bl, i);   // columns >= N carry 0 and are never stored
-        }
-        if (kFwd && ep.preact != nullptr) {  // SiLU pre-activations for the backward pass (measured: scalar stores here made the layer 10x slower)
-          if (full && (ep.ldp & 7) == 0) {
-            store_block_bf16(reinterpret_cast<uint4*>(red_stage), v,
-                             reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(m0 + quarter * 32) * ep.ldp + col0, ep.ldp,
-                             M - (m0 + quarter * 32), lane);
-          } else if (row_ok) {
-            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.preact) + static_cast<long long>(row) * ep.ldp + col0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
-          }
-        }
-        if (kFwd && ep.act != PULSE_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ep.act);
-        }
-        if (gate_fast) {
-          const int cc = c & 3;
-          const unsigned mk = cc == 0 ? gmask[0] : (cc == 1 ? gmask[1] : (cc == 2 ? gmask[2] : gmask[3]));
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((mk >> ((i >> 1) + 16 * (i & 1))) & 1u) ? v[i] : 0.0f;
-        } else if (kDgrad && ep.gate != nullptr && row_ok) {
-          const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.gate) + static_cast<long long>(row) * ep.ldg + col0;
-          if (full && (gate_vec || (ep.ldg & 7) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 u = gate_vec ? gq[i >> 3] : __ldg(reinterpret_cast<const uint4*>(g + i));
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(h[q]);
-                v[i + 2 * q] *= act_grad(f.x, ep.gate_mode);
-                v[i + 2 * q + 1] *= act_grad(f.y, ep.gate_mode);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) v[i] *= act_grad(__bfloat162float(g[i]), ep.gate_mode);
-          }
-        }
-        if (gate_vec && c != chalf * 4 + 3) gate_fetch(c + 1);  // consumed one chunk later: covered by the column sums + stores below
-        if (kDgrad && ep.sumsq != nullptr && row_ok) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full || col0 + i < N) sq = fmaf(v[i], v[i], sq);
-        }
-        if (kDgrad && ep.colsum != nullptr) {
-          // column sums of this warp's 32x32 block by a shuffle reduce-scatter (31 shuffles): lane l ends up with
-          // the sum over the warp's 32 rows of column l (bias gradients without a second pass over dY)
-          float wv[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) wv[i] = row_ok ? v[i] : 0.0f;
-#pragma unroll
-          for (int half = 16; half >= 1; half >>= 1) {
-            const bool upper = (lane & half) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float mine = upper ? wv[i + half] : wv[i];
-              const float send = upper ? wv[i] : wv[i + half];
-              wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, half);
-            }
-          }
-          if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, wv[0]);
-        }
-        if (kAccum && outf != nullptr && ep.accumulate) {
-          // fp32 atomics, coalesced: transpose the warp's 32x32 block through its private shared tile so that one
-          // warp instruction adds 32 consecutive columns of ONE row (128 contiguous bytes)
-#pragma unroll
-          for (int hr = 0; hr < 2; ++hr) {  // 16 rows at a time through the 16 x 33 tile
-            if ((lane >> 4) == hr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) red_stage[(lane & 15) * 33 + i] = v[i];
-            }
-            __syncwarp();
-            const int rbase = m0 + quarter * 32 + hr * 16;
-            const int rows_here = min(16, M - rbase);
-            if (col0 + lane < N) {
-              float* p = outf + static_cast<long long>(rbase) * ep.ldf + col0 + lane;
-              for (int rr = 0; rr < rows_here; ++rr) atomicAdd(p + static_cast<long long>(rr) * ep.ldf, red_stage[rr * 33 + lane]);
-            }
-            __syncwarp();
-          }
-        } else if (outf != nullptr && row_ok) {
-          float* p = outf + static_cast<long long>(row) * ep.ldf + col0;
-          if (full && (ep.ldf & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) p[i] = v[i];
-          }
-        }
-        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(24 + 4 * c);
-        if (kBf16Out && ep.out != nullptr) {
-          if (full && (ep.ldo & 7) == 0) {
-            store_block_bf16(reinterpret_cast<uint4*>(red_stage), v,
-                             reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(m0 + quarter * 32) * ep.ldo + col0, ep.ldo,
-                             M - (m0 + quarter * 32), lane);
-          } else if (row_ok) {
-            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) p[i] = __float2bfloat16(v[i]);
-          }
-        }
-        if (warp == 2 && lane == 0 && lw == 1 && c < 2) PULSE_TRACE(25 + 4 * c);
-        if (kFwd && ep.out_t != nullptr && row_ok) {
-          // transposed bf16 copy (not used by the MLP path any more; kept for API completeness): lanes hold consecutive
-          // rows -> consecutive 2-byte addresses of out_t[col][row]
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N)
-              reinterpret_cast<__nv_bfloat16*>(ep.out_t)[static_cast<long long>(col0 + i) * ep.ldot + row] = __float2bfloat16(v[i]);
-        }
-      }
-      if (kDgrad && ep.sumsq != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0) atomicAdd(ep.sumsq, static_cast<double>(sq));
-      }
-      if (warp == 2 && lane == 0 && lw < 3) PULSE_TRACE(17 + 2 * lw);
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (threadIdx.x == 0) PULSE_TRACE(10);
-  if (CTAS == 2) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the leader's MMAs can still touch the peer
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-  }
-}
+#define PULSE_GEMM_GROUPED 0
+#include "gemm_kernel.inc"
+#undef PULSE_GEMM_GROUPED
+#define PULSE_GEMM_GROUPED 1
+#include "gemm_kernel.inc"
+#undef PULSE_GEMM_GROUPED
 
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
