@@ -250,6 +250,18 @@ int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int6
                     const pulse_gemm_epilogue_t* ep, int32_t split_k, uint32_t flags, void* stream);
 int pulse_gemm_num_splits(int64_t k, int32_t split_k);
 
+/* Several GEMMs of the same kind in ONE persistent launch (work items of all problems concatenated): forward groups
+ * (flags 0), ReLU-dgrad groups (PULSE_GEMM_B_MN) or weight-gradient groups (PULSE_GEMM_A_MN | PULSE_GEMM_B_MN, fp32 atomic
+ * accumulation), at most 4 problems.  EXPERIMENTAL in round 1 (compiled, not yet validated on a device). */
+typedef struct {
+  const void* a; int64_t lda;
+  const void* b; int64_t ldb;
+  int64_t m, n, k;
+  pulse_gemm_epilogue_t ep;
+  int32_t split_k, reserved;
+} pulse_gemm_problem_t;
+int pulse_gemm_bf16_grouped(const pulse_gemm_problem_t* problems, int32_t count, uint32_t flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / reduction kernels around the GEMMs.
  * ---------------------------------------------------------------------------------------------- */

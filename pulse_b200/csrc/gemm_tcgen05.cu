@@ -20,6 +20,7 @@
 // What bounds it and why the epilogue looks the way it does: DESIGN.md section 3.3 (measured with the phase-trace build).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "pulse_common.cuh"
@@ -365,6 +366,56 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
   return PULSE_OK;
 }
 
+template <bool A_MN, bool B_MN, int MODE, int CTAS>
+int launch_gemm_grouped(const GemmGroup& grp, cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(GemmSmemT<CTAS>) + 1024;
+  if (!attr_set) {
+    PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_grouped_kernel<A_MN, B_MN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PULSE_CUDA_OK(cudaGetDevice(&dev));
+    PULSE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long slots = num_sms / CTAS;
+  const unsigned grid = static_cast<unsigned>((grp.total_items < slots ? grp.total_items : slots) * CTAS);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_grouped_kernel<A_MN, B_MN, MODE, CTAS>, grp));
+  PULSE_LAUNCH_OK("gemm_bf16_grouped_kernel");
+  return PULSE_OK;
+}
+
+int epilogue_mode(const pulse_gemm_epilogue_t* ep) {
+  const bool want_fwd = ep->bias || ep->act != PULSE_ACT_NONE || ep->preact || ep->out_t;
+  const bool want_dgrad = ep->gate || ep->colsum || ep->sumsq;
+  const bool want_accum = ep->accumulate != 0;
+  if (!want_dgrad && !want_accum) return kModeFwd;
+  if (!want_fwd && !want_accum) return (ep->gate && ep->gate_mode != PULSE_ACT_RELU) ? kModeDgradVec : kModeDgrad;
+  if (!want_fwd && !want_dgrad && !ep->out) return kModeWgrad;
+  return kModeGeneric;
+}
+
 }  // namespace
 }  // namespace pulse
 
@@ -453,4 +504,72 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
 extern "C" int pulse_gemm_bf16_nt(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                                   const pulse_gemm_epilogue_t* ep, int32_t split_k, void* stream) {
   return pulse_gemm_bf16(a, lda, b, ldb, m, n, k, ep, split_k, 0u, stream);
+}
+
+// Several GEMMs of the same kind (operand majors `flags`, same epilogue specialisation) in ONE persistent launch: the work items
+// of all problems are concatenated, so the tail of one problem fills with tiles of the next and the ~8 us of per-launch
+// prologue / drain is paid once (actor + critic layers of a PPO minibatch, or the weight gradients of several layers).
+// EXPERIMENTAL in round 1: compiled, not yet run on a device; nothing calls it unless PULSE_GROUPED=1 (pulse_b200/dense.py).
+extern "C" int pulse_gemm_bf16_grouped(const pulse_gemm_problem_t* problems, int32_t count, uint32_t flags, void* stream) {
+  using namespace pulse;
+  PULSE_REQUIRE(problems != nullptr && count >= 1 && count <= kMaxGroup, "pulse_gemm_bf16_grouped: 1..%d problems", kMaxGroup);
+  PULSE_REQUIRE((flags & ~3u) == 0, "pulse_gemm_bf16_grouped: bad flags");
+  const bool a_mn = flags & PULSE_GEMM_A_MN, b_mn = flags & PULSE_GEMM_B_MN;
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* e = getenv("PULSE_GEMM_PAIR");
+    use_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  bool pair = use_pair != 0;
+  int mode = -1;
+  for (int i = 0; i < count; ++i) {
+    const pulse_gemm_problem_t& q = problems[i];
+    PULSE_REQUIRE(q.a && q.b, "pulse_gemm_bf16_grouped: null operand in problem %d", i);
+    PULSE_REQUIRE(q.m > 0 && q.n > 0 && q.k > 0 && q.m < (1ll << 31) && q.n < (1ll << 31) && q.k < (1ll << 31), "pulse_gemm_bf16_grouped: bad shape in problem %d", i);
+    PULSE_REQUIRE(q.lda >= (a_mn ? q.m : q.k) && q.ldb >= (b_mn ? q.n : q.k) && (q.lda % 8) == 0 && (q.ldb % 8) == 0,
+                  "pulse_gemm_bf16_grouped: leading dimensions of problem %d must cover the contiguous extent and be multiples of 8", i);
+    PULSE_REQUIRE(aligned16(q.a) && aligned16(q.b), "pulse_gemm_bf16_grouped: operands of problem %d must be 16-byte aligned", i);
+    PULSE_REQUIRE(q.ep.out || q.ep.out_t || q.ep.out_f32, "pulse_gemm_bf16_grouped: problem %d has no output", i);
+    PULSE_REQUIRE(q.split_k >= 1, "pulse_gemm_bf16_grouped: split_k must be >= 1");
+    PULSE_REQUIRE(q.split_k == 1 || (q.ep.out_f32 && q.ep.accumulate && !q.ep.out && !q.ep.out_t && !q.ep.bias && q.ep.act == PULSE_ACT_NONE && !q.ep.gate &&
+                                     !q.ep.preact && !q.ep.colsum),
+                  "pulse_gemm_bf16_grouped: split-K only with fp32 atomic accumulation");
+    const int mq = epilogue_mode(&q.ep);
+    PULSE_REQUIRE(mode < 0 || mq == mode, "pulse_gemm_bf16_grouped: problem %d needs a different epilogue specialisation than problem 0", i);
+    mode = mq;
+    pair = pair && q.m > 128 && q.n > 128;
+  }
+  PULSE_REQUIRE(mode == kModeFwd || mode == kModeDgrad || mode == kModeWgrad, "pulse_gemm_bf16_grouped: forward, ReLU-dgrad and wgrad groups only");
+  PULSE_REQUIRE((mode == kModeFwd && !a_mn && !b_mn) || (mode == kModeDgrad && !a_mn && b_mn) || (mode == kModeWgrad && a_mn && b_mn),
+                "pulse_gemm_bf16_grouped: operand majors do not match the group kind (fwd K/K, dgrad K/MN, wgrad MN/MN)");
+  GemmGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  grp.count = count;
+  long long items = 0;
+  for (int i = 0; i < count; ++i) {
+    const pulse_gemm_problem_t& q = problems[i];
+    GemmProblem& g = grp.p[i];
+    const bool ok_a = a_mn ? make_map(&g.map_a, q.a, q.k, q.m, q.lda, 64) : make_map(&g.map_a, q.a, q.m, q.k, q.lda, BM);
+    const bool ok_b = b_mn ? make_map(&g.map_b, q.b, q.k, q.n, q.ldb, 64) : make_map(&g.map_b, q.b, q.n, q.k, q.ldb, pair ? BN / 2 : BN);
+    if (!ok_a || !ok_b) {
+      set_error("pulse_gemm_bf16_grouped: cuTensorMapEncodeTiled failed for problem %d", i);
+      return PULSE_ERR_CUDA;
+    }
+    g.ep = q.ep;
+    g.M = static_cast<int>(q.m);
+    g.N = static_cast<int>(q.n);
+    g.K = static_cast<int>(q.k);
+    const int num_kb = static_cast<int>((q.k + BK - 1) / BK);
+    const int splits = pulse_gemm_num_splits(q.k, q.split_k);
+    g.kb_per_split = (num_kb + splits - 1) / splits;
+    const int bmt = pair ? 2 * BM : BM;
+    items += static_cast<long long>((q.n + BN - 1) / BN) * ((q.m + bmt - 1) / bmt) * splits;
+    PULSE_REQUIRE(items < (1ll << 30), "pulse_gemm_bf16_grouped: too many work items");
+    g.item_end = static_cast<int>(items);
+  }
+  grp.total_items = static_cast<int>(items);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == kModeFwd) return pair ? launch_gemm_grouped<false, false, kModeFwd, 2>(grp, st) : launch_gemm_grouped<false, false, kModeFwd, 1>(grp, st);
+  if (mode == kModeDgrad) return pair ? launch_gemm_grouped<false, true, kModeDgrad, 2>(grp, st) : launch_gemm_grouped<false, true, kModeDgrad, 1>(grp, st);
+  return pair ? launch_gemm_grouped<true, true, kModeWgrad, 2>(grp, st) : launch_gemm_grouped<true, true, kModeWgrad, 1>(grp, st);
 }
