@@ -328,3 +328,88 @@ def normalize_to_bf16(x: torch.Tensor, mean: Optional[torch.Tensor], rstd: Optio
         _lib.check(lib.pulse_normalize_to_bf16(x.data_ptr(), x.stride(0), rows, cols, _lib.ptr(mean), _lib.ptr(rstd), out.data_ptr(), out.stride(0),
                                                _lib.ptr(out_t), out_t.stride(0) if out_t is not None else 0, _lib.current_stream(x.device)),
                    "pulse_normalize_to_bf16")
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Lock-step execution of several MLPs of the same depth through GROUPED launches (pulse_gemm_bf16_grouped): the hidden layers of
+# all nets in one persistent launch per layer, likewise their weight-gradient and their dgrad GEMMs.  EXPERIMENTAL in round 1
+# (compiled, not yet run on a device); used only when PULSE_GROUPED=1 (dense.grouped_enabled()).  MLP.forward / MLP.backward
+# above remain the validated path and are not touched by this code.
+# ---------------------------------------------------------------------------------------------------------------------------
+def forward_lockstep(mlps: Sequence["MLP"], xs: Sequence[torch.Tensor], train: bool = False) -> List[torch.Tensor]:
+    from .dense import gemm_grouped
+    depth = len(mlps[0].layers)
+    if any(len(m.layers) != depth for m in mlps) or any(x.shape[0] != xs[0].shape[0] for x in xs):
+        raise _lib.PulseError("forward_lockstep needs nets of the same depth on batches of the same size")
+    M = xs[0].shape[0]
+    wss = [m._workspace(M, train) for m in mlps]
+    hs = list(xs)
+    for i in range(depth - 1):
+        probs = []
+        for m, ws, h in zip(mlps, wss, hs):
+            l = m.layers[i]
+            probs.append((h, l.w_bf16, dict(bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)))
+        gemm_grouped(probs)
+        hs = [ws["act"][i] for ws in wss]
+    outs = []
+    for m, ws, h, x in zip(mlps, wss, hs, xs):       # heads: the single-net code of MLP.forward (GEMV kernel or fp32-output GEMM)
+        i = depth - 1
+        l = m.layers[i]
+        if m._head1(i):
+            with torch.cuda.device(m.flat.device):
+                _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), l.bias.data_ptr(),
+                                                           ws["out"].data_ptr(), ws["out"].stride(0), _lib.current_stream(m.flat.device)),
+                           "pulse_head1_forward")
+        else:
+            gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
+        if train:
+            m._ws[(M, True)]["x"] = x
+        outs.append(ws["out"])
+    return outs
+
+
+def backward_lockstep(mlps: Sequence["MLP"], douts: Sequence[torch.Tensor], M: int) -> None:
+    """ADDS the weight / bias gradients of every net into its flat gradient buffer (see MLP.backward)."""
+    from .dense import gemm_grouped
+    lib = _lib.load()
+    depth = len(mlps[0].layers)
+    wss = [m._ws[(M, True)] for m in mlps]
+    dys, tops = [], []
+    for m, ws, dy in zip(mlps, wss, douts):           # heads first, per net (MLP.backward's head handling)
+        dev = m.flat.device
+        head, top = m.layers[-1], depth - 1
+        if m._head1(top):
+            prev, h, dh = m.layers[top - 1], ws["act"][top - 1], ws["dact"][top - 1]
+            with torch.cuda.device(dev):
+                _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), M, head.Kp, dy.data_ptr(), dy.stride(0), head.w_bf16.data_ptr(),
+                                                    dh.data_ptr(), dh.stride(0), head.weight_grad.data_ptr(), head.bias_grad.data_ptr(),
+                                                    m.flat.view_padded(prev.b_idx, "grads", prev.Np).data_ptr(), _lib.current_stream(dev)),
+                           "pulse_head1_backward")
+            dy, top = dh, top - 1
+        else:
+            with torch.cuda.device(dev):
+                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
+                           "pulse_column_sum_bf16")
+        dys.append(dy)
+        tops.append(top)
+    for i in reversed(range(depth)):
+        live = [j for j in range(len(mlps)) if tops[j] >= i]     # a fused single-output head has consumed the top layer of its net
+        if not live:
+            continue
+        wg, dg = [], []
+        for j in live:
+            m, ws, dy = mlps[j], wss[j], dys[j]
+            l = m.layers[i]
+            x_in = ws["x"] if i == 0 else ws["act"][i - 1]
+            wg.append((dy[:, :l.N], x_in[:, :l.Kp], dict(a_mn=True, b_mn=True, out_f32=l.weight_grad, accumulate=True, split_k=ws["split"][i])))
+            if i > 0:
+                prev = m.layers[i - 1]
+                if prev.act != "relu":
+                    raise _lib.PulseError("backward_lockstep groups ReLU nets only (the grouped dgrad kernel is the ReLU-gate specialisation)")
+                dg.append((dy[:, :l.N], l.w_bf16, dict(b_mn=True, gate=ws["act"][i - 1], gate_mode="relu", out=ws["dact"][i - 1],
+                                                        colsum=m.flat.view_padded(prev.b_idx, "grads", prev.Np))))
+        gemm_grouped(wg)
+        if dg:
+            gemm_grouped(dg)
+            for j in live:
+                dys[j] = wss[j]["dact"][i - 1]

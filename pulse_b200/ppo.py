@@ -175,11 +175,17 @@ class PPOPolicy:
             self.obs_rms.normalize_update(obs, b["x"])       # (running_mean_std.py:91-107, train mode), one pass over obs
         else:
             self.obs_rms.normalize_into(obs, b["x"])
-        s_critic.wait_stream(main)
-        with torch.cuda.stream(s_critic):
-            value = self.critic.forward(b["x"], train=True)
-        mu = self.actor.forward(b["x"], train=True)
-        main.wait_stream(s_critic)
+        from .dense import grouped_enabled
+        grouped = grouped_enabled()    # PULSE_GROUPED=1: actor + critic in lock step through grouped launches (experimental, default off)
+        if grouped:
+            from .nets import backward_lockstep, forward_lockstep
+            mu, value = forward_lockstep((self.actor, self.critic), (b["x"], b["x"]), train=True)
+        else:
+            s_critic.wait_stream(main)
+            with torch.cuda.stream(s_critic):
+                value = self.critic.forward(b["x"], train=True)
+            mu = self.actor.forward(b["x"], train=True)
+            main.wait_stream(s_critic)
         a = _lib.PpoLossArgs(
             mu=mu.data_ptr(), ld_mu=mu.stride(0), value=value.data_ptr(), ld_value=value.stride(0), actions=actions.data_ptr(),
             old_neglogp=old_neglogp.data_ptr(), advantages=advantages.data_ptr(), returns=returns.data_ptr(),
@@ -189,11 +195,14 @@ class PPOPolicy:
             stats=self.stats.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream(self.device)), "pulse_ppo_loss")
-        s_critic.wait_stream(main)
-        with torch.cuda.stream(s_critic):
-            self.critic.backward(b["dv"], M)
-        self.actor.backward(b["dmu"], M)
-        main.wait_stream(s_critic)
+        if grouped:
+            backward_lockstep((self.actor, self.critic), (b["dmu"], b["dv"]), M)
+        else:
+            s_critic.wait_stream(main)
+            with torch.cuda.stream(s_critic):
+                self.critic.backward(b["dv"], M)
+            self.actor.backward(b["dmu"], M)
+            main.wait_stream(s_critic)
         if amp is not None:
             main.wait_stream(s_disc)
         if world_size > 1:
