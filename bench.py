@@ -515,6 +515,8 @@ def main():
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * h2d * world,
                     "d2h_bytes_per_step": T * d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches_eager), "cuda_graphs": bool(use_graphs), "clocks": clocks,
+            "gemm_switches": {"cta_pairs": os.environ.get("PULSE_GEMM_PAIR", "1") != "0", "pdl": os.environ.get("PULSE_GEMM_PDL", "1") != "0",
+                              "grouped_launches": os.environ.get("PULSE_GROUPED", "0") == "1"},
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/im_step_traffic.json)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
