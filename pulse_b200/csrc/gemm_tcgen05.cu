@@ -29,7 +29,7 @@ namespace pulse {
 namespace {
 
 #ifndef PULSE_GEMM_VARIANT
-#define PULSE_GEMM_VARIANT 0   // 0 = product; 3 = phase-trace build for tools/gemm_trace.py (tools/build_variant.sh 3)
+#define PULSE_GEMM_VARIANT 0   // 0 = product; 3 = phase-trace build for tools/gemm_trace.py (tools/build_variant.sh trace gemm_tcgen05.cu -DPULSE_GEMM_VARIANT=3)
 #endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns

@@ -30,10 +30,16 @@ namespace {
 constexpr int kNB = PULSE_NUM_BODIES;
 constexpr int kEnvs = 8;                   // envs per group
 constexpr int kTeam = kEnvs * kNB;         // 192 threads: one per (env, body)
-constexpr int kTeams = 3;                  // consumer teams per CTA
+#ifndef PULSE_STEP_TEAMS
+#define PULSE_STEP_TEAMS 3    // A/B knob (tools/build_variant.sh): 2 teams = 448 threads, register cap 146 instead of 96
+#endif
+#ifndef PULSE_STEP_STAGES
+#define PULSE_STEP_STAGES 5
+#endif
+constexpr int kTeams = PULSE_STEP_TEAMS;   // consumer teams per CTA
 constexpr int kConsumers = kTeam * kTeams; // 576
 constexpr int kThreads = kConsumers + 64;  // + issuer warp + planner warp (20 warps: register cap 102)
-constexpr int kStages = 5;                 // data stages
+constexpr int kStages = PULSE_STEP_STAGES; // data stages
 constexpr int kBatch = 4;                  // groups planned per planner pass (4 x 8 envs = 32 lanes)
 constexpr int kPlanSlots = 2;              // plan ring: planner passes in flight
 constexpr int kFrame = PULSE_FRAME_REC;    // 312 floats = 1248 B

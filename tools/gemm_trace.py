@@ -1,5 +1,6 @@
-"""Development tool: per-phase clock trace of CTA 0 of one GEMM launch (needs the PULSE_GEMM_VARIANT=3 build:
-tools/build_variant.sh 3; PULSE_ALT_LIB=pulse_b200/build/libpulse_v3.so python tools/gemm_trace.py)."""
+"""Development tool: per-phase clock trace of CTA 0 of one GEMM launch.  Needs the trace build:
+    tools/build_variant.sh trace gemm_tcgen05.cu -DPULSE_GEMM_VARIANT=3
+    PULSE_ALT_LIB=$PWD/pulse_b200/build/libpulse_trace.so python tools/gemm_trace.py"""
 import ctypes as C
 import os
 import sys
