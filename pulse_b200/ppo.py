@@ -130,8 +130,13 @@ class PPOPolicy:
         M = obs.shape[0]
         b = self._buf(M, False)
         self.obs_rms.normalize_into(obs, b["x"])
-        mu = self.actor.forward(b["x"])
-        value = self.critic.forward(b["x"])
+        from .dense import grouped_enabled
+        if grouped_enabled():   # experimental (default off): actor + critic hidden layers in one grouped launch per layer
+            from .nets import forward_lockstep
+            mu, value = forward_lockstep((self.actor, self.critic), (b["x"], b["x"]))
+        else:
+            mu = self.actor.forward(b["x"])
+            value = self.critic.forward(b["x"])
         if eps is None:
             eps = torch.randn(M, self.A, device=self.device)
         with torch.cuda.device(self.device):
