@@ -161,19 +161,48 @@ class HumanoidImCompute:
 
 
     # ------------------------------------------------------------------------------------------
-    def build_amp_obs_demo(self, motion_ids: torch.Tensor, motion_times0: torch.Tensor, num_steps: Optional[int] = None) -> torch.Tensor:
+    def build_amp_obs_demo(self, motion_ids: torch.Tensor, motion_times0: torch.Tensor, num_steps: Optional[int] = None,
+                           first_step: int = 0) -> torch.Tensor:
         """HumanoidAMP.build_amp_obs_demo (humanoid_amp.py:253-284): AMP observations of the reference motion at
         t0 - k*dt, k = 0..steps-1, one MotionLib query (no offset) + one AMP-obs launch.  Returns [n, steps*196]."""
         steps = int(num_steps or self.cfg.num_amp_obs_steps)
         n = int(motion_ids.shape[0])
         dev = self.device
         ids = motion_ids.to(dev).unsqueeze(-1).repeat(1, steps).reshape(-1)
-        times = (motion_times0.to(dev).unsqueeze(-1) + (-self.cfg.dt) * torch.arange(0, steps, device=dev)).reshape(-1)
+        k = torch.arange(0, steps, device=dev)
+        if first_step:   # _init_amp_obs_ref (humanoid_amp.py:540-541): -dt * (arange + 1)
+            k = k + first_step
+        times = (motion_times0.to(dev).unsqueeze(-1) + (-self.cfg.dt) * k).reshape(-1)
         ms = self.motion_lib.get_motion_state(ids, times)
         body = torch.cat([ms["rg_pos"], ms["rb_rot"], ms["body_vel"], ms["body_ang_vel"]], dim=-1).contiguous()   # [n*steps, 24, 13]
         out = torch.empty(n * steps, 1, AMP_OBS, device=dev)
         self.amp_obs(body_state=body, dof_pos=ms["dof_pos"], dof_vel=ms["dof_vel"], amp_obs_buf=out, shift_history=False)
         return out.view(n, steps * AMP_OBS)
+
+    def reset_ref_state(self, env_ids: torch.Tensor, motion_ids: torch.Tensor, motion_times: torch.Tensor, global_offset: torch.Tensor, *,
+                        root_states: torch.Tensor, dof_pos: torch.Tensor, dof_vel: torch.Tensor, rigid_body_state: Optional[torch.Tensor] = None,
+                        amp_obs_buf: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """`_reset_ref_state_init` -> `_sample_ref_state` + `_set_env_state` + `_init_amp_obs_ref` for the envs in `env_ids`
+        (humanoid_amp.py:468-488, :535-597; humanoid_im.py:966-989) WITHOUT a host round trip: one MotionLib query for the
+        reset poses (with the envs' global offsets), index_copy into the simulator's tensors (Isaac Gym views, written in
+        place: `root_states` [N,13], `dof_pos` / `dof_vel` [N,69] views, `rigid_body_state` [N,B>=24,13]), one query +
+        one AMP-obs launch for the `num_amp_obs_steps - 1` history frames at t - k*dt (no offset, as the reference).
+        `motion_ids` / `motion_times` / `global_offset` are the rows for `env_ids` (len(env_ids) each).
+        EXPERIMENTAL in round 1 (built from validated kernels, its own GPU test is opt-in).  Returns the motion state."""
+        ms = self.motion_lib.get_motion_state(motion_ids, motion_times, global_offset)
+        n = int(env_ids.shape[0])
+        root = torch.cat([ms["root_pos"], ms["root_rot"], ms["root_vel"], ms["root_ang_vel"]], dim=-1)
+        root_states.index_copy_(0, env_ids, root)
+        dof_pos.index_copy_(0, env_ids, ms["dof_pos"])
+        dof_vel.index_copy_(0, env_ids, ms["dof_vel"])
+        if rigid_body_state is not None:
+            body = torch.cat([ms["rg_pos"], ms["rb_rot"], ms["body_vel"], ms["body_ang_vel"]], dim=-1)      # [n, 24, 13]
+            rigid_body_state[:, :NUM_BODIES].index_copy_(0, env_ids, body)
+        if amp_obs_buf is not None:
+            steps = int(amp_obs_buf.shape[1])
+            hist = self.build_amp_obs_demo(motion_ids, motion_times, steps - 1, first_step=1).view(n, steps - 1, AMP_OBS)   # t - dt ... t - (steps-1) dt
+            amp_obs_buf[:, 1:].index_copy_(0, env_ids, hist)
+        return ms
 
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
         """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230) with HumanoidIm's `_sample_time` = sample_time_interval."""

@@ -1,12 +1,12 @@
 #!/bin/bash
 # One gpurun call that validates and measures everything round 1 left prepared but unvalidated (run
 # tools/round2_build_variants.sh first):
-#   1. opt-in GPU tests: grouped GEMM launches + lock-step PPO update, MotionDatasetB200.load_motions
+#   1. opt-in GPU tests: grouped GEMM launches + lock-step PPO update, MotionDatasetB200.load_motions, reset_ref_state
 #   2. step-kernel A/B: consumer teams / stages (isolated microbench, L2 flushed)
 #   3. headline bench with grouped launches off / on
 mkdir -p gpurun_out
 echo "== opt-in tests"
-PULSE_GROUPED_TEST=1 PULSE_EXPERIMENTAL_DATASET=1 timeout 300 python -m pytest tests/test_gpu_grouped.py tests/test_gpu_loader.py -q 2>&1 | tail -15
+PULSE_GROUPED_TEST=1 PULSE_EXPERIMENTAL_DATASET=1 PULSE_EXPERIMENTAL_RESET=1 timeout 300 python -m pytest tests/test_gpu_grouped.py tests/test_gpu_loader.py tests/test_gpu_reset.py -q 2>&1 | tail -15
 echo "== step kernel variants (im_step_ms / GB/s at 16384 envs)"
 for v in product t2 t2s4 t3s4; do
   if [ $v = product ]; then unset PULSE_ALT_LIB; else export PULSE_ALT_LIB=$PWD/pulse_b200/build/libpulse_$v.so; fi
