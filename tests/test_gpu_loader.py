@@ -30,8 +30,6 @@ def test_device_loader_matches_reference_tables():
     assert torch.equal(ml.length_starts.cpu(), tables["length_starts"]) and torch.equal(ml._motion_num_frames.cpu(), tables["num_frames"])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PULSE_EXPERIMENTAL_DATASET") != "1",
-                    reason="MotionDatasetB200.load_motions was written after the round's GPU budget was spent (opt in with PULSE_EXPERIMENTAL_DATASET=1)")
 def test_dataset_load_motions_reproduces_the_reference_tables():
     """`MotionDatasetB200.load_motions(random_sample=False)` = the reference's `load_motions` on the same clips (motionlib.npz was
     produced by exactly that call, make_golden.py): clip selection + heading protocol + device loader end to end."""

@@ -2,15 +2,12 @@
 scattered into the simulator's tensors and the AMP history back-filled, built from the validated MotionLib-query and AMP-obs
 kernels -- against the oracle's composition of the same reference steps.  Opt-in (PULSE_EXPERIMENTAL_RESET=1): written after
 round 1's GPU budget was spent."""
-import os
-
 import pytest
 import torch
 
 from tests.helpers import oracle_tables
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PULSE_EXPERIMENTAL_RESET") != "1",
-                                                  reason="reset scatter not yet run on a GPU (opt in with PULSE_EXPERIMENTAL_RESET=1)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
@@ -48,5 +45,5 @@ def test_reset_ref_state_matches_oracle():
         t_k = times + (-dt) * (k + 1)
         h = po.motion_state(tb, motion_ids, t_k)
         ref = po.amp_obs_smpl(h["root_pos"], h["root_rot"], h["root_vel"], h["root_ang_vel"], h["dof_pos"], h["dof_vel"],
-                              h["rg_pos"][:, list(po.KEY_BODY_IDS)])
+                              h["rg_pos"][:, list(po.KEY_BODY_IDS)], po.amp_dof_subset())
         torch.testing.assert_close(amp[env_ids, k + 1].cpu(), ref, atol=1e-4, rtol=1e-4)

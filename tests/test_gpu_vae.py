@@ -250,3 +250,61 @@ def test_reach_step_matches_reference():
     torch.testing.assert_close(task._tar_pos[sel], exp[sel], atol=1e-6, rtol=1e-6)
     assert torch.equal(task._tar_pos[~sel], before[~sel])
     assert torch.equal(task._tar_change_steps[sel], (prog + steps)[sel])
+
+
+def _vae_grad_checks(vae, E):
+    """(reference parameter name, our gradient) for every trainable tensor of the kin loss."""
+    checks = []
+    for mlp, prefix, head in ((vae.enc, "z_mlp", None), (vae.prior, "z_prior", None), (vae.dec, "actor_mlp", "mu")):
+        for i, l in enumerate(mlp.layers[:-1]):
+            gw = l.weight_grad[:, :l.K].cpu()
+            if i == 0 and mlp.in_perm is not None:
+                full = torch.empty_like(gw)
+                full[:, mlp.in_perm] = gw
+                gw = full
+            checks += [(f"{prefix}.{2 * i}.weight", gw), (f"{prefix}.{2 * i}.bias", l.bias_grad.cpu())]
+        if head is not None:
+            l = mlp.layers[-1]
+            checks += [(f"{head}.weight", l.weight_grad[:, :l.K].cpu()), (f"{head}.bias", l.bias_grad.cpu())]
+    for mlp, mu_name, lv_name in ((vae.enc, "z_mu", "z_logvar"), (vae.prior, "z_prior_mu", "z_prior_logvar")):
+        l = mlp.layers[-1]
+        gw, gb = l.weight_grad[:, :l.K].cpu(), l.bias_grad.cpu()
+        checks += [(mu_name + ".weight", gw[:E]), (lv_name + ".weight", gw[E:]), (mu_name + ".bias", gb[:E]), (lv_name + ".bias", gb[E:])]
+    return checks
+
+
+@pytest.mark.parametrize("regu", [False, True])
+def test_optimize_kin_full_width_losses_within_1e3(regu):
+    """SURVEY row a19 at im_z_fit.yaml WIDTHS (encoder 934-1536-1024-512-160, prior 358-..., decoder 390-3096-2048-1024-69,
+    2048 rows = 64 envs x 32 steps): every loss term of `_optimize_kin` within 1e-3 (relative) of the unmodified reference's
+    (tests/golden/vae_full.npz, make_golden_vae_full.py), gradients against the reference's autograd samples."""
+    from pulse_b200.vae import PulseVAE
+    from tests.helpers import VAE_FULL, vae_full_fixture
+    g = load_npz("vae_full.npz")
+    sd, batch, chk = vae_full_fixture()
+    assert abs(chk - float(g["checksum"])) < 1e-9 * max(1.0, abs(chk)), "regenerated fixture differs from the one the golden was made with"
+    d = VAE_FULL
+    vae = PulseVAE(self_obs_size=d["S"], task_obs_size=d["Tk"], num_actions=d["A"], latent=d["E"], task_units=d["task_units"], dec_units=d["dec_units"],
+                   device=DEV, horizon=d["T"], with_critic=False, use_vae_prior_regu=regu)
+    vae.load_state_dict({"a2c_network." + k: v for k, v in sd.items()})
+    vae.obs_rms.running_var.fill_(1.0 - 1e-5)       # rstd = 1 exactly: the batch is already normalised (the reference gets it through batch_dict['obs'])
+    vae.obs_rms._refresh()
+    B = batch["obs"].shape[0]
+    vae.optimize_kin(batch["obs"].to(DEV), batch["gt_action"].to(DEV), batch["progress"].to(DEV), noise=batch["noise"].to(DEV), step=False)
+    L = vae.losses(B)
+    tag = "regu_" if regu else ""
+    rel = {}
+    for k in ("kin_loss", "kin_action_loss", "kin_KLD", "kin_ar1") + (("kin_prior_regu",) if regu else ()):
+        ref = float(g[tag + "info." + k])
+        rel[k] = abs(L[k] - ref) / max(abs(ref), 1e-12)
+    assert all(v < 1e-3 for v in rel.values()), (rel, L)
+    if regu:
+        return
+    E = d["E"]
+    report = {}
+    for name, ours in _vae_grad_checks(vae, E):
+        ref = g["grad." + name]
+        mine = ours[:4] if ours.dim() == 2 else ours
+        report[name] = (round(_cos(mine, ref), 4), float(ours.double().norm()) / (float(g["gnorm." + name]) + 1e-30))
+    bad = {k: v for k, v in report.items() if v[0] < 0.99 or abs(v[1] - 1.0) > 0.03}
+    assert not bad, bad

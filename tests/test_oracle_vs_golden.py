@@ -202,6 +202,53 @@ def test_vae_distillation_teacher_zdecode_reach_pd():
     assert abs(po.kld_anneal(3750) - 0.0055) < 1e-9 and po.kld_anneal(6000) == 0.001
 
 
+def _check_against_step4096(out, g, obs_atol, sum_atol):
+    assert torch.equal(out["reset_buf"], g["reset_buf"]) and torch.equal(out["terminate_buf"], g["terminate_buf"])
+    assert torch.equal(out["frame_idx_rew"], g["frame_idx_rew"]) and torch.equal(out["frame_idx_obs"], g["frame_idx_obs"])
+    close(out["rew_buf"], g["rew_buf"], atol=obs_atol, rtol=0)
+    close(out["reward_raw"], g["reward_raw"], atol=obs_atol, rtol=0)
+    close(out["obs_buf"][::32], g["obs_rows"], atol=obs_atol, rtol=0)
+    close(out["obs_buf"].double().sum(1), g["obs_row_sum"], atol=sum_atol, rtol=0)
+
+
+def test_step_4096_envs_oracle_matches_reference():
+    """BASELINE config C2 size (4096 envs, 100 clips): the oracle's fused step on the regenerated inputs vs the reference's outputs
+    (tests/golden/step_n4096.npz, make_golden_step4096.py); also proves the bit-exact input regeneration on this host."""
+    from tests.helpers import exact_step_inputs, exact_tables, load_npz as _l
+    g = _l("step_n4096.npz")
+    tb = exact_tables(int(g["dims"][1]))
+    z, chk = exact_step_inputs(tb, int(g["dims"][0]))
+    assert abs(chk - float(g["checksum"])) < 1e-9 * abs(chk)
+    out = po.humanoid_im_step(tb, po.ImStepConfig(), z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"],
+                              z["start_times"], z["start_offset"], z["global_offset"], z["cycle_counter"], z["reset_buf_in"])
+    _check_against_step4096(out, g, 2e-6, 1e-4)
+    assert 0 < int(g["terminate_buf"].sum()) < 4096 and int(g["reset_buf"].sum()) > int(g["terminate_buf"].sum())
+
+
+def test_vae_full_width_oracle_matches_reference():
+    """Row a19 at im_z_fit.yaml widths: the oracle on the regenerated fixture vs the reference's losses / gradient samples
+    (tests/golden/vae_full.npz).  Also proves the integer-exact fixture regeneration (checksum) on this host."""
+    from tests.helpers import VAE_FULL, load_npz as _l, vae_full_fixture, vae_param_list
+    g = _l("vae_full.npz")
+    sd, batch, chk = vae_full_fixture()
+    assert abs(chk - float(g["checksum"])) < 1e-9 * max(1.0, abs(chk))
+    nets = po.VaeNets.from_state_dict(sd, VAE_FULL["S"])
+    params = vae_param_list(nets)
+    for p in params.values():
+        p.requires_grad_(True)
+    r = po.vae_kin_loss(nets, batch["obs"], batch["noise"], batch["gt_action"], batch["progress"], VAE_FULL["T"])
+    r["kin_loss"].backward()
+    for k in ("kin_loss", "kin_action_loss", "kin_KLD", "kin_ar1"):
+        close(r[k].detach(), torch.as_tensor(g["info." + k]), atol=1e-5, rtol=1e-5)
+    for name, p in params.items():
+        ref = g["grad." + name]
+        close(p.grad[:4] if p.grad.dim() == 2 else p.grad, ref, atol=2e-6, rtol=1e-3)
+    with torch.no_grad():
+        for k in ("pred_action", "vae_mu", "vae_log_var", "prior_mu", "prior_log_var"):
+            close(r[k][:64], g[k], atol=2e-5, rtol=1e-4)
+    assert float((g["vae_log_var"] >= 2).float().mean()) > 0.02      # the clamp is exercised at full width too
+
+
 def test_reach_full_step_pieces():
     from tests.helpers import load_npz as _l
     g = _l("vae.npz")
