@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PULSE_ABI_VERSION 1
+#define PULSE_ABI_VERSION 2
 
 enum pulse_status {
   PULSE_OK = 0,
@@ -161,6 +161,14 @@ typedef struct {
   float* ref_body_vel;   /* [N,24,3] optional */
   float* ref_body_rot;   /* [N,24,4] optional */
   float* ref_dof_pos;    /* [N,69]   optional (costs 2 extra 960-byte gathers per env) */
+  /* ---- ABI 2 ---- */
+  const int32_t* env_count;        /* optional DEVICE-side length of env_ids (the compacted list pulse_reset_ref_state writes): only the
+                                      first min(num_envs, *env_count) entries are processed -- no host read of the count is ever needed */
+  const int32_t* recovery_counter; /* [N] or NULL.  HumanoidImGetup._compute_reset (humanoid_im_getup.py:203-210): for envs with
+                                      recovery_counter > 0 the reset / terminate outputs are forced to 0 and progress_buf is decremented
+                                      (through progress_rw) BEFORE the observation time is formed */
+  int64_t* progress_rw;            /* writable alias of progress_buf; required with recovery_counter */
+  float* fdones_out;               /* [N] optional float copy of reset_buf (the experience buffer's `dones`, amp_agent.py:383) */
 } pulse_im_step_args_t;
 /* num_envs = number of envs processed (= len(env_ids) when env_ids is given). */
 int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_args_t* args, int64_t num_envs, void* stream);
@@ -180,6 +188,50 @@ typedef struct {
   int32_t shift_history;/* 1: shift then write slot 0;  0: write slot 0 only */
 } pulse_amp_obs_args_t;
 int pulse_amp_obs(const pulse_amp_obs_args_t* args, int64_t num_envs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-step env reset, fused and free of host synchronisation.  Replaces, for the envs whose
+ * reset_buf is set (mask mode: the `done_indices` of AMPAgent.play_steps, phc/learning/amp_agent.py:352 -> env_reset ->
+ * VecTaskPythonWrapper.reset -> Humanoid.reset, humanoid.py:526-541) or for an explicit id list:
+ *   HumanoidIm._reset_ref_state_init     phc/env/tasks/humanoid_im.py:921-948   (start offset / global offset / cycle counter <- 0)
+ *   HumanoidAMP._reset_ref_state_init    humanoid_amp.py:468-488, _sample_ref_state humanoid_im.py:966-989
+ *   MotionLibBase.sample_time_interval   phc/utils/motion_lib_base.py:411-420   (uniform draw injected or Philox)
+ *   HumanoidAMP._set_env_state           humanoid_amp.py:565-597  (root 13, dof pos / vel 69, rigid bodies 24 x 13, written in place
+ *                                        into the Isaac Gym views; the rigid-body write is the reference's own post-refresh hack :604-614)
+ *   Humanoid._reset_env_tensors          humanoid.py:589-609      (progress / reset / terminate <- 0, contact forces <- 0, and the
+ *                                        int32 actor-id list for gym.set_*_tensor_indexed, built on the device)
+ *   HumanoidAMP._init_amp_obs            humanoid_amp.py:519-563  (current AMP observation + the num_steps-1 history frames at
+ *                                        t - k*dt from the reference motion, no offset)
+ * Two launches (ordered compaction; one warp per (env, history step)).  The observation of the reset envs follows with
+ * pulse_im_step(flags = PULSE_STEP_OBS, env_ids = env_list, env_count = count).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t* reset_buf;            /* [N] mask mode: envs with reset_buf != 0 are reset; cleared for them afterwards */
+  const int64_t* env_ids_in;     /* list mode: explicit env ids [num_ids] (Humanoid.reset(env_ids)); NULL = mask mode */
+  int64_t num_ids;
+  const float* phase;            /* [N] uniform [0,1) draw per ENV (tests inject it) or NULL: Philox4x32-10(seed, env, offset) */
+  uint64_t seed, offset;
+  const int64_t* motion_ids;     /* [N] _sampled_motion_ids (each env keeps its clip, humanoid_im.py:966-989) */
+  float* motion_start_times;     /* [N] <- sampled start time */
+  float* motion_start_offset;    /* [N] <- 0 */
+  float* global_offset;          /* [N,3] <- 0 */
+  int32_t* cycle_counter;        /* [N] <- 0 (may be NULL) */
+  int64_t* progress_buf;         /* [N] <- 0 */
+  int64_t* terminate_buf;        /* [N] <- 0 (may be NULL) */
+  float* root_states; int64_t root_env_stride;           /* _humanoid_root_states: env e at root_states + e*root_env_stride, 13 floats */
+  float* dof_pos; float* dof_vel; int64_t dof_env_stride; int64_t dof_elem_stride;   /* Isaac Gym dof-state views (elem stride 2) */
+  float* rigid_body_state; int64_t body_env_stride;      /* [N, bodies_per_env, 13]; may be NULL */
+  float* contact_forces; int64_t contact_env_stride; int32_t contact_bodies;   /* [N, bodies_per_env, 3] <- 0; may be NULL */
+  int32_t num_amp_steps;         /* numAMPObsSteps; 0 with amp_obs_buf NULL */
+  float* amp_obs_buf;            /* [N, num_amp_steps, 196]; may be NULL */
+  float dt;                      /* control dt */
+  int32_t reserved;
+  const int32_t* actor_ids;      /* [N] _humanoid_actor_ids (humanoid.py:590) or NULL */
+  int64_t* env_list;             /* [N] out: the reset env ids, ascending (what `nonzero` returns) */
+  int32_t* actor_list;           /* [N] out: actor ids of those envs (argument of gym.set_*_tensor_indexed); may be NULL */
+  int32_t* count;                /* [1] out, device side: number of reset envs */
+} pulse_reset_args_t;
+int pulse_reset_ref_state(const pulse_motionlib_t* lib, const pulse_reset_args_t* args, int64_t num_envs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GAE / returns.  CommonAgent.discount_values  phc/learning/common_agent.py:493-505, mb_returns =

@@ -398,8 +398,12 @@ def im_motion_times(progress_buf, start_times, start_offset, dt: float, plus_one
 def humanoid_im_step(tb: MotionTables, cfg: ImStepConfig, body_state: torch.Tensor, dof_vel: torch.Tensor,
                      dof_force: torch.Tensor, progress_buf: torch.Tensor, motion_ids: torch.Tensor,
                      start_times: torch.Tensor, start_offset: torch.Tensor, global_offset: torch.Tensor,
-                     cycle_counter: torch.Tensor, reset_buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+                     cycle_counter: torch.Tensor, reset_buf: torch.Tensor,
+                     recovery_counter: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """HumanoidIm.post_physics_step compute, non-cycling branch, after `progress_buf += 1`.
+    With `recovery_counter` the HumanoidImGetup override of `_compute_reset` (humanoid_im_getup.py:203-210) is applied:
+    recovering envs are never reset and their progress counter is pulled back by one BEFORE the observation is computed
+    (out["progress_buf"] is the counter after the step).
 
     humanoid_im.py:853-919 (_compute_reward), :1119-1192 (_compute_reset), :677-851
     (_compute_observations / _compute_task_obs, obs_v 6), humanoid.py:1137-1213 (_compute_humanoid_obs).
@@ -433,6 +437,12 @@ def humanoid_im_step(tb: MotionTables, cfg: ImStepConfig, body_state: torch.Tens
     recovering = torch.logical_and(~pass_time, cycle_counter > 0)
     reset = torch.where(recovering, torch.zeros_like(reset), reset)
     terminated = torch.where(recovering, torch.zeros_like(terminated), terminated)
+    if recovery_counter is not None:                      # humanoid_im_getup.py:206-209
+        is_rec = recovery_counter > 0
+        reset = torch.where(is_rec, torch.zeros_like(reset), reset)
+        terminated = torch.where(is_rec, torch.zeros_like(terminated), terminated)
+        progress_buf = torch.where(is_rec, progress_buf - 1, progress_buf)
+        out["progress_buf"] = progress_buf
     out["reset_buf"], out["terminate_buf"] = reset, terminated
     out["frame_idx_rew"] = torch.stack([ref["frame_idx0"], ref["frame_idx1"]], dim=-1)
 
@@ -455,6 +465,62 @@ def amp_obs_step(amp_obs_buf: torch.Tensor, body_state: torch.Tensor, dof_pos: t
     cur = amp_obs_smpl(body_state[:, 0, 0:3], body_state[:, 0, 3:7], body_state[:, 0, 7:10], body_state[:, 0, 10:13],
                        dof_pos, dof_vel, body_state[:, list(KEY_BODY_IDS), 0:3], amp_dof_subset())
     return torch.cat([cur.unsqueeze(1), amp_obs_buf[:, :-1]], dim=1)
+
+
+def reset_envs(tb: MotionTables, cfg: ImStepConfig, st: Dict[str, torch.Tensor], env_ids: torch.Tensor, phase: torch.Tensor,
+               num_amp_steps: int = 10) -> Dict[str, torch.Tensor]:
+    """The reference's per-step env reset for the envs in `env_ids` (ascending, what `nonzero` returns), restated as one function
+    over a dict of buffers (all updated copies are returned; `phase[e]` is the uniform draw of env e):
+
+      Humanoid._reset_envs (humanoid.py:574-587)
+        -> HumanoidIm._reset_ref_state_init (humanoid_im.py:921-948): start offset, global offset, cycle counter <- 0
+        -> HumanoidAMP._reset_ref_state_init (humanoid_amp.py:468-488) / _sample_ref_state (humanoid_im.py:966-989):
+           start time = sample_time_interval (motion_lib_base.py:411-420), get_motion_state with the (zeroed) global offset
+        -> _set_env_state (humanoid_amp.py:565-597): root 13, dof pos / vel, rigid bodies (kept after the refresh, :604-614)
+        -> _reset_env_tensors (humanoid.py:589-609): progress / reset / terminate / contact forces <- 0
+        -> _compute_observations(env_ids) (humanoid_im.py:677-706)
+      HumanoidAMP._init_amp_obs (humanoid_amp.py:519-563): current AMP observation from the state just set, history rows from the
+      reference motion at t0 - dt*(k), k = 1 .. num_amp_steps-1, WITHOUT offset.
+
+    st keys: motion_ids, start_times, start_offset, global_offset [N,3], cycle_counter, progress_buf, reset_buf, terminate_buf,
+    root_states [N,13], dof_pos [N,69], dof_vel [N,69], body_state [N,24,13], contact_forces [N,24,3], amp_obs_buf [N,steps,196],
+    obs_buf [N,934], dof_force [N,69]."""
+    o = {k: v.clone() for k, v in st.items()}
+    ids = env_ids.long()
+    n = ids.shape[0]
+    if n == 0:
+        return o
+    mids = o["motion_ids"][ids]
+    o["start_offset"][ids] = 0
+    o["global_offset"][ids] = 0
+    o["cycle_counter"][ids] = 0
+    t0 = sample_time_interval(tb, mids, phase[ids])
+    ms = motion_state(tb, mids, t0, o["global_offset"][ids])
+    o["root_states"][ids] = torch.cat([ms["root_pos"], ms["root_rot"], ms["root_vel"], ms["root_ang_vel"]], dim=-1)
+    o["dof_pos"][ids] = ms["dof_pos"]
+    o["dof_vel"][ids] = ms["dof_vel"]
+    o["body_state"][ids] = torch.cat([ms["rg_pos"], ms["rb_rot"], ms["body_vel"], ms["body_ang_vel"]], dim=-1)
+    o["start_times"][ids] = t0
+    o["progress_buf"][ids] = 0
+    o["reset_buf"][ids] = 0
+    o["terminate_buf"][ids] = 0
+    o["contact_forces"][ids] = 0
+    # _compute_observations(env_ids): progress 0 -> observation query at dt + t0
+    sub = humanoid_im_step(tb, cfg, o["body_state"][ids], o["dof_vel"][ids], o["dof_force"][ids], o["progress_buf"][ids], mids, t0,
+                           o["start_offset"][ids], o["global_offset"][ids], o["cycle_counter"][ids], o["reset_buf"][ids])
+    o["obs_buf"][ids] = sub["obs_buf"]
+    # _init_amp_obs: slot 0 from the simulator tensors just written, slots 1.. from the reference motion (no offset)
+    bs = o["body_state"][ids]
+    cur = amp_obs_smpl(bs[:, 0, 0:3], bs[:, 0, 3:7], bs[:, 0, 7:10], bs[:, 0, 10:13], o["dof_pos"][ids], o["dof_vel"][ids],
+                       bs[:, list(KEY_BODY_IDS), 0:3], amp_dof_subset())
+    rows = [cur]
+    for k in range(1, num_amp_steps):
+        t_k = t0 + (-cfg.dt) * k
+        h = motion_state(tb, mids, t_k)
+        rows.append(amp_obs_smpl(h["root_pos"], h["root_rot"], h["root_vel"], h["root_ang_vel"], h["dof_pos"], h["dof_vel"],
+                                 h["rg_pos"][:, list(KEY_BODY_IDS)], amp_dof_subset()))
+    o["amp_obs_buf"][ids] = torch.stack(rows, dim=1)
+    return o
 
 
 # ------------------------------------------------------------------------------------------------

@@ -53,6 +53,21 @@ class ImStepArgs(C.Structure):
         ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
         ("pass_time", C.c_void_p), ("ref_body_pos", C.c_void_p), ("ref_body_vel", C.c_void_p),
         ("ref_body_rot", C.c_void_p), ("ref_dof_pos", C.c_void_p),
+        ("env_count", C.c_void_p), ("recovery_counter", C.c_void_p), ("progress_rw", C.c_void_p), ("fdones_out", C.c_void_p),
+    ]
+
+
+class ResetArgs(C.Structure):
+    _fields_ = [
+        ("reset_buf", C.c_void_p), ("env_ids_in", C.c_void_p), ("num_ids", C.c_int64), ("phase", C.c_void_p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("motion_ids", C.c_void_p), ("motion_start_times", C.c_void_p),
+        ("motion_start_offset", C.c_void_p), ("global_offset", C.c_void_p), ("cycle_counter", C.c_void_p), ("progress_buf", C.c_void_p),
+        ("terminate_buf", C.c_void_p), ("root_states", C.c_void_p), ("root_env_stride", C.c_int64),
+        ("dof_pos", C.c_void_p), ("dof_vel", C.c_void_p), ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64),
+        ("rigid_body_state", C.c_void_p), ("body_env_stride", C.c_int64),
+        ("contact_forces", C.c_void_p), ("contact_env_stride", C.c_int64), ("contact_bodies", C.c_int32),
+        ("num_amp_steps", C.c_int32), ("amp_obs_buf", C.c_void_p), ("dt", C.c_float), ("reserved", C.c_int32),
+        ("actor_ids", C.c_void_p), ("env_list", C.c_void_p), ("actor_list", C.c_void_p), ("count", C.c_void_p),
     ]
 
 
@@ -129,6 +144,7 @@ class LoaderArgs(C.Structure):
     ]
 
 
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 Z_SAMPLE, Z_MEAN, Z_RESIDUAL = 0, 1, 2
 STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
@@ -142,6 +158,7 @@ SIGNATURES = {
     "pulse_motionlib_destroy": (C.c_int, [C.c_void_p]),
     "pulse_motion_state": (C.c_int, [C.c_void_p, C.POINTER(MotionQuery), C.c_int64, C.c_void_p]),
     "pulse_im_step": (C.c_int, [C.c_void_p, C.POINTER(ImStepArgs), C.c_int64, C.c_void_p]),
+    "pulse_reset_ref_state": (C.c_int, [C.c_void_p, C.POINTER(ResetArgs), C.c_int64, C.c_void_p]),
     "pulse_amp_obs": (C.c_int, [C.POINTER(AmpObsArgs), C.c_int64, C.c_void_p]),
     "pulse_gae": (C.c_int, [C.POINTER(GaeArgs), C.c_int32, C.c_int64, C.c_void_p]),
     "pulse_normalize_advantages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -207,8 +224,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pulse_abi_version() != 1:
-        raise PulseError(f"ABI version mismatch: library {lib.pulse_abi_version()} != binding 1")
+    if lib.pulse_abi_version() != ABI_VERSION:
+        raise PulseError(f"ABI version mismatch: library {lib.pulse_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

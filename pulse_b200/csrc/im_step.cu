@@ -59,6 +59,7 @@ struct EnvParams {           // issuer -> consumers (copied into the stage)
   float gx, gy, gz;
   float t_rew, mlen;
   int cyc;
+  int rec;                   // recovery_counter > 0 (getup task)
   int valid;
   int body_bulk;
   unsigned char sl[4];       // copy slot (0..2, or kDirect) of logical rows: rew f0, rew f1, obs f0, obs f1
@@ -178,6 +179,9 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
   if (group < ngroups && widx < num_envs) {
     const long long e = a.env_ids != nullptr ? a.env_ids[widx] : widx;
     const long long prog = a.progress_buf[e];
+    // HumanoidImGetup._compute_reset (humanoid_im_getup.py:203-210): a recovering env does not advance its progress counter, so its
+    // observation is taken at (prog - 1) + 1
+    const int rec = (do_reset && a.recovery_counter != nullptr) ? (a.recovery_counter[e] > 0 ? 1 : 0) : 0;
     const long long mid = a.motion_ids[e];
     const float t_start = a.motion_start_times[e];
     const float t_off = a.motion_start_offset[e];
@@ -186,7 +190,7 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
     const long long nf = lib.num_frames[mid];
     const long long row0 = lib.length_starts[mid];
     const float t_rew = motion_time_rn(prog, a.dt, t_start, t_off);
-    const float t_obs = motion_time_rn(prog + 1, a.dt, t_start, t_off);
+    const float t_obs = motion_time_rn(prog + 1 - rec, a.dt, t_start, t_off);
     long long i0r, i1r, i0o, i1o;
     float b_rew, b_obs;
     frame_blend_rn(t_rew, mlen, nf, mdt, i0r, i1r, b_rew);
@@ -238,6 +242,7 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
     P.t_rew = t_rew;
     P.mlen = mlen;
     P.cyc = (do_reset && a.cycle_counter != nullptr) ? a.cycle_counter[e] : 0;
+    P.rec = rec;
     P.valid = 1;
     P.body_bulk = (reinterpret_cast<uintptr_t>(bsrc) & 15u) == 0 ? 1 : 0;
 #pragma unroll
@@ -313,6 +318,10 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
   const bool do_obs = a.flags & PULSE_STEP_OBS;
   const bool need_t = do_rew || do_reset;
   const bool do_power = do_rew && a.dof_force != nullptr;
+  if (a.env_count != nullptr) {   // device-side length of the env list (pulse_reset_ref_state): no host read of the count
+    const long long c = *a.env_count;
+    num_envs = c < num_envs ? (c < 0 ? 0 : c) : num_envs;
+  }
   const long long ngroups = (num_envs + kEnvs - 1) / kEnvs;
 
   if (tid == 0) {
@@ -541,8 +550,14 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
           reset = 0;
           terminated = 0;
         }
+        if (Q.rec) {                    // humanoid_im_getup.py:203-210
+          reset = 0;
+          terminated = 0;
+          a.progress_rw[ee] = Q.prog - 1;
+        }
         a.reset_buf[ee] = reset;
         a.terminate_buf[ee] = terminated;
+        if (a.fdones_out != nullptr) a.fdones_out[ee] = static_cast<float>(reset);
       }
       if (a.pass_time != nullptr) a.pass_time[ee] = (Q.t_rew >= Q.mlen) ? 1 : 0;
     }
@@ -564,6 +579,7 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
   PULSE_REQUIRE(num_envs >= 0, "pulse_im_step: negative num_envs");
   if (num_envs == 0) return PULSE_OK;
   const pulse_im_step_args_t& a = *args;
+  PULSE_REQUIRE(a.env_count == nullptr || a.env_ids != nullptr, "pulse_im_step: env_count limits an env_ids list");
   PULSE_REQUIRE((a.flags & PULSE_STEP_ALL) != 0 && (a.flags & ~PULSE_STEP_ALL) == 0, "pulse_im_step: bad flags 0x%x", a.flags);
   PULSE_REQUIRE(a.body_state && a.progress_buf && a.motion_ids && a.motion_start_times && a.motion_start_offset &&
                     a.global_offset, "pulse_im_step: null state/task buffer");
@@ -582,6 +598,7 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
   }
   if (a.flags & PULSE_STEP_RESET) {
     PULSE_REQUIRE(a.reset_buf && a.terminate_buf && a.termination_distances, "pulse_im_step: null reset buffer");
+    PULSE_REQUIRE(a.recovery_counter == nullptr || a.progress_rw != nullptr, "pulse_im_step: recovery_counter needs the writable progress_rw");
     PULSE_REQUIRE((a.reset_body_mask & 0xffffffu) != 0, "pulse_im_step: empty reset_body_mask");
   }
   if (a.flags & PULSE_STEP_OBS) {

@@ -72,7 +72,9 @@ class HumanoidImCompute:
              reward_raw: Optional[torch.Tensor] = None, reset_buf: Optional[torch.Tensor] = None,
              terminate_buf: Optional[torch.Tensor] = None, pass_time: Optional[torch.Tensor] = None,
              ref_body_pos=None, ref_body_vel=None, ref_body_rot=None, ref_dof_pos=None,
-             env_ids: Optional[torch.Tensor] = None, flags: int = _lib.STEP_ALL, num_envs: Optional[int] = None) -> None:
+             env_ids: Optional[torch.Tensor] = None, flags: int = _lib.STEP_ALL, num_envs: Optional[int] = None,
+             env_count: Optional[torch.Tensor] = None, recovery_counter: Optional[torch.Tensor] = None,
+             fdones_out: Optional[torch.Tensor] = None) -> None:
         """One fused launch.  `body_state` is the [N, bodies_per_env, 13] rigid-body-state view (or its
         [:, :24] slice); `dof_vel` may be the strided Isaac Gym view dof_state[..., 1]."""
         c = self.cfg
@@ -138,6 +140,18 @@ class HumanoidImCompute:
                 raise _lib.PulseError("env_ids must be contiguous int64")
             a.env_ids = env_ids.data_ptr()
             n = int(env_ids.shape[0])
+            if env_count is not None:                 # device-side list length (reset path): never read on the host
+                if env_count.dtype != torch.int32 or env_count.numel() < 1:
+                    raise _lib.PulseError("env_count must be an int32 device scalar")
+                a.env_count = env_count.data_ptr()
+        if recovery_counter is not None:              # HumanoidImGetup (humanoid_im_getup.py:203-210)
+            if recovery_counter.dtype != torch.int32 or not recovery_counter.is_contiguous():
+                raise _lib.PulseError("recovery_counter must be contiguous int32")
+            a.recovery_counter, a.progress_rw = recovery_counter.data_ptr(), progress_buf.data_ptr()
+        if fdones_out is not None:
+            if fdones_out.dtype != torch.float32 or not fdones_out.is_contiguous():
+                raise _lib.PulseError("fdones_out must be contiguous float32 [N]")
+            a.fdones_out = fdones_out.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_im_step(self.motion_lib.handle, C.byref(a), n, _lib.current_stream(self.device)), "pulse_im_step")
 
@@ -179,30 +193,81 @@ class HumanoidImCompute:
         self.amp_obs(body_state=body, dof_pos=ms["dof_pos"], dof_vel=ms["dof_vel"], amp_obs_buf=out, shift_history=False)
         return out.view(n, steps * AMP_OBS)
 
-    def reset_ref_state(self, env_ids: torch.Tensor, motion_ids: torch.Tensor, motion_times: torch.Tensor, global_offset: torch.Tensor, *,
-                        root_states: torch.Tensor, dof_pos: torch.Tensor, dof_vel: torch.Tensor, rigid_body_state: Optional[torch.Tensor] = None,
-                        amp_obs_buf: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """`_reset_ref_state_init` -> `_sample_ref_state` + `_set_env_state` + `_init_amp_obs_ref` for the envs in `env_ids`
-        (humanoid_amp.py:468-488, :535-597; humanoid_im.py:966-989) WITHOUT a host round trip: one MotionLib query for the
-        reset poses (with the envs' global offsets), index_copy into the simulator's tensors (Isaac Gym views, written in
-        place: `root_states` [N,13], `dof_pos` / `dof_vel` [N,69] views, `rigid_body_state` [N,B>=24,13]), one query +
-        one AMP-obs launch for the `num_amp_obs_steps - 1` history frames at t - k*dt (no offset, as the reference).
-        `motion_ids` / `motion_times` / `global_offset` are the rows for `env_ids` (len(env_ids) each).
-        EXPERIMENTAL in round 1 (built from validated kernels, its own GPU test is opt-in).  Returns the motion state."""
-        ms = self.motion_lib.get_motion_state(motion_ids, motion_times, global_offset)
-        n = int(env_ids.shape[0])
-        root = torch.cat([ms["root_pos"], ms["root_rot"], ms["root_vel"], ms["root_ang_vel"]], dim=-1)
-        root_states.index_copy_(0, env_ids, root)
-        dof_pos.index_copy_(0, env_ids, ms["dof_pos"])
-        dof_vel.index_copy_(0, env_ids, ms["dof_vel"])
-        if rigid_body_state is not None:
-            body = torch.cat([ms["rg_pos"], ms["rb_rot"], ms["body_vel"], ms["body_ang_vel"]], dim=-1)      # [n, 24, 13]
-            rigid_body_state[:, :NUM_BODIES].index_copy_(0, env_ids, body)
+    def reset_envs(self, *, motion_ids: torch.Tensor, motion_start_times: torch.Tensor, motion_start_offset: torch.Tensor,
+                   global_offset: torch.Tensor, progress_buf: torch.Tensor, root_states: torch.Tensor, dof_pos: torch.Tensor,
+                   dof_vel: torch.Tensor, rigid_body_state: torch.Tensor, reset_buf: Optional[torch.Tensor] = None,
+                   env_ids: Optional[torch.Tensor] = None, terminate_buf: Optional[torch.Tensor] = None,
+                   cycle_counter: Optional[torch.Tensor] = None, contact_forces: Optional[torch.Tensor] = None,
+                   amp_obs_buf: Optional[torch.Tensor] = None, actor_ids: Optional[torch.Tensor] = None,
+                   phase: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, obs_buf: Optional[torch.Tensor] = None,
+                   self_obs_buf: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """The per-step env reset of the rollout loop (`self.obs = self.env_reset(done_indices)`, amp_agent.py:352 ->
+        Humanoid.reset -> _reset_envs, humanoid.py:526-587, humanoid_amp.py:347-356, :468-488, :519-597, humanoid_im.py:921-989)
+        WITHOUT a host round trip: `pulse_reset_ref_state` (device-side compaction of `reset_buf` -- or the explicit `env_ids` --
+        start-time draw, MotionLib query, scatter into the simulator's root / dof / rigid-body views, counters cleared, AMP
+        history back-filled) followed by the fused step kernel in observation mode on the compacted list.
+        `phase`: per-ENV uniform draws (tests); None -> Philox4x32-10(seed, env, offset) inside the kernel.
+        Returns {'env_list', 'actor_list', 'count'}: device tensors for gym.set_*_tensor_indexed (count stays on the device)."""
+        N = int(progress_buf.shape[0])
+        dev = self.device
+        ws = getattr(self, "_reset_ws", None)
+        if ws is None or ws["env_list"].shape[0] < N:
+            ws = {"env_list": torch.zeros(N, dtype=torch.int64, device=dev), "actor_list": torch.zeros(N, dtype=torch.int32, device=dev),
+                  "count": torch.zeros(1, dtype=torch.int32, device=dev)}
+            self._reset_ws = ws
+        if (reset_buf is None) == (env_ids is None):
+            raise _lib.PulseError("reset_envs takes either the reset_buf mask or an explicit env_ids list")
+        if rigid_body_state.dim() != 3 or rigid_body_state.shape[-1] != 13 or rigid_body_state.stride(1) != 13 or rigid_body_state.stride(2) != 1:
+            raise _lib.PulseError("rigid_body_state must be a [N,B,13] view with row stride 13")
+        if dof_pos.stride() != dof_vel.stride():
+            raise _lib.PulseError("dof_pos and dof_vel must share strides (views of one dof-state tensor)")
+        a = _lib.ResetArgs()
+        if reset_buf is not None:
+            if reset_buf.dtype != torch.int64:
+                raise _lib.PulseError("reset_buf must be int64")
+            a.reset_buf = reset_buf.data_ptr()
+        else:
+            if env_ids.dtype != torch.int64 or not env_ids.is_contiguous():
+                raise _lib.PulseError("env_ids must be contiguous int64")
+            a.env_ids_in, a.num_ids = env_ids.data_ptr(), int(env_ids.shape[0])
+        if phase is not None:
+            if phase.dtype != torch.float32 or phase.shape[0] != N:
+                raise _lib.PulseError("phase must be float32 [N] (one uniform draw per env)")
+            a.phase = phase.data_ptr()
+        a.seed, a.offset = int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1)
+        for name, t, dt_ in (("motion_ids", motion_ids, torch.int64), ("motion_start_times", motion_start_times, torch.float32),
+                             ("motion_start_offset", motion_start_offset, torch.float32), ("global_offset", global_offset, torch.float32),
+                             ("progress_buf", progress_buf, torch.int64)):
+            if t.dtype != dt_ or not t.is_contiguous() or t.shape[0] != N:
+                raise _lib.PulseError(f"{name}: expected contiguous {dt_} with {N} rows")
+            setattr(a, name, t.data_ptr())
+        if cycle_counter is not None:
+            a.cycle_counter = cycle_counter.data_ptr()
+        if terminate_buf is not None:
+            a.terminate_buf = terminate_buf.data_ptr()
+        a.root_states, a.root_env_stride = root_states.data_ptr(), root_states.stride(0)
+        a.dof_pos, a.dof_vel, a.dof_env_stride, a.dof_elem_stride = dof_pos.data_ptr(), dof_vel.data_ptr(), dof_pos.stride(0), dof_pos.stride(1)
+        a.rigid_body_state, a.body_env_stride = rigid_body_state.data_ptr(), rigid_body_state.stride(0)
+        if contact_forces is not None:
+            a.contact_forces, a.contact_env_stride, a.contact_bodies = contact_forces.data_ptr(), contact_forces.stride(0), int(contact_forces.shape[1])
         if amp_obs_buf is not None:
-            steps = int(amp_obs_buf.shape[1])
-            hist = self.build_amp_obs_demo(motion_ids, motion_times, steps - 1, first_step=1).view(n, steps - 1, AMP_OBS)   # t - dt ... t - (steps-1) dt
-            amp_obs_buf[:, 1:].index_copy_(0, env_ids, hist)
-        return ms
+            if not amp_obs_buf.is_contiguous() or amp_obs_buf.shape[-1] != AMP_OBS:
+                raise _lib.PulseError("amp_obs_buf must be contiguous [N, steps, 196]")
+            a.amp_obs_buf, a.num_amp_steps = amp_obs_buf.data_ptr(), int(amp_obs_buf.shape[1])
+        a.dt = self.cfg.dt
+        if actor_ids is not None:
+            if actor_ids.dtype != torch.int32:
+                raise _lib.PulseError("actor_ids must be int32 (humanoid.py:590)")
+            a.actor_ids = actor_ids.data_ptr()
+        a.env_list, a.actor_list, a.count = ws["env_list"].data_ptr(), ws["actor_list"].data_ptr(), ws["count"].data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.pulse_reset_ref_state(self.motion_lib.handle, C.byref(a), N, _lib.current_stream(dev)), "pulse_reset_ref_state")
+        if obs_buf is not None:   # _compute_observations(env_ids) on the compacted list; its length stays on the device
+            n_list = N if env_ids is None else int(env_ids.shape[0])
+            self.step(body_state=rigid_body_state, progress_buf=progress_buf, motion_ids=motion_ids, motion_start_times=motion_start_times,
+                      motion_start_offset=motion_start_offset, global_offset=global_offset, obs_buf=obs_buf, self_obs_buf=self_obs_buf,
+                      env_ids=ws["env_list"][:n_list], env_count=ws["count"], flags=_lib.STEP_OBS)
+        return ws
 
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
         """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230) with HumanoidIm's `_sample_time` = sample_time_interval."""

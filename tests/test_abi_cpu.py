@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pulse_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in pulse_b200/_lib.py"
-    assert lib.pulse_abi_version() == 1
+    assert lib.pulse_abi_version() == 2
 
 
 def test_struct_sizes_match_header(lib):
@@ -38,14 +38,14 @@ def test_struct_sizes_match_header(lib):
     import subprocess
     import tempfile
     from pulse_b200 import _lib
-    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t), sizeof(pulse_reset_args_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
     assert sizes == [C.sizeof(_lib.MotionLibDesc), C.sizeof(_lib.MotionQuery), C.sizeof(_lib.ImStepArgs), C.sizeof(_lib.AmpObsArgs),
                      C.sizeof(_lib.GaeArgs), C.sizeof(_lib.GemmEpilogue), C.sizeof(_lib.PpoLossArgs), C.sizeof(_lib.VaeLatentArgs),
-                     C.sizeof(_lib.ReachStepArgs), C.sizeof(_lib.LoaderArgs), C.sizeof(_lib.GemmProblem)]
+                     C.sizeof(_lib.ReachStepArgs), C.sizeof(_lib.LoaderArgs), C.sizeof(_lib.GemmProblem), C.sizeof(_lib.ResetArgs)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -111,3 +111,25 @@ def test_new_entry_points_validate_arguments_without_gpu(lib):
     r.reach_body_id, r.enable_early_termination = 23, 1
     assert lib.pulse_reach_step(C.byref(r), 4, None) == -1 and b"termination_heights" in lib.pulse_last_error()
     assert lib.pulse_reach_update_task(ptr, ptr, ptr, ptr, None, 1.0, 0.5, 1.5, 4, None) == -1
+
+
+def test_reset_entry_point_validates_arguments_without_gpu(lib):
+    """pulse_reset_ref_state (row a13 / 8f-3) rejects incomplete argument blocks before any launch."""
+    from pulse_b200 import _lib
+    assert lib.pulse_reset_ref_state(None, None, 4, None) == -1 and b"null" in lib.pulse_last_error()
+    buf = (C.c_float * 256)()
+    ptr = C.cast(buf, C.c_void_p)
+    fake_lib = C.cast((C.c_char * 256)(), C.c_void_p)
+    a = _lib.ResetArgs()
+    assert lib.pulse_reset_ref_state(fake_lib, C.byref(a), 4, None) == -1 and b"mask" in lib.pulse_last_error()
+    a.reset_buf = ptr
+    assert lib.pulse_reset_ref_state(fake_lib, C.byref(a), 4, None) == -1 and b"env_list" in lib.pulse_last_error()
+    a.env_list, a.count = ptr, ptr
+    assert lib.pulse_reset_ref_state(fake_lib, C.byref(a), 4, None) == -1 and b"task buffer" in lib.pulse_last_error()
+    a.motion_ids = a.motion_start_times = a.motion_start_offset = a.global_offset = a.progress_buf = ptr
+    a.root_states = a.dof_pos = a.dof_vel = ptr
+    a.root_env_stride, a.dof_env_stride, a.dof_elem_stride = 5, 138, 2
+    assert lib.pulse_reset_ref_state(fake_lib, C.byref(a), 4, None) == -1 and b"strides" in lib.pulse_last_error()
+    a.root_env_stride = 13
+    a.amp_obs_buf, a.num_amp_steps = ptr, 40
+    assert lib.pulse_reset_ref_state(fake_lib, C.byref(a), 4, None) == -1 and b"num_amp_steps" in lib.pulse_last_error()

@@ -283,6 +283,35 @@ def test_step_16384_envs_matches_oracle():
     assert 0 < int(ref["terminate_buf"].sum()) < 16384
 
 
+def test_getup_recovery_masking_matches_oracle():
+    """HumanoidImGetup._compute_reset (humanoid_im_getup.py:203-210) inside the fused kernel: recovering envs are never reset, their
+    progress counter is pulled back by one and their observation is taken at that earlier time."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.humanoid_im import HumanoidImCompute
+    tb, z, _ = _exact_case(515, 40)
+    g = torch.Generator().manual_seed(4)
+    rec = (torch.rand(515, generator=g) < 0.3).int() * torch.randint(1, 150, (515,), generator=g, dtype=torch.int32)
+    ref = po.humanoid_im_step(tb, po.ImStepConfig(), z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"],
+                              z["start_times"], z["start_offset"], z["global_offset"], z["cycle_counter"], z["reset_buf_in"], recovery_counter=rec)
+    dev = _dev()
+    comp = HumanoidImCompute(_mlib(tb))
+    n = 515
+    prog = z["progress_buf"].to(dev).clone()
+    out = {"obs_buf": torch.zeros(n, 934, device=dev), "rew_buf": torch.zeros(n, device=dev), "reward_raw": torch.zeros(n, 5, device=dev),
+           "reset_buf": torch.full((n,), -1, dtype=torch.long, device=dev), "terminate_buf": torch.full((n,), -1, dtype=torch.long, device=dev)}
+    fd = torch.full((n,), -1.0, device=dev)
+    comp.step(body_state=z["body_state"].to(dev), dof_vel=z["dof_vel"].to(dev), dof_force=z["dof_force"].to(dev), progress_buf=prog,
+              motion_ids=z["motion_ids"].to(dev), motion_start_times=z["start_times"].to(dev), motion_start_offset=z["start_offset"].to(dev),
+              global_offset=z["global_offset"].to(dev), cycle_counter=z["cycle_counter"].to(dev), recovery_counter=rec.to(dev), fdones_out=fd, **out)
+    torch.cuda.synchronize()
+    assert torch.equal(prog.cpu(), ref["progress_buf"]) and int((prog.cpu() != z["progress_buf"]).sum()) == int((rec > 0).sum())
+    assert torch.equal(out["reset_buf"].cpu(), ref["reset_buf"]) and torch.equal(out["terminate_buf"].cpu(), ref["terminate_buf"])
+    assert torch.equal(fd.cpu(), ref["reset_buf"].float())
+    assert int(ref["reset_buf"][rec > 0].sum()) == 0
+    torch.testing.assert_close(out["obs_buf"].cpu(), ref["obs_buf"], atol=OBS_ATOL, rtol=0)
+    torch.testing.assert_close(out["rew_buf"].cpu(), ref["rew_buf"], atol=OBS_ATOL, rtol=0)
+
+
 def test_build_amp_obs_demo_matches_oracle():
     """humanoid_amp.py:253-284: demo AMP observations from the reference motion (MotionLib query + AMP obs)."""
     from oracle import pulse_oracle as po
