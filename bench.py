@@ -90,7 +90,7 @@ def pick_cpu_threads(max_threads):
     for t in sorted({1, 4, 8, 16, 32, 64, max_threads}):
         if t > max_threads:
             continue
-        rate, _ = cpu_port_rate(512, 1, t, gae=True)
+        rate, _ = cpu_port_rate(2048, 1, t, gae=True)      # chosen on the sample that is then timed
         if rate > best_rate:
             best, best_rate = t, rate
     return best
@@ -111,7 +111,17 @@ def cpu_port_rate(n_envs, n_iters, threads, gae=True):
     r, v, nv = (torch.randn(T, n_envs, 1) for _ in range(3))
     d = (torch.rand(T, n_envs) < 0.05).float()
 
+    # per-step env reset of ~5 % of the envs (amp_agent.py:352 -> humanoid.py:526-609, humanoid_amp.py:468-597): the oracle's composite
+    reset_ids = torch.arange(0, n_envs, 20)
+    phase = torch.rand(n_envs)
+    st = {"motion_ids": z["motion_ids"], "start_times": z["start_times"], "start_offset": z["start_offset"], "global_offset": z["global_offset"],
+          "cycle_counter": z["cycle_counter"], "progress_buf": z["progress_buf"], "reset_buf": z["reset_buf_in"],
+          "terminate_buf": z["reset_buf_in"], "root_states": z["body_state"][:, 0].clone(), "dof_pos": z["dof_pos"], "dof_vel": z["dof_vel"],
+          "body_state": z["body_state"], "contact_forces": torch.zeros(n_envs, 24, 3), "amp_obs_buf": amp, "obs_buf": torch.zeros(n_envs, 934),
+          "dof_force": z["dof_force"]}
+
     def one_env_step():
+        po.reset_envs(tb, cfg, st, reset_ids, phase)
         po.humanoid_im_step(tb, cfg, z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"],
                             z["start_times"], z["start_offset"], z["global_offset"], z["cycle_counter"], z["reset_buf_in"])
         return po.amp_obs_step(amp, z["body_state"], z["dof_pos"], z["dof_vel"])
@@ -193,11 +203,15 @@ def run_reference(a):
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * sum(per) / len(per) * (a.envs / n), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": 1e3 * sum(per) / len(per) * (a.envs / n), "extrapolated": True,
+        "sample_seconds_measured": sum(per) / len(per) / (HORIZON * (1 + MINI_EPOCHS)) * 3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, 1, a.envs),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n} envs: 2 env-steps (obs/reward/reset/AMP) + policy/critic/disc fwd + one PPO minibatch fwd/bwd/Adam + GAE, fp32, scaled to a 32-step iteration with 6 mini-epochs; torch {torch.__version__} CPU"},
+                         "sample": f"{n} envs: 2 env-steps (5% env resets + obs/reward/reset/AMP) + policy/critic/disc fwd + one PPO minibatch fwd/bwd/Adam + GAE, "
+                                   f"fp32; value and ms_per_step are EXTRAPOLATED from that sample to a 32-step iteration with 6 mini-epochs of {a.envs} envs "
+                                   f"(thread count chosen on the same 2048-env sample); torch {torch.__version__} CPU"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -210,24 +224,32 @@ def workload_config(a, world, envs_total):
                     f"lognormal lengths, median {a.median_frames} frames @30fps), horizon 32, im.yaml nets (BASELINE configs[3])",
         "envs_total": envs_total, "envs_per_gpu": envs_total // world, "horizon": HORIZON, "minibatch": MINIBATCH,
         "mini_epochs": MINI_EPOCHS, "minibatches_per_epoch_per_gpu": mb, "parallelism": f"env-shard x{world}, grad all-reduce per minibatch",
-        "phases": ["32x [obs normalise + actor/critic MLP fwd (tcgen05) + Gaussian sample (K7-K9) + action -> PD target (K22)]",
-                   "32x fused reward+reset+obs kernel (K1-K5)", "32x AMP obs + history kernel (K6)",
-                   "32x critic fwd on next obs (next_values)", "discriminator fwd + AMP reward over 32xN rows (K10)",
+        "phases": ["32x fused env reset of the done envs, no host sync (pulse_reset_ref_state: compaction, start-time draw, MotionLib query, scatter into "
+                   "root / dof / rigid-body state, AMP history back-fill) + observation of the reset envs (a13)",
+                   "32x [obs normalise + actor/critic MLP fwd (tcgen05) + in-kernel Gaussian sample, neglogp, value de-normalisation, PD targets, "
+                   "written straight into the experience slices (K7-K9, K22)]",
+                   "32x fused progress += 1 + reward + reset + next observation kernel (K1-K5)", "32x AMP observation row written into its experience slice (K6)",
+                   "32x critic fwd on the next obs -> next_values * (1 - terminated)", "discriminator fwd + AMP reward over 32xN rows (K10)",
                    "GAE + returns + adv-norm (K11,K12)", "value/return normalisation (running stats)",
                    f"{MINI_EPOCHS} mini-epochs x minibatches: obs-RMS update, actor/critic fwd, PPO loss, bwd (dgrad+wgrad), "
                    "discriminator loss on 3x4096 AMP rows: BCE + logit reg + weight decay + ANALYTIC gradient penalty (K14), "
                    "NCCL grad all-reduce (N>1), grad-norm clip + Adam incl. bf16 operand mirror (K13,K15,K16)",
                    "AMP demo fetch (MotionLib query + AMP obs), demo / replay ring updates and per-minibatch draws"],
-        "not_yet": [],
+        "not_yet": ["physics (gym.simulate + refresh/set tensor calls): excluded on every arm",
+                    "per-epoch cross-rank RunningMeanStd sync + KL average (hvd.sync_stats / average_value, common_agent.py:126-127, amp_agent.py:524)"
+                    if world > 1 else "cross-rank statistics sync: n/a at 1 GPU",
+                    "rl_games bookkeeping outside the arithmetic: episode reward / length meters, tensorboard / wandb logging, checkpoint writes",
+                    "AMP replay-buffer insertion uses a fixed-size random subset (amp_replay_keep_prob) instead of a Bernoulli mask"],
         "physics": "excluded (Isaac Gym not installable; simulator state tensors are synthetic, resident in HBM)",
         "l2": "256 MiB L2 flush write before every timed iteration; per-iteration working set (tables 3.9 GB + 6 GB rollout buffers at N=1) exceeds L2",
     }
 
 
-# per env-step MLP FLOPs actually executed inside the timed region (2 x MAC), im.yaml nets with K padded 934->960, 1960->1960
+# per env-step ALGORITHMIC MLP FLOPs inside the timed region (2 x MAC), im.yaml nets (K = 934 / 1960: the zero padding to 960 the
+# operands carry is not counted)
 def mlp_flops_per_env_step():
-    a = 960 * 1024 + 1024 * 512 + 512 * 69     # actor fwd MACs
-    c = 960 * 1024 + 1024 * 512 + 512 * 1      # critic fwd MACs
+    a = 934 * 1024 + 1024 * 512 + 512 * 69     # actor fwd MACs
+    c = 934 * 1024 + 1024 * 512 + 512 * 1      # critic fwd MACs
     d = 1960 * 1024 + 1024 * 512 + 512 * 1     # disc fwd MACs
     rollout = a + 2 * c + d                    # actor + critic (values) + critic (next values) + disc reward
     # update: fwd + wgrad for every layer, dgrad for all but the first layer of each net
@@ -292,7 +314,6 @@ def main():
     comp = HumanoidImCompute(ml)
     policy = PPOPolicy(device=dev, seed=0, with_disc=True)   # replicated: same seed on every rank (Horovod broadcast equivalent)
     disc = policy.disc
-    amp_x = torch.zeros(T * n, pad_k(1960), device=dev, dtype=torch.bfloat16)
     AMP_MB = 4096                                        # amp_minibatch_size (im.yaml:81)
     REPLAY = 200000                                      # amp_replay_buffer_size / amp_obs_demo_buffer_size (im.yaml:77-78)
     replay_buf = torch.randn(REPLAY, 1960, device=dev)   # AMP replay ring (amp_agent.py:1043-1057), pre-filled
@@ -301,80 +322,48 @@ def main():
     demo_mb = torch.zeros(num_mb, AMP_MB, 1960, device=dev)
     ring_pos = [0]
 
-    # experience buffers, ENV-MAJOR so a minibatch (512 envs x 32 steps) is a contiguous row range
-    obses = torch.zeros(n, T, 934, device=dev)
-    obs_carry = torch.zeros(n, 934, device=dev)
-    actions = torch.zeros(n, T, 69, device=dev)
-    mus = torch.zeros(n, T, 69, device=dev)
-    neglogp = torch.zeros(n, T, device=dev)
-    amp_obs = torch.zeros(n, T, 1960, device=dev)      # env-major like the other experience tensors
-    values = torch.zeros(T, n, 1, device=dev)
-    next_values = torch.zeros(T, n, 1, device=dev)
-    rewards = torch.zeros(T, n, device=dev)
-    dones = torch.zeros(T, n, device=dev)
-    reward_raw = torch.zeros(n, 5, device=dev)
-    reset_buf = torch.zeros(n, dtype=torch.long, device=dev)
-    term_buf = torch.zeros(n, dtype=torch.long, device=dev)
-    amp_buf = torch.zeros(n, 10, 196, device=dev)
-    progress0 = z["progress_buf"].clone()
+    # ---- the rollout driver: AMPAgent.play_steps on the device (pulse_b200/rollout.py), experience buffers ENV-MAJOR ----------------
+    from pulse_b200.rollout import PlayStepsB200
+    root_states = torch.zeros(n, 1, 13, device=dev)        # _humanoid_root_states view of the actor root tensor (humanoid.py:197-200)
+    root_states[:, 0] = z["body_state"][:, 0]
+    contact = torch.zeros(n, z["body_state"].shape[1], 3, device=dev)
+    sim = dict(body_state=z["body_state"], root_states=root_states[:, 0], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], dof_force=z["dof_force"],
+               progress_buf=z["progress_buf"], motion_ids=z["motion_ids"], motion_start_times=z["motion_start_times"],
+               motion_start_offset=z["motion_start_offset"], global_offset=z["global_offset"], cycle_counter=z["cycle_counter"],
+               contact_forces=contact, actor_ids=torch.arange(n, dtype=torch.int32, device=dev))
     pd_offset, pd_scale = torch.zeros(69, device=dev), torch.full((69,), 1.2, device=dev)   # _build_pd_action_offset_scale (humanoid.py:492-543)
-    pd_tar = torch.zeros(n, 69, device=dev)              # what gym.set_dof_position_target_tensor would receive
+    use_graphs = os.environ.get("PULSE_NO_GRAPHS", "0") != "1"
+    single_graph = os.environ.get("PULSE_ROLLOUT_GRAPH", "1") != "0"
+    ps = PlayStepsB200(comp, policy, sim, horizon=T, pd_offset=pd_offset, pd_scale=pd_scale, use_graphs=use_graphs, single_graph=single_graph,
+                       reset_seed=1000 + rank)
+    ps.first_observation()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # pinned host mirrors for the end-to-end arm
+    # pinned host mirrors for the end-to-end arm: the simulator state is re-uploaded before every env step, rewards / resets read back
     h_body = z["body_state"].cpu().pin_memory()
     h_dof = z["dof_state"].cpu().pin_memory()
     h_force = z["dof_force"].cpu().pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_reset = torch.empty(n, dtype=torch.long).pin_memory()
+    h_reset = torch.empty(n, dtype=torch.float32).pin_memory()
     h_term = torch.empty(n, dtype=torch.long).pin_memory()
     h2d = h_body.numel() * 4 + h_dof.numel() * 4 + h_force.numel() * 4
-    d2h = n * (4 + 8 + 8)
-    step_events, update_events = [], []
-    step_kw = dict(body_state=z["body_state"], dof_vel=z["dof_vel"], dof_force=z["dof_force"], progress_buf=z["progress_buf"],
-                   motion_ids=z["motion_ids"], motion_start_times=z["motion_start_times"], motion_start_offset=z["motion_start_offset"],
-                   global_offset=z["global_offset"], cycle_counter=z["cycle_counter"], reward_raw=reward_raw, reset_buf=reset_buf,
-                   terminate_buf=term_buf)
-    # first observation of the first iteration
-    comp.step(obs_buf=obs_carry, rew_buf=rewards[0], **step_kw)
+    d2h = n * (4 + 4 + 8)
 
-    adv_buf = torch.zeros(T * n, device=dev)
-    ret_buf = torch.zeros(T * n, device=dev)
-    obs_f, act_f, mu_f, nlp_f = obses.view(T * n, 934), actions.view(T * n, 69), mus.view(T * n, 69), neglogp.view(T * n)
+    def upload(t):
+        z["body_state"].copy_(h_body, non_blocking=True)
+        z["dof_state"].copy_(h_dof, non_blocking=True)
+        z["dof_force"].copy_(h_force, non_blocking=True)
 
-    def pre_step(t, e2e):
-        """everything of rollout step t before the fused env kernel"""
-        if e2e:
-            z["body_state"].copy_(h_body, non_blocking=True)
-            z["dof_state"].copy_(h_dof, non_blocking=True)
-            z["dof_force"].copy_(h_force, non_blocking=True)
-        res = policy.act(obses[:, t])                       # get_action_values (common_agent.py:262-288)
-        actions[:, t].copy_(res["actions"])
-        mus[:, t].copy_(res["mus"])
-        neglogp[:, t].copy_(res["neglogpacs"])
-        values[t].copy_(res["values"])
-        pd_targets(res["actions"], pd_offset, pd_scale, out=pd_tar)   # pre_physics_step -> _action_to_pd_targets (K22)
-        z["progress_buf"] += 1                                # physics would run here (excluded); post_physics_step follows
+    def download(t):
+        h_rew.copy_(ps.rewards[t], non_blocking=True)
+        h_reset.copy_(ps.dones[t], non_blocking=True)
+        h_term.copy_(ps.terminate_buf, non_blocking=True)
 
-    def env_step(t):
-        nxt = obses[:, t + 1] if t + 1 < T else obs_carry
-        comp.step(obs_buf=nxt, rew_buf=rewards[t], **step_kw)
-
-    def post_step(t, e2e):
-        nxt = obses[:, t + 1] if t + 1 < T else obs_carry
-        comp.amp_obs(body_state=z["body_state"], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], amp_obs_buf=amp_buf)
-        amp_obs[:, t].copy_(amp_buf.view(n, 1960))
-        dones[t].copy_(reset_buf)
-        nv = policy.critic_values(nxt)                       # _eval_critic on the next obs (amp_agent.py:396-398)
-        next_values[t].copy_(nv * (1.0 - term_buf.unsqueeze(1).float()))
-        if e2e:
-            h_rew.copy_(rewards[t], non_blocking=True)
-            h_reset.copy_(reset_buf, non_blocking=True)
-            h_term.copy_(term_buf, non_blocking=True)
+    update_events = []
+    done_frac = torch.zeros(1, device=dev)
+    obs_f, act_f, mu_f, nlp_f = ps.obses.view(T * n, 934), ps.actions.view(T * n, 69), ps.mus.view(T * n, 69), ps.neglogp.view(T * n)
+    amp_f = ps.amp_obs.view(n * T, 1960)
 
     def post_rollout():
-        # discriminator reward over the whole horizon (amp_agent.py:422-424, :1027-1041)
-        disc_r = disc.rewards(amp_obs.view(n * T, 1960), amp_x)                  # env-major [n*T, 1]
-        mb_rewards = 0.5 * rewards.unsqueeze(-1) + 0.5 * disc_r.view(n, T).t().unsqueeze(-1)   # _combine_rewards, task_w = disc_w = 0.5
         # AMP demo / replay bookkeeping of train_epoch (amp_agent.py:476-483, :998-1001, :1043-1057): new demo samples into the
         # demo ring, this rollout's AMP observations into the replay ring, one random draw per minibatch from each
         new_demo = comp.fetch_amp_obs_demo(512)
@@ -385,22 +374,16 @@ def main():
         idx2 = torch.randint(0, REPLAY, (num_mb * AMP_MB,), device=dev)
         torch.index_select(demo_buf, 0, idx2, out=demo_mb.view(-1, 1960))
         keep = torch.randint(0, n * T, (2048,), device=dev)                       # amp_replay_keep_prob 0.01 of the batch
-        replay_buf[p0:p0 + 2048].copy_(amp_obs.view(n * T, 1960)[keep])
-        adv, ret = discount_values(dones, values, mb_rewards, next_values, normalize_advantage=True)
-        # value / return normalisation in train mode (prepare_dataset, common_agent.py:372-374)
-        policy.value_rms.update(values.view(T, n).t().reshape(T * n, 1))
-        policy.value_rms.update(ret.view(-1, 1))
-        adv_buf.copy_(adv)
-        ret_buf.copy_(policy.value_rms.normalize_values(ret.view(-1, 1)).view(-1))
+        replay_buf[p0:p0 + 2048].copy_(amp_f[keep])
+        ps.finish()            # disc rewards, reward mix, GAE, advantage + value / return normalisation (rollout.py)
+        done_frac.add_(ps.dones.mean())
 
     def update_mb(i):
         r0, r1 = i * MINIBATCH, (i + 1) * MINIBATCH
-        amp_f = amp_obs.view(n * T, 1960)
-        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], adv_buf[r0:r1], ret_buf[r0:r1], old_mu=mu_f[r0:r1], world_size=world,
+        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], ps.adv[r0:r1], ps.ret[r0:r1], old_mu=mu_f[r0:r1], world_size=world,
                                amp=(amp_f[r0:r0 + AMP_MB], replay_mb[i], demo_mb[i]))   # amp_obs[0:amp_minibatch_size] (amp_agent.py:621-628)
 
     # ---- CUDA graphs: every launch sequence with fixed buffers is captured once and replayed -----------------
-    use_graphs = os.environ.get("PULSE_NO_GRAPHS", "0") != "1"
     graphs = {}
     pool = torch.cuda.graph_pool_handle() if use_graphs else None   # replays are sequential: one shared private pool
 
@@ -408,8 +391,10 @@ def main():
         if not use_graphs:
             return fn(*args)
         g = graphs.get(key)
-        if g is None:
-            fn(*args)                                   # eager once (lazy workspaces, one-time attribute calls)
+        if g is None:                                   # first use: eager (lazy workspaces, one-time attribute calls)
+            graphs[key] = False
+            return fn(*args)
+        if g is False:                                  # second use: capture (records only), then replay = this use's one execution
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
@@ -417,23 +402,22 @@ def main():
             graphs[key] = g
         g.replay()
 
+    step_ms = []
+
+    phase_events = []
+
     def iteration(e2e, record):
-        z["progress_buf"].copy_(progress0)
-        obses[:, 0].copy_(obs_carry)
-        for t in range(T):
-            run(("pre", t, e2e), pre_step, t, e2e)
-            if record:
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-            env_step(t)                                      # eager, so the dominant HBM kernel is timed live by events
-            if record:
-                e.record()
-                step_events.append((s, e))
-            run(("post", t, e2e), post_step, t, e2e)
+        ps.host_io = (upload, download) if e2e else None
+        if record:
+            r0, r1, us, ue = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            r0.record()
+        ps.play_steps()
+        if record:
+            r1.record()
         run(("post_rollout",), post_rollout)
         if record:
-            us, ue = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             us.record()
+            phase_events.append((r0, r1, us))
         for _ in range(MINI_EPOCHS):
             for i in range(num_mb):
                 run(("upd", i), update_mb, i)
@@ -461,6 +445,8 @@ def main():
             iteration(e2e, record)
             e.record()
             barrier()
+            if record:
+                step_ms.extend(ps.step_kernel_ms())     # graph-safe events around every fused step kernel of this iteration
             ms = torch.tensor([s.elapsed_time(e)], device=dev)
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -469,11 +455,14 @@ def main():
 
     # count our kernels per iteration once, eagerly (graph replays do not pass through the library's counter)
     use_graphs, saved = False, use_graphs
+    ps.use_graphs = False
     iteration(False, False)
     l0 = lib.pulse_launch_count()
     iteration(False, False)
     launches_eager = lib.pulse_launch_count() - l0
-    use_graphs = saved
+    use_graphs = ps.use_graphs = saved
+    done_frac.zero_()
+    iters_counted = [0]
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -482,9 +471,13 @@ def main():
     ms_e2e, _ = timed(True, max(2, a.steps // 2), False)
 
     torch.cuda.synchronize()
-    k_ms = sorted(s.elapsed_time(e) for s, e in step_events)
+    k_ms = sorted(step_ms)
     k_avg = sum(k_ms) / len(k_ms)
     u_ms = sum(s.elapsed_time(e) for s, e in update_events) / len(update_events)
+    rollout_ms = sum(a0.elapsed_time(a1) for a0, a1, _ in phase_events) / len(phase_events)
+    post_ms = sum(a1.elapsed_time(a2) for _, a1, a2 in phase_events) / len(phase_events)
+    n_iters_total = 2 * a.warmup + a.steps + max(2, a.steps // 2)          # iterations since done_frac was cleared
+    resets_per_step = float(done_frac.item()) / n_iters_total
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -503,7 +496,7 @@ def main():
     env_steps = T * a.envs
     _d = 1960 * 1024 + 1024 * 512 + 512
     _gp = 3 * (512 * 1024 + 1024 * 1960)
-    upd_flops = 2.0 * MINI_EPOCHS * (2 * (960 * 1024 + 1024 * 512 + 512 * 69 + 960 * 1024 + 1024 * 512 + 512)
+    upd_flops = 2.0 * MINI_EPOCHS * (2 * (934 * 1024 + 1024 * 512 + 512 * 69 + 934 * 1024 + 1024 * 512 + 512)
                                      + 2 * 1024 * 512 + 512 * 69 + 512
                                      + 0.75 * (2 * _d + 1024 * 512 + 512) + 0.25 * _gp) * T * n
     if rank == 0:
@@ -514,7 +507,11 @@ def main():
             "config": workload_config(a, world, a.envs),
             "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * h2d * world,
                     "d2h_bytes_per_step": T * d2h * world, "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches_eager), "cuda_graphs": bool(use_graphs), "clocks": clocks,
+            "gpu_launches": int(launches_eager), "cuda_graphs": bool(use_graphs), "rollout_single_graph": bool(use_graphs and single_graph),
+            "clocks": clocks,
+            "phases_ms": {"rollout_32_steps": rollout_ms, "post_rollout": post_ms, "update": u_ms,
+                          "note": "device-resident arm, this rank; rollout = resets + policy + fused step + AMP + next values per step"},
+            "resets_per_env_step": resets_per_step,
             "gemm_switches": {"cta_pairs": os.environ.get("PULSE_GEMM_PAIR", "1") != "0", "pdl": os.environ.get("PULSE_GEMM_PDL", "1") != "0",
                               "grouped_launches": os.environ.get("PULSE_GROUPED", "0") == "1"},
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -533,14 +530,16 @@ def main():
             threads = pick_cpu_threads(os.cpu_count() or 1)
             rate, per_iter = cpu_port_rate(2048, 2, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                                    "sample": "2048 envs: 2 env-steps (obs/reward/reset/AMP) + policy fwd + one PPO minibatch fwd/bwd + GAE "
-                                              "(oracle port of the reference PyTorch path, fp32), scaled to a 32-step iteration"}
+                                    "extrapolated": True,
+                                    "sample": "2048 envs: 2 env-steps (5% env resets + obs/reward/reset/AMP) + policy fwd + one PPO minibatch fwd/bwd + GAE "
+                                              "(oracle port of the reference PyTorch path, fp32), extrapolated to a 32-step iteration with 6 mini-epochs"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing the communicator down: destroy_process_group() was measured to hang at N=2 while CUDA graphs
         # holding captured NCCL kernels are alive.  Everything is done and printed; a barrier keeps the ranks together, then
         # every rank exits 0 directly.
         graphs.clear()
+        ps._graphs.clear()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()

@@ -117,6 +117,7 @@ int pulse_motion_state(const pulse_motionlib_t* lib, const pulse_motion_query_t*
 #define PULSE_STEP_RESET 2u
 #define PULSE_STEP_OBS 4u
 #define PULSE_STEP_ALL 7u
+#define PULSE_STEP_ADVANCE 8u   /* ABI 2: the kernel itself performs `progress_buf += 1` (humanoid.py:1317) through progress_rw before using it */
 
 typedef struct {
   /* simulator state (Isaac Gym views, read-only) */
@@ -190,6 +191,52 @@ typedef struct {
 int pulse_amp_obs(const pulse_amp_obs_args_t* args, int64_t num_envs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Rollout glue of AMPAgent.play_steps (phc/learning/amp_agent.py:341-439), written straight into the experience-buffer slices.
+ *   pulse_policy_post   get_action_values' sampling (common_agent.py:262-288; ModelA2CContinuousLogStd [rl_games]): action = mu +
+ *                       exp(logstd) * eps, neglogp, de-normalised value (running_mean_std.py:84-87), optional PD targets
+ *                       (Humanoid._action_to_pd_targets, humanoid.py:1392-1394).  eps: injected, or Philox4x32-10(seed,
+ *                       row, *rng_offset + rng_step) drawn in the kernel (a device-side offset keeps CUDA-graph replays fresh).
+ *   pulse_value_post    next_values = unnormalise(critic(next obs)) * (1 - terminated)   (amp_agent.py:396-398)
+ *   pulse_amp_obs_row   AMP observation row of this step = [current 196 | first (steps-1)*196 floats of the previous row], written
+ *                       into its experience slice (humanoid_amp.py:622-667 + amp_agent.py:385)
+ *   pulse_bump_counter  *counter += by (one thread): advances the device-side RNG offset once per iteration
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* mu; int64_t ld_mu;            /* [rows, A] actor head output */
+  const float* logstd;                       /* [A] */
+  const float* eps; int64_t ld_eps;          /* [rows, A] injected standard-normal draws, or NULL -> Philox */
+  uint64_t seed; const uint64_t* rng_offset; uint64_t rng_step;
+  int32_t num_actions; int32_t reserved;
+  float* actions; int64_t ld_actions;        /* out */
+  float* neglogp; int64_t ld_neglogp;        /* out, element stride */
+  float* mus_out; int64_t ld_mus;            /* optional copy of mu (NULL when the head GEMM already wrote the experience slice) */
+  const float* value; int64_t ld_value;      /* [rows] normalised critic output (optional) */
+  const double* value_mean; const double* value_var; float value_eps; int32_t reserved2;   /* RunningMeanStd of the value (NULL = identity) */
+  float* values_out; int64_t ld_values;      /* optional */
+  const float* pd_offset; const float* pd_scale; float* pd_targets; int64_t ld_pd;   /* optional */
+} pulse_policy_post_args_t;
+int pulse_policy_post(const pulse_policy_post_args_t* args, int64_t rows, void* stream);
+int pulse_value_post(const float* value, int64_t ld_value, const double* mean, const double* var, float eps, const int64_t* terminate,
+                     float* out, int64_t ld_out, int64_t rows, void* stream);
+typedef struct {
+  const float* body_state; int64_t body_env_stride;
+  const float* dof_pos; const float* dof_vel; int64_t dof_env_stride; int64_t dof_elem_stride;
+  const float* prev; int64_t ld_prev;        /* previous step's row of every env (floats between envs) */
+  float* out; int64_t ld_out;                /* this step's row */
+  int32_t num_steps; int32_t reserved;
+  int32_t* fresh;                            /* [N] optional flags set by pulse_reset_ref_state; cleared here */
+  const float* fresh_rows;                   /* [N, num_steps, 196] the back-filled rows of reset envs */
+} pulse_amp_row_args_t;
+int pulse_amp_obs_row(const pulse_amp_row_args_t* args, int64_t num_envs, void* stream);
+int pulse_bump_counter(uint64_t* counter, uint64_t by, void* stream);
+/* Timing events that stay readable when the launches around them are captured into a CUDA graph (cudaEventRecordExternal): bench.py
+ * times the fused step kernel live inside a whole-rollout graph with these. */
+int pulse_event_create(void** event);
+int pulse_event_destroy(void* event);
+int pulse_event_record(void* event, void* stream);
+int pulse_event_elapsed_ms(void* start, void* stop, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-step env reset, fused and free of host synchronisation.  Replaces, for the envs whose
  * reset_buf is set (mask mode: the `done_indices` of AMPAgent.play_steps, phc/learning/amp_agent.py:352 -> env_reset ->
  * VecTaskPythonWrapper.reset -> Humanoid.reset, humanoid.py:526-541) or for an explicit id list:
@@ -230,6 +277,9 @@ typedef struct {
   int64_t* env_list;             /* [N] out: the reset env ids, ascending (what `nonzero` returns) */
   int32_t* actor_list;           /* [N] out: actor ids of those envs (argument of gym.set_*_tensor_indexed); may be NULL */
   int32_t* count;                /* [1] out, device side: number of reset envs */
+  int32_t* amp_fresh;            /* [N] optional: set to 1 for every reset env -- tells pulse_amp_obs_row to take that env's history from
+                                    amp_obs_buf (the back-filled rows) at the next step */
+  const uint64_t* offset_dev;    /* optional device-side counter added to `offset` (fresh draws on every CUDA-graph replay) */
 } pulse_reset_args_t;
 int pulse_reset_ref_state(const pulse_motionlib_t* lib, const pulse_reset_args_t* args, int64_t num_envs, void* stream);
 

@@ -67,7 +67,29 @@ class ResetArgs(C.Structure):
         ("rigid_body_state", C.c_void_p), ("body_env_stride", C.c_int64),
         ("contact_forces", C.c_void_p), ("contact_env_stride", C.c_int64), ("contact_bodies", C.c_int32),
         ("num_amp_steps", C.c_int32), ("amp_obs_buf", C.c_void_p), ("dt", C.c_float), ("reserved", C.c_int32),
-        ("actor_ids", C.c_void_p), ("env_list", C.c_void_p), ("actor_list", C.c_void_p), ("count", C.c_void_p),
+        ("actor_ids", C.c_void_p), ("env_list", C.c_void_p), ("actor_list", C.c_void_p), ("count", C.c_void_p), ("amp_fresh", C.c_void_p),
+        ("offset_dev", C.c_void_p),
+    ]
+
+
+class PolicyPostArgs(C.Structure):
+    _fields_ = [
+        ("mu", C.c_void_p), ("ld_mu", C.c_int64), ("logstd", C.c_void_p), ("eps", C.c_void_p), ("ld_eps", C.c_int64),
+        ("seed", C.c_uint64), ("rng_offset", C.c_void_p), ("rng_step", C.c_uint64), ("num_actions", C.c_int32), ("reserved", C.c_int32),
+        ("actions", C.c_void_p), ("ld_actions", C.c_int64), ("neglogp", C.c_void_p), ("ld_neglogp", C.c_int64),
+        ("mus_out", C.c_void_p), ("ld_mus", C.c_int64), ("value", C.c_void_p), ("ld_value", C.c_int64),
+        ("value_mean", C.c_void_p), ("value_var", C.c_void_p), ("value_eps", C.c_float), ("reserved2", C.c_int32),
+        ("values_out", C.c_void_p), ("ld_values", C.c_int64),
+        ("pd_offset", C.c_void_p), ("pd_scale", C.c_void_p), ("pd_targets", C.c_void_p), ("ld_pd", C.c_int64),
+    ]
+
+
+class AmpRowArgs(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("body_env_stride", C.c_int64), ("dof_pos", C.c_void_p), ("dof_vel", C.c_void_p),
+        ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64), ("prev", C.c_void_p), ("ld_prev", C.c_int64),
+        ("out", C.c_void_p), ("ld_out", C.c_int64), ("num_steps", C.c_int32), ("reserved", C.c_int32),
+        ("fresh", C.c_void_p), ("fresh_rows", C.c_void_p),
     ]
 
 
@@ -147,7 +169,7 @@ class LoaderArgs(C.Structure):
 ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 Z_SAMPLE, Z_MEAN, Z_RESIDUAL = 0, 1, 2
-STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL = 1, 2, 4, 7
+STEP_REWARD, STEP_RESET, STEP_OBS, STEP_ALL, STEP_ADVANCE = 1, 2, 4, 7, 8
 
 # name -> (restype, argtypes); mirrors include/pulse_b200.h one to one
 SIGNATURES = {
@@ -159,6 +181,14 @@ SIGNATURES = {
     "pulse_motion_state": (C.c_int, [C.c_void_p, C.POINTER(MotionQuery), C.c_int64, C.c_void_p]),
     "pulse_im_step": (C.c_int, [C.c_void_p, C.POINTER(ImStepArgs), C.c_int64, C.c_void_p]),
     "pulse_reset_ref_state": (C.c_int, [C.c_void_p, C.POINTER(ResetArgs), C.c_int64, C.c_void_p]),
+    "pulse_policy_post": (C.c_int, [C.POINTER(PolicyPostArgs), C.c_int64, C.c_void_p]),
+    "pulse_value_post": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "pulse_amp_obs_row": (C.c_int, [C.POINTER(AmpRowArgs), C.c_int64, C.c_void_p]),
+    "pulse_bump_counter": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "pulse_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "pulse_event_destroy": (C.c_int, [C.c_void_p]),
+    "pulse_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pulse_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "pulse_amp_obs": (C.c_int, [C.POINTER(AmpObsArgs), C.c_int64, C.c_void_p]),
     "pulse_gae": (C.c_int, [C.POINTER(GaeArgs), C.c_int32, C.c_int64, C.c_void_p]),
     "pulse_normalize_advantages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -244,3 +274,26 @@ def ptr(t):
 def current_stream(device=None):
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class GraphEvent:
+    """CUDA event recorded with cudaEventRecordExternal: usable for timing INSIDE captured CUDA graphs (every replay re-records it)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(load().pulse_event_create(C.byref(self._h)), "pulse_event_create")
+
+    def record(self, device=None):
+        check(load().pulse_event_record(self._h, current_stream(device)), "pulse_event_record")
+
+    def elapsed_ms(self, stop: "GraphEvent") -> float:
+        ms = C.c_float()
+        check(load().pulse_event_elapsed_ms(self._h, stop._h, C.byref(ms)), "pulse_event_elapsed_ms")
+        return float(ms.value)
+
+    def __del__(self):
+        try:
+            if self._h:
+                load().pulse_event_destroy(self._h)
+        except Exception:
+            pass

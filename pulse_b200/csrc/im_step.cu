@@ -178,10 +178,14 @@ __device__ __forceinline__ void plan_batch(const pulse_motionlib_desc_t& lib, co
   PlanEntry& E = slot[gb][ks];
   if (group < ngroups && widx < num_envs) {
     const long long e = a.env_ids != nullptr ? a.env_ids[widx] : widx;
-    const long long prog = a.progress_buf[e];
+    long long prog = a.progress_buf[e];
     // HumanoidImGetup._compute_reset (humanoid_im_getup.py:203-210): a recovering env does not advance its progress counter, so its
     // observation is taken at (prog - 1) + 1
     const int rec = (do_reset && a.recovery_counter != nullptr) ? (a.recovery_counter[e] > 0 ? 1 : 0) : 0;
+    if (a.flags & PULSE_STEP_ADVANCE) {   // `self.progress_buf += 1` of post_physics_step (humanoid.py:1317) done here
+      prog += 1;
+      if (!rec) a.progress_rw[e] = prog;  // a recovering env's counter is written once, by the reset epilogue (prog - 1)
+    }
     const long long mid = a.motion_ids[e];
     const float t_start = a.motion_start_times[e];
     const float t_off = a.motion_start_offset[e];
@@ -580,7 +584,8 @@ extern "C" int pulse_im_step(const pulse_motionlib_t* lib, const pulse_im_step_a
   if (num_envs == 0) return PULSE_OK;
   const pulse_im_step_args_t& a = *args;
   PULSE_REQUIRE(a.env_count == nullptr || a.env_ids != nullptr, "pulse_im_step: env_count limits an env_ids list");
-  PULSE_REQUIRE((a.flags & PULSE_STEP_ALL) != 0 && (a.flags & ~PULSE_STEP_ALL) == 0, "pulse_im_step: bad flags 0x%x", a.flags);
+  PULSE_REQUIRE((a.flags & PULSE_STEP_ALL) != 0 && (a.flags & ~(PULSE_STEP_ALL | PULSE_STEP_ADVANCE)) == 0, "pulse_im_step: bad flags 0x%x", a.flags);
+  PULSE_REQUIRE(!(a.flags & PULSE_STEP_ADVANCE) || a.progress_rw != nullptr, "pulse_im_step: PULSE_STEP_ADVANCE needs the writable progress_rw");
   PULSE_REQUIRE(a.body_state && a.progress_buf && a.motion_ids && a.motion_start_times && a.motion_start_offset &&
                     a.global_offset, "pulse_im_step: null state/task buffer");
   PULSE_REQUIRE(a.body_env_stride >= PULSE_NUM_BODIES * PULSE_BODY_STATE_W, "pulse_im_step: body_env_stride %lld < 312",

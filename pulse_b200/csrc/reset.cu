@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) reset_ref_state_kernel(const pulse_motion
     const float mlen = lib.lengths[mid];
     float ph;
     if (a.phase != nullptr) ph = a.phase[e];
-    else ph = philox_uniform(a.seed, static_cast<unsigned long long>(e), a.offset);
+    else ph = philox_uniform(a.seed, static_cast<unsigned long long>(e), a.offset + (a.offset_dev != nullptr ? *a.offset_dev : 0ull));
     // ((phase * motion_len) / curr_fps).long() * curr_fps
     const float t0 = __fmul_rn(__ll2float_rn(static_cast<long long>(__fdiv_rn(__fmul_rn(ph, mlen), step30))), step30);
     // _init_amp_obs_ref: motion_times + (-dt * (arange + 1)) (humanoid_amp.py:540-542); k = 0 is the reset pose itself
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256) reset_ref_state_kernel(const pulse_motion
         a.progress_buf[e] = 0;
         if (a.reset_buf != nullptr) a.reset_buf[e] = 0;
         if (a.terminate_buf != nullptr) a.terminate_buf[e] = 0;
+        if (a.amp_fresh != nullptr) a.amp_fresh[e] = 1;
       }
     }
     if (a.amp_obs_buf == nullptr) continue;

@@ -74,7 +74,7 @@ class HumanoidImCompute:
              ref_body_pos=None, ref_body_vel=None, ref_body_rot=None, ref_dof_pos=None,
              env_ids: Optional[torch.Tensor] = None, flags: int = _lib.STEP_ALL, num_envs: Optional[int] = None,
              env_count: Optional[torch.Tensor] = None, recovery_counter: Optional[torch.Tensor] = None,
-             fdones_out: Optional[torch.Tensor] = None) -> None:
+             fdones_out: Optional[torch.Tensor] = None, advance: bool = False) -> None:
         """One fused launch.  `body_state` is the [N, bodies_per_env, 13] rigid-body-state view (or its
         [:, :24] slice); `dof_vel` may be the strided Isaac Gym view dof_state[..., 1]."""
         c = self.cfg
@@ -152,6 +152,9 @@ class HumanoidImCompute:
             if fdones_out.dtype != torch.float32 or not fdones_out.is_contiguous():
                 raise _lib.PulseError("fdones_out must be contiguous float32 [N]")
             a.fdones_out = fdones_out.data_ptr()
+        if advance:                                   # `self.progress_buf += 1` (humanoid.py:1317) inside the launch
+            a.flags = flags | _lib.STEP_ADVANCE
+            a.progress_rw = progress_buf.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_im_step(self.motion_lib.handle, C.byref(a), n, _lib.current_stream(self.device)), "pulse_im_step")
 
@@ -173,6 +176,28 @@ class HumanoidImCompute:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_amp_obs(C.byref(a), int(body_state.shape[0]), _lib.current_stream(self.device)), "pulse_amp_obs")
 
+
+    def amp_obs_row(self, *, body_state: torch.Tensor, dof_pos: torch.Tensor, dof_vel: torch.Tensor, prev: torch.Tensor, out: torch.Tensor,
+                    fresh: Optional[torch.Tensor] = None, fresh_rows: Optional[torch.Tensor] = None) -> None:
+        """This step's AMP observation row of every env, [current 196 | the previous row's first (steps-1)*196 floats], written straight
+        into its experience slice `out` [N, steps*196] (any row stride) from the previous step's slice `prev` -- `_update_hist_amp_obs`
+        + `_compute_amp_observations` + the experience-buffer copy (humanoid_amp.py:622-667, amp_agent.py:385) without moving the
+        history twice.  Envs flagged in `fresh` (set by `reset_envs`) take their history from `fresh_rows` [N, steps, 196]."""
+        a = _lib.AmpRowArgs()
+        a.body_state, a.body_env_stride = _strided(body_state, 13)
+        if dof_pos.stride() != dof_vel.stride():
+            raise _lib.PulseError("dof_pos and dof_vel must share strides (views of one dof-state tensor)")
+        a.dof_pos, a.dof_vel, a.dof_env_stride, a.dof_elem_stride = dof_pos.data_ptr(), dof_vel.data_ptr(), dof_pos.stride(0), dof_pos.stride(1)
+        steps = out.shape[-1] // AMP_OBS
+        if out.shape[-1] != steps * AMP_OBS or prev.shape != out.shape or out.stride(-1) != 1 or prev.stride(-1) != 1:
+            raise _lib.PulseError("prev / out must be [N, steps*196] views with contiguous rows")
+        a.prev, a.ld_prev, a.out, a.ld_out, a.num_steps = prev.data_ptr(), prev.stride(0), out.data_ptr(), out.stride(0), steps
+        if fresh is not None:
+            if fresh.dtype != torch.int32 or fresh_rows is None or not fresh_rows.is_contiguous():
+                raise _lib.PulseError("fresh must be int32 [N] and come with contiguous fresh_rows [N, steps, 196]")
+            a.fresh, a.fresh_rows = fresh.data_ptr(), fresh_rows.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_amp_obs_row(C.byref(a), int(body_state.shape[0]), _lib.current_stream(self.device)), "pulse_amp_obs_row")
 
     # ------------------------------------------------------------------------------------------
     def build_amp_obs_demo(self, motion_ids: torch.Tensor, motion_times0: torch.Tensor, num_steps: Optional[int] = None,
@@ -200,7 +225,8 @@ class HumanoidImCompute:
                    cycle_counter: Optional[torch.Tensor] = None, contact_forces: Optional[torch.Tensor] = None,
                    amp_obs_buf: Optional[torch.Tensor] = None, actor_ids: Optional[torch.Tensor] = None,
                    phase: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, obs_buf: Optional[torch.Tensor] = None,
-                   self_obs_buf: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                   self_obs_buf: Optional[torch.Tensor] = None, amp_fresh: Optional[torch.Tensor] = None,
+                   offset_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """The per-step env reset of the rollout loop (`self.obs = self.env_reset(done_indices)`, amp_agent.py:352 ->
         Humanoid.reset -> _reset_envs, humanoid.py:526-587, humanoid_amp.py:347-356, :468-488, :519-597, humanoid_im.py:921-989)
         WITHOUT a host round trip: `pulse_reset_ref_state` (device-side compaction of `reset_buf` -- or the explicit `env_ids` --
@@ -260,6 +286,12 @@ class HumanoidImCompute:
                 raise _lib.PulseError("actor_ids must be int32 (humanoid.py:590)")
             a.actor_ids = actor_ids.data_ptr()
         a.env_list, a.actor_list, a.count = ws["env_list"].data_ptr(), ws["actor_list"].data_ptr(), ws["count"].data_ptr()
+        if amp_fresh is not None:
+            if amp_fresh.dtype != torch.int32 or amp_fresh.shape[0] != N:
+                raise _lib.PulseError("amp_fresh must be int32 [N]")
+            a.amp_fresh = amp_fresh.data_ptr()
+        if offset_dev is not None:                    # int64 / uint64 device counter added to `offset`
+            a.offset_dev = offset_dev.data_ptr()
         with torch.cuda.device(dev):
             _lib.check(self.lib.pulse_reset_ref_state(self.motion_lib.handle, C.byref(a), N, _lib.current_stream(dev)), "pulse_reset_ref_state")
         if obs_buf is not None:   # _compute_observations(env_ids) on the compacted list; its length stays on the device

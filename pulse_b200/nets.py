@@ -208,7 +208,8 @@ class MLP:
                     ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
                     tiles = ((l.N + 127) // 128) * ((l.Kp + 255) // 256)   # 128 x 256 output tiles
                     ws["split"].append(pick_split(tiles, (M + 63) // 64))
-            ws["out"] = torch.zeros(M, self.layers[-1].N, device=dev)
+            hn = self.layers[-1].N     # fp32 head output: rows padded to a multiple of 4 floats so the epilogue's 16-byte stores apply (N = 69)
+            ws["out"] = torch.zeros(M, (hn + 3) // 4 * 4, device=dev)[:, :hn]
             if train and self.input_grad_cols:
                 ws["dx"] = torch.zeros(M, self.input_grad_cols, device=dev)
             self._ws[key] = ws

@@ -108,6 +108,8 @@ class PPOPolicy:
         self.stats = torch.zeros(6, dtype=torch.float64, device=self.device)
         self.lib = _lib.load()
         self._side = None
+        self.rng_seed = (int(seed) * 0x9E3779B97F4A7C15 + 0x243F6A8885A308D3) & (2 ** 64 - 1)
+        self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)    # uint64 counter read by the sampling kernel
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, M: int, train: bool):
@@ -146,6 +148,50 @@ class PPOPolicy:
         values = self.value_rms.unnormalize(value) if self.value_rms is not None else value
         return {"actions": b["actions"], "neglogpacs": b["neglogp"], "values": values, "mus": mu,
                 "sigmas": torch.exp(self.logstd).expand(M, self.A)}
+
+    def act_into(self, obs: torch.Tensor, *, actions: torch.Tensor, neglogp: torch.Tensor, mus: torch.Tensor, values: Optional[torch.Tensor] = None,
+                 pd: Optional[tuple] = None, eps: Optional[torch.Tensor] = None, rng_step: int = 0) -> None:
+        """get_action_values (common_agent.py:262-288) + the experience-buffer updates of play_steps (amp_agent.py:361-378) + the PD
+        targets of pre_physics_step (humanoid.py:1222-1257) with NO intermediate copies: the actor head GEMM writes `mus` (a
+        [M, A] slice of the experience buffer, any row stride), `pulse_policy_post` draws the noise in-kernel (Philox; `eps`
+        injects it for tests) and writes actions / neglogp / de-normalised values / PD targets through (pointer, stride).
+        pd = (offset [A], scale [A], out [M, A])."""
+        M = obs.shape[0]
+        b = self._buf(M, False)
+        self.obs_rms.normalize_into(obs, b["x"])
+        self.actor.forward(b["x"], out=mus)
+        value = self.critic.forward(b["x"]) if values is not None else None
+        a = _lib.PolicyPostArgs(mu=mus.data_ptr(), ld_mu=mus.stride(0), logstd=self.logstd.data_ptr(), seed=self.rng_seed,
+                                rng_offset=self.rng_offset.data_ptr(), rng_step=int(rng_step), num_actions=self.A,
+                                actions=actions.data_ptr(), ld_actions=actions.stride(0), neglogp=neglogp.data_ptr(), ld_neglogp=neglogp.stride(0))
+        if eps is not None:
+            a.eps, a.ld_eps = eps.data_ptr(), eps.stride(0)
+        if values is not None:
+            a.value, a.ld_value, a.values_out, a.ld_values = value.data_ptr(), value.stride(0), values.data_ptr(), values.stride(0)
+            if self.value_rms is not None:
+                a.value_mean, a.value_var, a.value_eps = self.value_rms.running_mean.data_ptr(), self.value_rms.running_var.data_ptr(), self.value_rms.eps
+        if pd is not None:
+            a.pd_offset, a.pd_scale, a.pd_targets, a.ld_pd = pd[0].data_ptr(), pd[1].data_ptr(), pd[2].data_ptr(), pd[2].stride(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_policy_post(C.byref(a), M, _lib.current_stream(self.device)), "pulse_policy_post")
+
+    def critic_values_into(self, obs: torch.Tensor, out: torch.Tensor, terminate: Optional[torch.Tensor] = None) -> None:
+        """`next_vals = self._eval_critic(self.obs); next_vals *= (1.0 - terminated)` (amp_agent.py:396-398) into `out` ([M] / [M,1] view)."""
+        M = obs.shape[0]
+        b = self._buf(M, False)
+        self.obs_rms.normalize_into(obs, b["x"])
+        value = self.critic.forward(b["x"])
+        rms = self.value_rms
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_value_post(value.data_ptr(), value.stride(0), rms.running_mean.data_ptr() if rms is not None else None,
+                                                 rms.running_var.data_ptr() if rms is not None else None, rms.eps if rms is not None else 0.0,
+                                                 _lib.ptr(terminate), out.data_ptr(), out.stride(0), M, _lib.current_stream(self.device)),
+                       "pulse_value_post")
+
+    def advance_rng(self, steps: int) -> None:
+        """Moves the device-side Philox offset past the `steps` draws of a rollout (keeps CUDA-graph replays statistically fresh)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_bump_counter(self.rng_offset.data_ptr(), int(steps), _lib.current_stream(self.device)), "pulse_bump_counter")
 
     def critic_values(self, obs: torch.Tensor) -> torch.Tensor:
         """_eval_critic (common_agent.py:552-562)."""

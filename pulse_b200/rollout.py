@@ -34,3 +34,177 @@ def discount_values(mb_fdones: torch.Tensor, mb_values: torch.Tensor, mb_rewards
         if normalize_advantage:
             _lib.check(lib.pulse_normalize_advantages(adv.data_ptr(), stats.data_ptr(), N * T, st), "pulse_normalize_advantages")
     return adv, ret
+
+
+class PlayStepsB200:
+    """`AMPAgent.play_steps` (phc/learning/amp_agent.py:341-439) on the device: for every step of the horizon
+         env_reset(done envs) -> get_action_values -> env step (post-physics compute) -> AMP observation -> next values,
+    then the discriminator rewards / reward mix / GAE / value normalisation of `play_steps` + `prepare_dataset`
+    (amp_agent.py:418-437, common_agent.py:357-398).  Every kernel writes straight into the ENV-MAJOR experience buffers
+    (`obses[n, T, 934]`, ...: a PPO minibatch is a contiguous row range, there is no swap_and_flatten01 copy); no ATen elementwise op,
+    no host synchronisation and no boolean-mask indexing is left inside the loop.  Physics is the caller's: `physics(t)` is invoked
+    between the action and the post-physics compute (bench.py passes nothing -- Isaac Gym is not installable).
+
+    `sim`: the simulator's tensors, read / written IN PLACE through their strides (Isaac Gym views):
+        body_state [N,B>=24,13], root_states [N,13] view, dof_pos / dof_vel [N,69] views, dof_force [N,69], progress_buf,
+        motion_ids, motion_start_times, motion_start_offset, global_offset, cycle_counter (+ optional contact_forces, actor_ids).
+    Launch structure: the work between two env steps (AMP row + next values of step t-1, resets + actions of step t) is one CUDA-graph
+    segment; with `single_graph` the whole horizon including the fused step kernels is ONE graph and the step kernel is timed through
+    graph-safe events (`_lib.GraphEvent`)."""
+
+    def __init__(self, comp, policy, sim: dict, horizon: int = 32, task_reward_w: float = 0.5, disc_reward_w: float = 0.5,
+                 pd_offset: torch.Tensor = None, pd_scale: torch.Tensor = None, use_graphs: bool = True, single_graph: bool = False,
+                 gamma: float = 0.99, tau: float = 0.95, reset_seed: int = 0, time_steps: bool = True):
+        self.comp, self.policy, self.sim, self.T = comp, policy, sim, int(horizon)
+        self.dev = comp.device
+        n = self.n = int(sim["progress_buf"].shape[0])
+        T, dev = self.T, self.dev
+        z = lambda *s, **k: torch.zeros(*s, device=dev, **k)
+        self.obses, self.obs_carry = z(n, T, 934), z(n, 934)
+        self.actions, self.mus, self.neglogp = z(n, T, policy.A), z(n, T, policy.A), z(n, T)
+        self.amp_obs = z(n, T, 1960)
+        self.values, self.next_values = z(T, n, 1), z(T, n, 1)
+        self.rewards, self.dones = z(T, n), z(T, n)
+        self.reward_raw = z(n, 5)
+        self.reset_buf, self.terminate_buf = z(n, dtype=torch.long), z(n, dtype=torch.long)
+        self.amp_init, self.amp_fresh = z(n, 10, 196), z(n, dtype=torch.int32)
+        self.pd_tar = z(n, policy.A)
+        self.pd = (pd_offset if pd_offset is not None else z(policy.A), pd_scale if pd_scale is not None else torch.ones(policy.A, device=dev))
+        self.adv, self.ret = z(n * T), z(n * T)
+        self.task_w, self.disc_w, self.gamma, self.tau = task_reward_w, disc_reward_w, gamma, tau
+        self.reset_seed = (int(reset_seed) * 0x9E3779B97F4A7C15 + 0x13198A2E03707344) & (2 ** 64 - 1)
+        self.use_graphs, self.single_graph, self.time_steps = use_graphs, single_graph, time_steps
+        self._graphs, self._pool = {}, None
+        self.step_events = [(_lib.GraphEvent(), _lib.GraphEvent()) for _ in range(T)] if time_steps else None
+        self.amp_x = None
+        self.host_io = None            # bench.py's end-to-end arm: (upload(t), download(t)) callables
+        self.physics = None
+
+    # ------------------------------------------------------------------ the pieces of one step
+    def _step_kw(self):
+        s = self.sim
+        return dict(body_state=s["body_state"], dof_vel=s["dof_vel"], dof_force=s["dof_force"], progress_buf=s["progress_buf"],
+                    motion_ids=s["motion_ids"], motion_start_times=s["motion_start_times"], motion_start_offset=s["motion_start_offset"],
+                    global_offset=s["global_offset"], cycle_counter=s.get("cycle_counter"), reward_raw=self.reward_raw,
+                    reset_buf=self.reset_buf, terminate_buf=self.terminate_buf)
+
+    def _reset_and_act(self, t: int) -> None:
+        """`self.obs = self.env_reset(done_indices)` (amp_agent.py:352) + `get_action_values` + experience updates (:355-378) + PD targets."""
+        s, pol = self.sim, self.policy
+        self.comp.reset_envs(motion_ids=s["motion_ids"], motion_start_times=s["motion_start_times"], motion_start_offset=s["motion_start_offset"],
+                             global_offset=s["global_offset"], progress_buf=s["progress_buf"], root_states=s["root_states"], dof_pos=s["dof_pos"],
+                             dof_vel=s["dof_vel"], rigid_body_state=s["body_state"], reset_buf=self.reset_buf, terminate_buf=self.terminate_buf,
+                             cycle_counter=s.get("cycle_counter"), contact_forces=s.get("contact_forces"), amp_obs_buf=self.amp_init,
+                             actor_ids=s.get("actor_ids"), seed=self.reset_seed, offset=t, offset_dev=pol.rng_offset, obs_buf=self.obses[:, t],
+                             amp_fresh=self.amp_fresh)
+        pol.act_into(self.obses[:, t], actions=self.actions[:, t], neglogp=self.neglogp[:, t], mus=self.mus[:, t], values=self.values[t],
+                     pd=(self.pd[0], self.pd[1], self.pd_tar), rng_step=t)
+
+    def _next_obs(self, t: int) -> torch.Tensor:
+        return self.obses[:, t + 1] if t + 1 < self.T else self.obs_carry
+
+    def _env_step(self, t: int) -> None:
+        """post_physics_step (humanoid.py:1315-1346): progress += 1, reward, reset, next observation -- one fused launch."""
+        ev = self.step_events[t] if self.step_events is not None else None
+        if ev is not None:
+            ev[0].record(self.dev)
+        self.comp.step(obs_buf=self._next_obs(t), rew_buf=self.rewards[t], fdones_out=self.dones[t], advance=True, **self._step_kw())
+        if ev is not None:
+            ev[1].record(self.dev)
+
+    def _after_step(self, t: int) -> None:
+        """AMP observation row of step t (humanoid_amp.py:194-210, amp_agent.py:385) and next_values (:396-398)."""
+        s = self.sim
+        prev = self.amp_obs[:, t - 1] if t > 0 else self.amp_obs[:, self.T - 1]
+        self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
+                              fresh=self.amp_fresh, fresh_rows=self.amp_init)
+        self.policy.critic_values_into(self._next_obs(t), self.next_values[t].view(-1), terminate=self.terminate_buf)
+
+    def _segment(self, t: int) -> None:
+        """Everything between env step t-1 and env step t."""
+        if t > 0:
+            self._after_step(t - 1)
+            if self.host_io is not None:
+                self.host_io[1](t - 1)
+        if t < self.T:
+            if self.host_io is not None:
+                self.host_io[0](t)
+            self._reset_and_act(t)
+
+    # ------------------------------------------------------------------ graphs
+    def _run(self, key, fn, *args):
+        if not self.use_graphs:
+            return fn(*args)
+        g = self._graphs.get(key)
+        if g is None:
+            # first use: plain eager execution (lazy workspaces, one-time attribute calls).  The segments are NOT idempotent (progress
+            # counters advance, reset / fresh flags are consumed), so nothing may run twice: the capture happens on the second use,
+            # where it only records, and the replay that follows is that use's single execution.
+            self._graphs[key] = False
+            return fn(*args)
+        if g is False:
+            torch.cuda.synchronize(self.dev)
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool):
+                fn(*args)
+            self._graphs[key] = g
+        g.replay()
+
+    def _whole(self) -> None:
+        for t in range(self.T):
+            self._segment(t)
+            if self.physics is not None:
+                self.physics(t)
+            self._env_step(t)
+        self._segment(self.T)
+
+    def play_steps(self) -> None:
+        """One horizon.  The first observation of the iteration is the last next-observation of the previous one."""
+        self.obses[:, 0].copy_(self.obs_carry)
+        io = self.host_io is not None
+        if self.single_graph and self.physics is None:
+            self._run(("rollout", io), self._whole)
+        else:
+            for t in range(self.T):
+                self._run(("seg", t, io), self._segment, t)
+                if self.physics is not None:
+                    self.physics(t)
+                self._env_step(t)
+            self._run(("seg", self.T, io), self._segment, self.T)
+
+    def first_observation(self) -> None:
+        """Observation of the initial state (Humanoid.reset -> _compute_observations at start-up): fills `obs_carry`."""
+        kw = self._step_kw()
+        self.comp.step(obs_buf=self.obs_carry, rew_buf=self.rewards[0], **kw)
+        self.reset_buf.zero_()
+        self.terminate_buf.zero_()
+
+    def step_kernel_ms(self):
+        """Live durations of the fused step kernel launches of the LAST horizon (graph-safe events)."""
+        return [a.elapsed_ms(b) for a, b in self.step_events] if self.step_events is not None else []
+
+    # ------------------------------------------------------------------ after the horizon
+    def finish(self) -> None:
+        """Discriminator rewards over the whole horizon (amp_agent.py:422-424, :1027-1041), `_combine_rewards` (:1011-1025), GAE +
+        returns (common_agent.py:493-505), advantage normalisation (:589-599), value / return normalisation in training mode
+        (prepare_dataset :372-374: each tensor is normalised with the statistics BEFORE its own merge, running_mean_std.py:69-109)."""
+        pol, n, T = self.policy, self.n, self.T
+        if pol.disc is not None:
+            if self.amp_x is None:
+                from .nets import pad_k
+                self.amp_x = torch.zeros(T * n, pad_k(1960), device=self.dev, dtype=torch.bfloat16)
+            disc_r = pol.disc.rewards(self.amp_obs.view(n * T, 1960), self.amp_x)                    # env-major [n*T, 1]
+            mb_rewards = self.task_w * self.rewards.unsqueeze(-1) + self.disc_w * disc_r.view(n, T).t().unsqueeze(-1)
+        else:
+            mb_rewards = self.rewards.unsqueeze(-1)
+        adv, ret = discount_values(self.dones, self.values, mb_rewards, self.next_values, gamma=self.gamma, tau=self.tau, normalize_advantage=True)
+        self.adv.copy_(adv)
+        if pol.value_rms is not None:
+            pol.value_rms.update(self.values.view(T * n, 1))                         # values: normalised copy unused (clip_value False), stats merged
+            self.ret.copy_(pol.value_rms.normalize_values(ret.view(-1, 1)).view(-1))  # returns see the statistics that include the values batch ...
+            pol.value_rms.update(ret.view(-1, 1))                                    # ... and are merged afterwards
+        else:
+            self.ret.copy_(ret)
+        pol.advance_rng(T)
