@@ -335,6 +335,12 @@ typedef struct {
   int32_t accumulate;        /* 1: out_f32 += result with fp32 atomics (weight gradients; caller zeroes), 0: overwrite */
   int32_t reserved;
   double* sumsq;             /* *sumsq += sum of squares of the final values over the valid [M,N] region (fp64 atomics), or NULL */
+  /* ---- ABI 2: ReLU masks as bit words.  Forward: bit i of relu_mask[(col/32) * ld_rmask + row] = (pre-activation of column
+   * 32*(col/32)+i of `row`) > 0, written next to the bf16 activations (2 MB instead of the 32 MB the backward pass used to re-read
+   * for a 16384 x 1024 layer).  ReLU-dgrad: gate_mask in the same layout replaces `gate`: one coalesced 4-byte load per
+   * (row, 32-column chunk).  Chunk-major ([ceil(N/32), ld] words, ld >= M) so that consecutive rows are consecutive words. */
+  uint32_t* relu_mask; int64_t ld_rmask;
+  const uint32_t* gate_mask; int64_t ld_gmask;
 } pulse_gemm_epilogue_t;
 
 #define PULSE_GEMM_A_MN 1u   /* A is given as [K, M] row-major (the reduction dimension is the ROW index) */
@@ -370,9 +376,11 @@ int pulse_gemm_bf16_grouped(const pulse_gemm_problem_t* problems, int32_t count,
 /* RunningMeanStd.forward, eval path (phc/utils/running_mean_std.py:69-95): y = clamp((x-mean)*rstd, -5, 5),
  * written as bf16 [rows, ld_out] (columns >= cols zero-filled up to ld_out) and optionally transposed
  * bf16 [ld_out, ld_t] (operand of the first layer's wgrad).  mean / rstd: fp32 [cols] (rstd = 1/sqrt(var+eps),
- * prepared by the caller from the fp64 statistics); NULL mean = plain cast. */
+ * prepared by the caller from the fp64 statistics); NULL mean = plain cast.  pad_one: value of the FIRST pad column (index cols) when
+ * ld_out > cols -- 1.0 makes it the "ones" column of a bias-augmented GEMM operand (the layer's bias then sits in column `cols` of its
+ * weight matrix: bias add and bias gradient ride the tensor cores), 0.0 = plain zero fill. */
 int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
-                            pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, void* stream);
+                            pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, float pad_one, void* stream);
 
 /* Batch moments for RunningMeanStd's training-mode update (:96-107): per-column sum and sum of squares of
  * fp32 x [rows, cols] accumulated in fp64 into sums[2*cols] (caller zeroes). */
@@ -382,7 +390,7 @@ int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols
  * (phc/utils/running_mean_std.py:91-107) normalises with the statistics from before the batch and merges the
  * batch afterwards, so both read the same rows.  out [rows, ld_out] (padding columns zeroed), sums[2*cols] += . */
 int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
-                            pulse_bf16_t* out, int64_t ld_out, double* sums, void* stream);
+                            pulse_bf16_t* out, int64_t ld_out, double* sums, float pad_one, void* stream);
 
 /* RunningMeanStd._update_mean_var_count_from_moments (:54-66) on the device: merges the batch sums of
  * pulse_column_moments (n rows) into the fp64 running mean / var / count and refreshes the fp32 mean / rstd
@@ -441,6 +449,14 @@ int pulse_disc_loss(const float* logits, int64_t ld, int64_t n_agent, int64_t n_
 int pulse_relu_mask_scale(const pulse_bf16_t* h, int64_t ldh, int64_t rows, int64_t cols, const float* w, pulse_bf16_t* out, int64_t ldo,
                           void* stream);
 int pulse_axpy(float a, const float* x, float* y, int64_t count, void* stream);
+/* Weight decay / logit regulariser gradients + the sums of squares of the logged terms for up to four weight blocks in one launch
+ * (AMPAgent._disc_loss, amp_agent.py:905-908, :932-937): g[r,c] += coef * w[r,c] for c < cols of a [rows, ld] matrix; *sumsq (and
+ * *sumsq2) += sum w^2 in fp64.  g / sumsq / sumsq2 may be NULL. */
+typedef struct {
+  const float* w; float* g; int64_t rows, cols, ld; float coef; int32_t reserved; double* sumsq; double* sumsq2;
+} pulse_weight_block_t;
+typedef struct { pulse_weight_block_t block[4]; int32_t count; int32_t reserved; } pulse_weight_reg_t;
+int pulse_weight_reg(const pulse_weight_reg_t* desc, void* stream);
 
 /* out[c] (+)= sum over rows of bf16 x[rows, ldx] (bias gradients). */
 int pulse_column_sum_bf16(const pulse_bf16_t* x, int64_t ldx, int64_t rows, int64_t cols, float* out, void* stream);
@@ -452,9 +468,12 @@ int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream
  * defaults beta 0.9/0.999): scale = min(1, max_norm/(sqrt(sumsq)+1e-6)) read on the device, no host sync. */
 /* `step` is a DEVICE counter (int32[1]) incremented by this call, so the launch sequence is CUDA-graph replayable.
  * params_bf16 (optional, same flat layout): bf16 copy of the updated parameters = the GEMM operands. */
-int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sumsq,
-                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, pulse_bf16_t* params_bf16,
-                    void* stream);
+#define PULSE_ADAM_ZERO_GRADS 1u      /* the kernel zeroes every gradient it has consumed (the next minibatch accumulates from zero) */
+#define PULSE_ADAM_SELF_CONTAINED 2u  /* no bump / memset launches: this launch is step *step + 1; its last block stores the new step and
+                                         re-zeroes *grad_sumsq (block_counter: one zero-initialised uint32 owned by the optimizer) */
+int pulse_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, double* grad_sumsq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, pulse_bf16_t* params_bf16, uint32_t flags,
+                    uint32_t* block_counter, void* stream);
 /* refresh the bf16 operand copies of one weight matrix W fp32 [n, k] (contiguous):
  *   w_bf16 [n, ld_k] (K-major, forward / wgrad-free) and wt_bf16 [k, ld_n] (transposed, dgrad operand); pads zeroed. */
 int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,

@@ -72,6 +72,15 @@ class ResetArgs(C.Structure):
     ]
 
 
+class WeightBlock(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("ld", C.c_int64), ("coef", C.c_float),
+                ("reserved", C.c_int32), ("sumsq", C.c_void_p), ("sumsq2", C.c_void_p)]
+
+
+class WeightReg(C.Structure):
+    _fields_ = [("block", WeightBlock * 4), ("count", C.c_int32), ("reserved", C.c_int32)]
+
+
 class PolicyPostArgs(C.Structure):
     _fields_ = [
         ("mu", C.c_void_p), ("ld_mu", C.c_int64), ("logstd", C.c_void_p), ("eps", C.c_void_p), ("ld_eps", C.c_int64),
@@ -114,6 +123,7 @@ class GemmEpilogue(C.Structure):
         ("alpha", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int64), ("out_t", C.c_void_p), ("ldot", C.c_int64),
         ("out_f32", C.c_void_p), ("ldf", C.c_int64), ("split_stride", C.c_int64), ("preact", C.c_void_p), ("ldp", C.c_int64),
         ("colsum", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32), ("sumsq", C.c_void_p),
+        ("relu_mask", C.c_void_p), ("ld_rmask", C.c_int64), ("gate_mask", C.c_void_p), ("ld_gmask", C.c_int64),
     ]
 
 
@@ -199,9 +209,9 @@ SIGNATURES = {
     "pulse_gemm_num_splits": (C.c_int, [C.c_int64, C.c_int32]),
     "pulse_gemm_bf16_grouped": (C.c_int, [C.POINTER(GemmProblem), C.c_int32, C.c_uint32, C.c_void_p]),
     "pulse_normalize_to_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                          C.c_void_p, C.c_int64, C.c_void_p]),
+                                          C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "pulse_normalize_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                          C.c_void_p, C.c_void_p]),
+                                          C.c_void_p, C.c_float, C.c_void_p]),
     "pulse_head1_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pulse_head1_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -213,12 +223,13 @@ SIGNATURES = {
     "pulse_ppo_loss": (C.c_int, [C.POINTER(PpoLossArgs), C.c_int64, C.c_void_p]),
     "pulse_disc_loss": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_relu_mask_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pulse_weight_reg": (C.c_int, [C.POINTER(WeightReg), C.c_void_p]),
     "pulse_axpy": (C.c_int, [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pulse_column_sum_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_reduce_slabs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_sum_squares": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
-                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pulse_refresh_weight_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "pulse_normalize_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64,
                                        C.c_int64, C.c_void_p]),

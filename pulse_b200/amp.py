@@ -27,13 +27,15 @@ class AmpDiscriminator:
     def __init__(self, flat: FlatParams, amp_obs_size: int = 1960, units: Sequence[int] = (1024, 512), disc_coef: float = 5.0,
                  logit_reg: float = 0.01, grad_penalty: float = 5.0, weight_decay: float = 0.0001, reward_scale: float = 2.0):
         self.flat, self.device = flat, flat.device
-        self.size, self.Kp = amp_obs_size, pad_k(amp_obs_size)
-        self.mlp = MLP(flat, amp_obs_size, units, 1, "relu")
+        self.size = amp_obs_size
+        self.mlp = MLP(flat, amp_obs_size, units, 1, "relu", aug=True)     # biases ride in the weights' extra column (nets.Dense)
+        self.Kp = self.mlp.Kp0
         if len(units) != 2:
             raise _lib.PulseError("the analytic gradient penalty is written for the 2-hidden-layer discriminator of im.yaml")
         self.disc_coef, self.logit_reg, self.grad_penalty, self.weight_decay = disc_coef, logit_reg, grad_penalty, weight_decay
         self.reward_scale = reward_scale
         self.rms = RunningMeanStdB200(amp_obs_size, self.device)       # _amp_input_mean_std
+        self.rms.pad_one = 1.0                                          # the normalised operand carries the ones column of the first layer
         self.stats = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._bufs: Dict[int, dict] = {}
         self.lib = _lib.load()
@@ -86,29 +88,34 @@ class AmpDiscriminator:
             _lib.check(lib.pulse_disc_loss(logits.data_ptr(), logits.stride(0), 2 * B, B, self.disc_coef, b["dlogit"].data_ptr(),
                                            b["dlogit"].stride(0), self.stats.data_ptr(), st), "pulse_disc_loss")
         self.mlp.backward(b["dlogit"], 3 * B)                          # prediction-loss gradients
-        # ---- gradient penalty on the demo rows, analytic (see module docstring) -------------------------------------
+        # ---- gradient penalty on the demo rows, analytic (see module docstring); ReLU masks = the bit words of the forward epilogue ----
         ws = self.mlp._ws[(3 * B, True)]
-        h1, h2, xd = ws["act"][0][2 * B:], ws["act"][1][2 * B:], x[2 * B:]
-        w3 = L3.weight.view(-1)                                         # fp32 [512]
+        h2 = ws["act"][1][2 * B:]
+        m1, m2 = ws["mask"][0][:, 2 * B:], ws["mask"][1][:, 2 * B:]      # [N/32, B] views (row stride 3B) of the demo rows' masks
+        w3 = L3.weight.view(-1)                                         # fp32 [Kp3]; only the first 512 are read
         with torch.cuda.device(dev):
             _lib.check(lib.pulse_relu_mask_scale(h2.data_ptr(), h2.stride(0), B, L2.N, w3.data_ptr(), b["g2"].data_ptr(), b["g2"].stride(0),
                                                  _lib.current_stream(dev)), "pulse_relu_mask_scale")
-        gemm(b["g2"][:, :L2.N], L2.w_bf16, b_mn=True, gate=h1, gate_mode="relu", out=b["g1"])             # g1 = m1 * (g2 W2)
+        W1, W2 = L1.w_bf16[:, :L1.K], L2.w_bf16[:, :L1.N]               # weight blocks WITHOUT the bias column
+        gemm(b["g2"][:, :L2.N], W2, b_mn=True, gate_mask=m1, out=b["g1"])                                  # g1 = m1 * (g2 W2)
         c = 2.0 * self.disc_coef * self.grad_penalty / B
-        gemm(b["g1"][:, :L1.N], L1.w_bf16, b_mn=True, alpha=c, out=b["Gb"], sumsq=self.stats[4:])         # G = c * g1 W1, stats[4] += sum G^2
-        gemm(b["g1"][:, :L1.N], b["Gb"], a_mn=True, b_mn=True, out_f32=L1.weight_grad, accumulate=True, split_k=b["split1"])  # dW1 += g1^T G
-        gemm(b["Gb"], L1.w_bf16, gate=h1, gate_mode="relu", out=b["du"])                                  # du = m1 * (G W1^T)
+        gemm(b["g1"][:, :L1.N], W1, b_mn=True, alpha=c, out=b["Gb"], sumsq=self.stats[4:])                  # G = c * g1 W1, stats[4] += sum G^2
+        gemm(b["g1"][:, :L1.N], b["Gb"], a_mn=True, b_mn=True, out_f32=L1.weight_grad, accumulate=True, split_k=b["split1"])  # dW1 += g1^T G (G's bias column is 0)
+        gemm(b["Gb"], L1.w_bf16, gate_mask=m1, out=b["du"])                                                # du = m1 * (G W1^T); G's bias / pad columns are 0
         gemm(b["g2"][:, :L2.N], b["du"][:, :L1.N], a_mn=True, b_mn=True, out_f32=L2.weight_grad, accumulate=True, split_k=b["split2"])  # dW2 += g2^T du
-        gemm(b["du"][:, :L1.N], L2.w_bf16, gate=h2, gate_mode="relu", out=b["scratch"],
-             colsum=self.flat.view_padded(L3.w_idx, "grads", L3.Kp))                                      # dw3 += colsum(m2 * (du W2^T))
-        # ---- logit regulariser and weight decay (amp_agent.py:905-908, :932-937): d/dw coef*sum(w^2) = 2*coef*w ------
+        gemm(b["du"][:, :L1.N], W2, gate_mask=m2, out=b["scratch"], colsum=L3.weight_grad.view(-1))        # dw3 += colsum(m2 * (du W2^T))
+        # ---- logit regulariser and weight decay (amp_agent.py:905-908, :932-937): d/dw coef*sum(w^2) = 2*coef*w, weights only ------
+        reg = _lib.WeightReg()
+        reg.count = 3
+        for k, l in enumerate((L1, L2, L3)):
+            coef = 2.0 * self.disc_coef * (self.weight_decay + (self.logit_reg if l is L3 else 0.0))
+            blk = reg.block[k]
+            blk.w, blk.g, blk.rows, blk.cols, blk.ld, blk.coef = l.weight.data_ptr(), l.weight_grad.data_ptr(), l.N, l.K, l.Kp, coef
+            blk.sumsq = self.stats[6:].data_ptr()
+            if l is L3:
+                blk.sumsq2 = self.stats[5:].data_ptr()
         with torch.cuda.device(dev):
-            st = _lib.current_stream(dev)
-            _lib.check(lib.pulse_sum_squares(L3.weight.data_ptr(), L3.weight.numel(), self.stats[5:].data_ptr(), st), "pulse_sum_squares")
-            for l in (L1, L2, L3):
-                coef = 2.0 * self.disc_coef * (self.weight_decay + (self.logit_reg if l is L3 else 0.0))
-                _lib.check(lib.pulse_axpy(coef, l.weight.data_ptr(), l.weight_grad.data_ptr(), l.weight.numel(), st), "pulse_axpy")
-                _lib.check(lib.pulse_sum_squares(l.weight.data_ptr(), l.weight.numel(), self.stats[6:].data_ptr(), st), "pulse_sum_squares")
+            _lib.check(lib.pulse_weight_reg(C.byref(reg), _lib.current_stream(dev)), "pulse_weight_reg")
         return self.stats
 
     def loss_from_stats(self, stats: torch.Tensor, B: int) -> Dict[str, float]:

@@ -32,8 +32,21 @@ namespace {
 #define PULSE_GEMM_VARIANT 0   // 0 = product; 3 = phase-trace build for tools/gemm_trace.py (tools/build_variant.sh trace gemm_tcgen05.cu -DPULSE_GEMM_VARIANT=3)
 #endif
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int kEpiWarps = 8;     // two per TMEM lane quarter: each drains 128 of the 256 accumulator columns
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+// Epilogue warps per CTA: kEpi / 4 per TMEM lane quarter, each draining 256 / (kEpi / 4) accumulator columns in 32-column chunks.
+// Measured (round 2, profiles/r02_gemm_epilogue_warps.txt): 16 epilogue warps on the CTA-pair kernel are SLOWER than 8 (PPO update set
+// 765 vs 687 us; ReLU-dgrad 16384x1024x512 52.8 vs 36 us): the epilogue is not short of warps, it is short of shared-memory pipe -- at
+// full MMA rate the UMMA operand reads (64 B/clk/SM) plus the TMA fills (64 B/clk/SM) already take the whole 128 B/clk, so every LDS /
+// STS / SHFL of the epilogue queues behind them.  The lever is fewer shared-pipe operations per output, not more warps.
+#ifndef PULSE_GEMM_EPI_PAIR
+#define PULSE_GEMM_EPI_PAIR 8
+#endif
+template <int CTAS>
+struct EpiCfg {
+  static constexpr int kWarps = CTAS == 2 ? PULSE_GEMM_EPI_PAIR : 8;
+  static constexpr int kCols = 256 / (kWarps / 4);      // accumulator columns per epilogue warp
+  static constexpr int kChunks = kCols / 32;            // 32-column chunks per epilogue warp
+  static constexpr int kThreads = 64 + 32 * kWarps;
+};
 constexpr unsigned kStageBytesA = BM * BK * 2;
 constexpr unsigned kTmemCols = 512;  // two 256-column fp32 accumulators (all of TMEM)
 
@@ -41,18 +54,23 @@ constexpr unsigned kTmemCols = 512;  // two 256-column fp32 accumulators (all of
 // 256 x 256 tile -- each CTA stages its own 128 rows of A and HALF of B (128 of the 256 columns), the leader's MMA reads both
 // halves, so the L2 -> SM operand traffic per MAC drops by a third (the single-CTA kernel was measured at the L2 delivery
 // limit: 8.9 TB/s of operand reads at 47 % tensor-pipe activity) and the 32 KB stages allow a 6-deep ring.
-template <int CTAS>
+// WG (weight-gradient specialisation): the epilogue stages each warp's 32 x 32 fp32 block in a 4 KB, 128-byte-swizzled tile that ONE
+// bulk tensor reduction (cp.reduce.async.bulk.tensor ... .add) adds into the gradient matrix -- double-buffered per warp (64 KB), paid for
+// with ring stages (the weight-gradient main loops are long, 4 / 3 stages cover the L2 latency).
+template <int CTAS, bool WG>
 struct __align__(1024) GemmSmemT {
-  static constexpr int kStages = CTAS == 2 ? 6 : 4;
+  static constexpr int kEpiWarps = EpiCfg<CTAS>::kWarps;
+  static constexpr int kStages = WG ? (CTAS == 2 ? 4 : 3) : (CTAS == 2 ? (kEpiWarps > 8 ? 5 : 6) : 4);
   static constexpr unsigned kStageBytesB = (BN / CTAS) * BK * 2;
+  static constexpr int kRedFloats = WG ? 2 * 1024 : 16 * 33;
   unsigned char a[kStages][kStageBytesA];
   unsigned char b[kStages][kStageBytesB];
+  float red[kEpiWarps][kRedFloats];   // per-epilogue-warp tile: bf16 store staging / fp32 transpose for atomics / (WG) two 4 KB reduction tiles
+  float bias[kEpiWarps][EpiCfg<CTAS>::kCols];   // per-epilogue-warp copy of the bias of its columns (broadcast reads in the forward epilogue)
   unsigned long long full[kStages];
   unsigned long long empty[kStages];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
-  float red[kEpiWarps][16 * 33];   // per-epilogue-warp tile: fp32 transpose for coalesced atomics / bf16 store staging
-  float bias[kEpiWarps][128];      // per-epilogue-warp copy of the bias of its 128 columns (broadcast reads in the forward epilogue)
   unsigned tmem_base;
 };
 
@@ -272,11 +290,12 @@ enum : int { kModeGeneric = 0, kModeFwd = 1, kModeDgrad = 2, kModeWgrad = 3, kMo
 // ---- grouped launch: several problems of the same operand majors / epilogue mode in ONE persistent launch ------------------
 constexpr int kMaxGroup = 4;
 struct GemmProblem {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   pulse_gemm_epilogue_t ep;
   int M, N, K, kb_per_split;
   int item_end;   // cumulative work items (tiles x split-K slices) up to and including this problem
-  int pad[3];
+  int use_tma_red;
+  int pad[2];
 };
 struct GemmGroup {
   GemmProblem p[kMaxGroup];
@@ -318,11 +337,38 @@ bool make_map(CUtensorMap* map, const void* base, long long rows, long long cols
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 [rows, cols] output (row stride ld floats) as a tensor map with 32 x 32 boxes, 128-byte swizzle: the target of the weight-gradient
+// epilogue's bulk tensor reductions (out-of-range rows / columns of a box are clipped by the hardware).
+bool make_map_c(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the reduction path needs 16-byte aligned rows; otherwise the kernel falls back to fp32 atomics
+bool tma_reduce_ok(const pulse_gemm_epilogue_t& ep) {
+  return ep.out_f32 != nullptr && ep.accumulate && (ep.ldf % 4) == 0 && (reinterpret_cast<uintptr_t>(ep.out_f32) % 16) == 0;
+}
+
 template <bool A_MN, bool B_MN, int MODE, int CTAS>
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_gemm_epilogue_t& ep, int m, int n, int k, int splits,
                 int kb_per_split, cudaStream_t stream) {
   static bool attr_set = false;
-  const size_t smem = sizeof(GemmSmemT<CTAS>) + 1024;  // slack so the kernel can align the ring to 1024 B
+  const size_t smem = sizeof(GemmSmemT<CTAS, MODE == kModeWgrad>) + 1024;  // slack so the kernel can align the ring to 1024 B
+  CUtensorMap map_c;
+  memset(&map_c, 0, sizeof(map_c));
+  int use_tma_red = 0;
+  if (MODE == kModeWgrad && tma_reduce_ok(ep)) {
+    if (!make_map_c(&map_c, ep.out_f32, m, n, ep.ldf)) {
+      set_error("pulse_gemm_bf16: cuTensorMapEncodeTiled failed for the fp32 output");
+      return PULSE_ERR_CUDA;
+    }
+    use_tma_red = 1;
+  }
   if (!attr_set) {
     PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -344,7 +390,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.blockDim = dim3(EpiCfg<CTAS>::kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -363,7 +409,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE, CTAS>, map_a, map_b, ep, m, n, k, kb_per_split, splits));
+  PULSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE, CTAS>, map_a, map_b, map_c, ep, m, n, k, kb_per_split, splits, use_tma_red));
   PULSE_LAUNCH_OK("gemm_bf16_kernel");
   return PULSE_OK;
 }
@@ -371,7 +417,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
 template <bool A_MN, bool B_MN, int MODE, int CTAS>
 int launch_gemm_grouped(const GemmGroup& grp, cudaStream_t stream) {
   static bool attr_set = false;
-  const size_t smem = sizeof(GemmSmemT<CTAS>) + 1024;
+  const size_t smem = sizeof(GemmSmemT<CTAS, MODE == kModeWgrad>) + 1024;
   if (!attr_set) {
     PULSE_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_grouped_kernel<A_MN, B_MN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -386,7 +432,7 @@ int launch_gemm_grouped(const GemmGroup& grp, cudaStream_t stream) {
   const unsigned grid = static_cast<unsigned>((grp.total_items < slots ? grp.total_items : slots) * CTAS);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.blockDim = dim3(EpiCfg<CTAS>::kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -409,8 +455,8 @@ int launch_gemm_grouped(const GemmGroup& grp, cudaStream_t stream) {
 }
 
 int epilogue_mode(const pulse_gemm_epilogue_t* ep) {
-  const bool want_fwd = ep->bias || ep->act != PULSE_ACT_NONE || ep->preact || ep->out_t;
-  const bool want_dgrad = ep->gate || ep->colsum || ep->sumsq;
+  const bool want_fwd = ep->bias || ep->act != PULSE_ACT_NONE || ep->preact || ep->out_t || ep->relu_mask;
+  const bool want_dgrad = ep->gate || ep->colsum || ep->sumsq || ep->gate_mask;
   const bool want_accum = ep->accumulate != 0;
   if (!want_dgrad && !want_accum) return kModeFwd;
   if (!want_fwd && !want_accum) return (ep->gate && ep->gate_mode != PULSE_ACT_RELU) ? kModeDgradVec : kModeDgrad;
@@ -452,6 +498,9 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   PULSE_REQUIRE(split_k == 1 || (ep->out_f32 && !ep->out && !ep->out_t && !ep->bias && ep->act == PULSE_ACT_NONE && !ep->gate && !ep->preact && !ep->colsum),
                 "pulse_gemm_bf16: split-K only supports plain fp32 outputs (slabs or atomic accumulation)");
   PULSE_REQUIRE(ep->gate == nullptr || ep->gate_mode == PULSE_ACT_RELU || ep->gate_mode == PULSE_ACT_SILU, "pulse_gemm_bf16: bad gate_mode");
+  PULSE_REQUIRE((ep->relu_mask == nullptr || ep->ld_rmask >= m) && (ep->gate_mask == nullptr || ep->ld_gmask >= m),
+                "pulse_gemm_bf16: mask word rows must hold at least M entries");
+  PULSE_REQUIRE(!(ep->gate_mask && ep->gate), "pulse_gemm_bf16: give the ReLU gate either as bf16 activations or as bit words, not both");
   // CTA pairs (256 x 256 tiles, cta_group::2) for everything large enough to fill them; PULSE_GEMM_PAIR=0 forces single CTAs
   static int use_pair = -1;
   if (use_pair < 0) {
@@ -471,8 +520,8 @@ extern "C" int pulse_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   const int kb_per_split = (num_kb + splits - 1) / splits;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // smallest epilogue specialisation that covers the request (see the MODE comment on the kernel)
-  const bool want_fwd = ep->bias || ep->act != PULSE_ACT_NONE || ep->preact || ep->out_t;
-  const bool want_dgrad = ep->gate || ep->colsum || ep->sumsq;
+  const bool want_fwd = ep->bias || ep->act != PULSE_ACT_NONE || ep->preact || ep->out_t || ep->relu_mask;
+  const bool want_dgrad = ep->gate || ep->colsum || ep->sumsq || ep->gate_mask;
   const bool want_accum = ep->accumulate != 0;
   int mode = kModeGeneric;
   if (!want_dgrad && !want_accum) mode = kModeFwd;
@@ -558,6 +607,14 @@ extern "C" int pulse_gemm_bf16_grouped(const pulse_gemm_problem_t* problems, int
       return PULSE_ERR_CUDA;
     }
     g.ep = q.ep;
+    g.use_tma_red = 0;
+    if (mode == kModeWgrad && tma_reduce_ok(q.ep)) {
+      if (!make_map_c(&g.map_c, q.ep.out_f32, q.m, q.n, q.ep.ldf)) {
+        set_error("pulse_gemm_bf16_grouped: cuTensorMapEncodeTiled failed for the fp32 output of problem %d", i);
+        return PULSE_ERR_CUDA;
+      }
+      g.use_tma_red = 1;
+    }
     g.M = static_cast<int>(q.m);
     g.N = static_cast<int>(q.n);
     g.K = static_cast<int>(q.k);

@@ -27,7 +27,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         __nv_bfloat16* __restrict__ out, long long ld_out,
-                                                        __nv_bfloat16* __restrict__ out_t, long long ld_t) {
+                                                        __nv_bfloat16* __restrict__ out_t, long long ld_t, float pad_one) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const long long col_tiles = (ld_out + 31) / 32;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long r = rt * 32 + ty + 8 * i;
-      float y = 0.0f;
+      float y = c == cols ? pad_one : 0.0f;   // first pad column: the "ones" column of a bias-augmented operand (else zero fill)
       if (r < rows && c < cols) {
         y = (x[r * ldx + c] - m) * rs;
         if (mean != nullptr) y = fminf(fmaxf(y, -5.0f), 5.0f);
@@ -89,14 +89,15 @@ __global__ void __launch_bounds__(256) column_moments_kernel(const float* __rest
 __global__ void __launch_bounds__(256) normalize_moments_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols,
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 __nv_bfloat16* __restrict__ out, long long ld_out,
-                                                                double* __restrict__ sums) {
+                                                                double* __restrict__ sums, float pad_one) {
   const long long c = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   if (c >= ld_out) return;
   const bool live = c < cols;  // cols is even on this path: a pair is either fully inside or fully padding
   const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
   if (!live) {
-    for (long long r = r0; r < r1; ++r) *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = __floats2bfloat162_rn(0.0f, 0.0f);
+    const __nv_bfloat162 fill = __floats2bfloat162_rn(c == cols ? pad_one : 0.0f, 0.0f);   // (ones column | 0) on the first pad pair
+    for (long long r = r0; r < r1; ++r) *reinterpret_cast<__nv_bfloat162*>(out + r * ld_out + c) = fill;
     return;
   }
   const float2 m = *reinterpret_cast<const float2*>(mean + c), rs = *reinterpret_cast<const float2*>(rstd + c);
@@ -159,80 +160,94 @@ __global__ void __launch_bounds__(128) gaussian_sample_kernel(const float* __res
 }
 
 // ---- PPO losses + gradients w.r.t. mu / value ---------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ppo_loss_kernel(const pulse_ppo_loss_args_t a, long long rows) {
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  __shared__ double s_stats[4][6];
-  const int warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const pulse_ppo_loss_args_t a, long long rows) {
+  // Warps stride over the rows (a few rows each on a one-wave grid): the per-action constants are computed once per lane, the loss
+  // statistics stay in registers until ONE set of fp64 atomics per block (round 1 issued six per 128-thread block: 24 k serialised
+  // atomics on six addresses were most of this kernel's 19 us).
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  __shared__ double s_stats[8][6];
+  const int A = a.num_actions;
+  constexpr int kPer = 4;                       // actions per lane: A <= 128
+  float sg[kPer], inv_sg2[kPer], lsum = 0.0f;
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int k = lane + 32 * q;
+    const float l = k < A ? a.logstd[k] : 0.0f;
+    sg[q] = expf(l);
+    inv_sg2[q] = 1.0f / (sg[q] * sg[q]);
+    lsum += k < A ? l : 0.0f;
+  }
+  lsum = warp_sum_f(lsum);
+  const float inv_rows = 1.0f / static_cast<float>(rows);
   double st[6] = {0, 0, 0, 0, 0, 0};
-  if (row < rows) {
-    const int A = a.num_actions;
-    const float inv_rows = 1.0f / static_cast<float>(rows);
-    // pass 1: neglogp, bound loss, kl
-    float z2 = 0.0f, ls = 0.0f, bl = 0.0f, kl = 0.0f;
-    for (int k = lane; k < A; k += 32) {
-      const float l = a.logstd[k];
-      const float sg = expf(l);
-      const float m = a.mu[row * a.ld_mu + k];
-      const float z = (a.actions[row * A + k] - m) / sg;
-      z2 += z * z;
-      ls += l;
-      const float hi = fmaxf(m - 1.0f, 0.0f), lo = fminf(m + 1.0f, 0.0f);
-      bl += hi * hi + lo * lo;
-      if (a.old_mu != nullptr) {
-        // policy_kl(p0 = current, p1 = old) with equal sigma: log(s1/s0 + 1e-5) + (s0^2 + (mu1-mu0)^2)/(2(s1^2+1e-5)) - 0.5
-        const float d = a.old_mu[row * A + k] - m;
-        kl += logf(1.0f + 1e-5f) + (sg * sg + d * d) / (2.0f * (sg * sg + 1e-5f)) - 0.5f;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float m[kPer], act[kPer];
+    float z2 = 0.0f, bl = 0.0f, kl = 0.0f;
+    const float adv = a.advantages[row], old_nlp = a.old_neglogp[row], v = a.value[row * a.ld_value], ret = a.returns[row];   // in flight with the row
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int k = lane + 32 * q;
+      if (k < A) {
+        m[q] = a.mu[row * a.ld_mu + k];
+        act[q] = a.actions[row * A + k];
+        const float z = (act[q] - m[q]) / sg[q];
+        z2 += z * z;
+        const float hi = fmaxf(m[q] - 1.0f, 0.0f), lo = fminf(m[q] + 1.0f, 0.0f);
+        bl += hi * hi + lo * lo;
+        if (a.old_mu != nullptr) {
+          // policy_kl(p0 = current, p1 = old) with equal sigma: log(s1/s0 + 1e-5) + (s0^2 + (mu1-mu0)^2)/(2(s1^2+1e-5)) - 0.5
+          const float d = a.old_mu[row * A + k] - m[q];
+          kl += logf(1.0f + 1e-5f) + (sg[q] * sg[q] + d * d) / (2.0f * (sg[q] * sg[q] + 1e-5f)) - 0.5f;
+        }
       }
     }
     z2 = warp_sum_f(z2);
-    ls = warp_sum_f(ls);
     bl = warp_sum_f(bl);
     kl = warp_sum_f(kl);
-    const float nlp = 0.5f * z2 + 0.5f * 1.8378770664093453f * A + ls;
-    const float adv = a.advantages[row];
-    const float ratio = expf(a.old_neglogp[row] - nlp);
+    const float nlp = 0.5f * z2 + 0.5f * 1.8378770664093453f * A + lsum;
+    const float ratio = expf(old_nlp - nlp);
     const float rc = fminf(fmaxf(ratio, 1.0f - a.e_clip), 1.0f + a.e_clip);
     const float s1 = -adv * ratio, s2 = -adv * rc;
     const float a_loss = fmaxf(s1, s2);
     // d a_loss / d nlp: the unclipped branch is active when s1 >= s2 (torch.max sends the gradient there on ties);
     // the clipped branch has zero gradient unless ratio is inside the clip range, where both coincide.
     const float da_dnlp = (s1 >= s2) ? adv * ratio : 0.0f;
-    const float v = a.value[row * a.ld_value];
-    const float ret = a.returns[row];
     const float c_loss = (ret - v) * (ret - v);
-    // pass 2: gradients
-    for (int k = lane; k < A; k += 32) {
-      const float l = a.logstd[k];
-      const float sg = expf(l);
-      const float m = a.mu[row * a.ld_mu + k];
-      const float dnlp_dmu = -(a.actions[row * A + k] - m) / (sg * sg);
-      const float hi = fmaxf(m - 1.0f, 0.0f), lo = fminf(m + 1.0f, 0.0f);
-      const float g = (da_dnlp * dnlp_dmu + a.bounds_coef * 2.0f * (hi + lo)) * inv_rows;
-      const __nv_bfloat16 gb = __float2bfloat16(g);
-      if (a.dmu != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu)[row * a.ld_dmu + k] = gb;
-      if (a.dmu_t != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu_t)[k * a.ld_dmu_t + row] = gb;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int k = lane + 32 * q;
+      if (k < A) {
+        const float dnlp_dmu = -(act[q] - m[q]) * inv_sg2[q];
+        const float hi = fmaxf(m[q] - 1.0f, 0.0f), lo = fminf(m[q] + 1.0f, 0.0f);
+        const float g = (da_dnlp * dnlp_dmu + a.bounds_coef * 2.0f * (hi + lo)) * inv_rows;
+        const __nv_bfloat16 gb = __float2bfloat16(g);
+        if (a.dmu != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu)[row * a.ld_dmu + k] = gb;
+        if (a.dmu_t != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dmu_t)[k * a.ld_dmu_t + row] = gb;
+      }
     }
     if (lane == 0) {
       const __nv_bfloat16 gv = __float2bfloat16(-2.0f * (ret - v) * a.critic_coef * inv_rows);
       if (a.dvalue != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dvalue)[row * a.ld_dv] = gv;
       if (a.dvalue_t != nullptr) reinterpret_cast<__nv_bfloat16*>(a.dvalue_t)[row] = gv;
-      st[0] = a_loss;
-      st[1] = c_loss;
-      st[2] = bl;
-      st[3] = kl;
-      st[4] = fabsf(ratio - 1.0f) > a.e_clip ? 1.0 : 0.0;
-      st[5] = nlp;
+      st[0] += a_loss;
+      st[1] += c_loss;
+      st[2] += bl;
+      st[3] += kl;
+      st[4] += fabsf(ratio - 1.0f) > a.e_clip ? 1.0 : 0.0;
+      st[5] += nlp;
     }
   }
   if (lane == 0)
     for (int i = 0; i < 6; ++i) s_stats[warp][i] = st[i];
   __syncthreads();
   if (threadIdx.x < 6 && a.stats != nullptr) {
-    const double t = s_stats[0][threadIdx.x] + s_stats[1][threadIdx.x] + s_stats[2][threadIdx.x] + s_stats[3][threadIdx.x];
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_stats[w][threadIdx.x];
     atomicAdd(a.stats + threadIdx.x, t);
   }
 }
+
 
 // ---- column sums of a bf16 matrix (bias gradients) ------------------------------------------------------------------
 // Block = 16 column groups (8 columns each, one 16-byte load) x 16 row lanes; blockIdx.y strides over row chunks.
@@ -309,43 +324,94 @@ __global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(256) sum_squares_kernel(const float* __restrict__ x, long long count, double* __restrict__ out) {
+  // fp64 multiplies run at a small fraction of the fp32 rate on this part: square in fp32 (exact enough: 24-bit operands, the sum of
+  // eight products is then widened), accumulate the groups in fp64
   double s = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const double v = x[i];
-    s += v * v;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? count / 4 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride);
+    const float p = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w))) + fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, b.w * b.w)));
+    s += static_cast<double>(p);
   }
+  for (; i < n4; i += stride) {
+    const float4 a = __ldg(x4 + i);
+    s += static_cast<double>(fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w))));
+  }
+  for (long long k = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) s += static_cast<double>(x[k] * x[k]);
   s = warp_sum_d(s);
   __shared__ double ws[8];
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += ws[i];
+    for (int k = 0; k < 8; ++k) t += ws[k];
     atomicAdd(out, t);
   }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long count, const double* __restrict__ sumsq, float max_norm,
                                                    float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr,
-                                                   __nv_bfloat16* __restrict__ p_bf16) {
-  const float step = static_cast<float>(*step_ptr);  // already incremented by bump_step_kernel
+                                                   __nv_bfloat16* __restrict__ p_bf16, int zero_grads, int* __restrict__ step_rw,
+                                                   unsigned* __restrict__ block_counter, double* __restrict__ sumsq_rw) {
+  // self-contained mode (block_counter != NULL): this launch IS optimizer step *step_ptr + 1; the last block to finish stores the new
+  // step, re-zeroes the gradient-norm accumulator and its own counter -- no bump / memset launches around the update
+  const float step = static_cast<float>(*step_ptr + (block_counter != nullptr ? 1 : 0));
   const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
   float scale = 1.0f;
   if (sumsq != nullptr && max_norm > 0.0f) {
     const float norm = static_cast<float>(sqrt(*sumsq));
     scale = fminf(1.0f, max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * scale;
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
+  const float lr1 = lr / bc1, rs2 = sqrtf(bc2);
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    gi *= scale;
+    mi = b1 * mi + (1.0f - b1) * gi;
+    vi = b2 * vi + (1.0f - b2) * gi * gi;
     // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-    const float pn = p[i] - (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
-    p[i] = pn;
-    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16(pn);  // the GEMM operand copy shares the flat layout
+    pi = pi - lr1 * mi / (sqrtf(vi) / rs2 + eps);
+  };
+  const long long n4 = count / 4;   // the flat buffers are 256-byte aligned and padded to multiples of 64 elements
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    upd(g4.x, m4.x, v4.x, p4.x);
+    upd(g4.y, m4.y, v4.y, p4.y);
+    upd(g4.z, m4.z, v4.z, p4.z);
+    upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // consumed: the next minibatch accumulates from zero
+    if (p_bf16 != nullptr) {  // the GEMM operand copy shares the flat layout
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+      uint2 u;
+      u.x = *reinterpret_cast<unsigned*>(&lo);
+      u.y = *reinterpret_cast<unsigned*>(&hi);
+      reinterpret_cast<uint2*>(p_bf16)[i] = u;
+    }
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (zero_grads) g[i] = 0.0f;
+    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16(pi);
+  }
+  if (block_counter != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(block_counter, 1u) == gridDim.x - 1) {   // every block has read *step_ptr / *sumsq by now
+        *step_rw = static_cast<int>(step);
+        if (sumsq_rw != nullptr) *sumsq_rw = 0.0;
+        *block_counter = 0u;
+        __threadfence();
+      }
+    }
   }
 }
 
@@ -391,13 +457,33 @@ __global__ void __launch_bounds__(256) disc_loss_kernel(const float* __restrict_
 // out[r, c] = h[r, c] > 0 ? w[c] : 0   (first step of the analytic input gradient of a ReLU MLP: m2 * w_logit)
 __global__ void __launch_bounds__(256) relu_mask_scale_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, long long rows, long long cols,
                                                               const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long ldo) {
+  const bool vec = (cols % 8) == 0 && (ldh % 8) == 0 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(h) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) % 16) == 0;
+  if (vec) {   // thread = (row, group of 8 columns): one 16-byte load and store
+    const long long groups = cols / 8, total = rows * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / groups, c = (i - r * groups) * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(h + r * ldh + c);
+      const unsigned wd[4] = {u.x, u.y, u.z, u.w};
+      uint4 o;
+      unsigned* od = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // bf16 > 0  <=>  sign clear and magnitude non-zero
+        const bool p0 = (wd[q] & 0x8000u) == 0 && (wd[q] & 0x7fffu) != 0, p1 = (wd[q] & 0x80000000u) == 0 && (wd[q] & 0x7fff0000u) != 0;
+        const __nv_bfloat162 v = __floats2bfloat162_rn(p0 ? w[c + 2 * q] : 0.0f, p1 ? w[c + 2 * q + 1] : 0.0f);
+        od[q] = *reinterpret_cast<const unsigned*>(&v);
+      }
+      *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
+    }
+    return;
+  }
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols, c = i - r * cols;
     out[r * ldo + c] = __float2bfloat16(__bfloat162float(h[r * ldh + c]) > 0.0f ? w[c] : 0.0f);
   }
 }
-
 __global__ void __launch_bounds__(256) axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, long long count) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
@@ -439,25 +525,35 @@ __global__ void __launch_bounds__(256) head1_forward_kernel(const __nv_bfloat16*
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float b = bias != nullptr ? __ldg(bias) : 0.0f;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const __nv_bfloat16* hr = h + r * ldh;
-    float acc = 0.0f;
+  constexpr int R = 4;                            // rows in flight per warp: the loads of all four are issued before any is consumed
+  for (long long r0 = warp0 * R; r0 < rows; r0 += nwarps * R) {
+    float acc[R] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int k = lane * 8; k < K; k += 256) {
-      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(hr + k));
+      uint4 u[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        u[i] = (r0 + i < rows) ? __ldcs(reinterpret_cast<const uint4*>(h + (r0 + i) * ldh + k)) : make_uint4(0u, 0u, 0u, 0u);
       const uint4 wu = __ldg(reinterpret_cast<const uint4*>(w + k));
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u);
       const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wu);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 a = __bfloat1622float2(a2[q]), ww = __bfloat1622float2(w2[q]);
-        acc = fmaf(a.x, ww.x, acc);
-        acc = fmaf(a.y, ww.y, acc);
+      for (int i = 0; i < R; ++i) {
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = __bfloat1622float2(a2[q]), ww = __bfloat1622float2(w2[q]);
+          acc[i] = fmaf(a.x, ww.x, acc[i]);
+          acc[i] = fmaf(a.y, ww.y, acc[i]);
+        }
       }
     }
-    acc = warp_sum_f(acc);
-    if (lane == 0) out[r * ldo] = acc + b;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float t = warp_sum_f(acc[i]);
+      if (lane == 0 && r0 + i < rows) out[(r0 + i) * ldo] = t + b;
+    }
   }
 }
+
 
 // dh[m,k] = dv[m] * w[k] * (h[m,k] > 0);  dw[k] += sum_m dv[m] h[m,k];  db += sum_m dv[m];  dbias_prev[k] += sum_m dh[m,k].
 // Thread = 8 columns (one 16-byte load / store); blockDim.x / (K/8) row lanes per CTA; fp32 atomics once per CTA.
@@ -484,32 +580,46 @@ __global__ void __launch_bounds__(256) head1_backward_kernel(const __nv_bfloat16
         wf[2 * q + 1] = f.y;
       }
     }
-    for (long long r = r0 + rl; r < r1; r += lanes) {
-      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(h + r * ldh + cg * 8));
-      const float d = __bfloat162float(dv[r * ld_dv]);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-      float o[8];
+    constexpr int R = 4;   // rows in flight per thread: one 16-byte load each, all issued before the first is consumed
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * R) {
+      uint4 u[R];
+      float dd[R];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 a = __bfloat1622float2(a2[q]);
-        aw[2 * q] = fmaf(d, a.x, aw[2 * q]);
-        aw[2 * q + 1] = fmaf(d, a.y, aw[2 * q + 1]);
-        o[2 * q] = a.x > 0.0f ? d * wf[2 * q] : 0.0f;
-        o[2 * q + 1] = a.y > 0.0f ? d * wf[2 * q + 1] : 0.0f;
-        ac[2 * q] += o[2 * q];
-        ac[2 * q + 1] += o[2 * q + 1];
+      for (int i = 0; i < R; ++i) {
+        const long long r = rb + (long long)i * lanes;
+        const bool ok = r < r1;
+        u[i] = ok ? __ldcs(reinterpret_cast<const uint4*>(h + r * ldh + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        dd[i] = ok ? __bfloat162float(dv[r * ld_dv]) : 0.0f;
       }
-      if (dh != nullptr) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
-        uint4 st;
-        st.x = *reinterpret_cast<unsigned*>(&p0);
-        st.y = *reinterpret_cast<unsigned*>(&p1);
-        st.z = *reinterpret_cast<unsigned*>(&p2);
-        st.w = *reinterpret_cast<unsigned*>(&p3);
-        *reinterpret_cast<uint4*>(dh + r * ld_dh + cg * 8) = st;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const long long r = rb + (long long)i * lanes;
+        if (r >= r1) break;
+        const float d = dd[i];
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = __bfloat1622float2(a2[q]);
+          aw[2 * q] = fmaf(d, a.x, aw[2 * q]);
+          aw[2 * q + 1] = fmaf(d, a.y, aw[2 * q + 1]);
+          o[2 * q] = a.x > 0.0f ? d * wf[2 * q] : 0.0f;
+          o[2 * q + 1] = a.y > 0.0f ? d * wf[2 * q + 1] : 0.0f;
+          ac[2 * q] += o[2 * q];
+          ac[2 * q + 1] += o[2 * q + 1];
+        }
+        if (dh != nullptr) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+          uint4 st;
+          st.x = *reinterpret_cast<unsigned*>(&p0);
+          st.y = *reinterpret_cast<unsigned*>(&p1);
+          st.z = *reinterpret_cast<unsigned*>(&p2);
+          st.w = *reinterpret_cast<unsigned*>(&p3);
+          *reinterpret_cast<uint4*>(dh + r * ld_dh + cg * 8) = st;
+        }
+        if (cg == 0) adb += d;
       }
-      if (cg == 0) adb += d;
     }
     float* mine = red + (long long)rl * (2 * K + 1);
 #pragma unroll
@@ -547,7 +657,7 @@ inline unsigned grid_for(long long work_items, int per_block, int waves = 8) {
 using namespace pulse;
 
 extern "C" int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
-                                       pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, void* stream) {
+                                       pulse_bf16_t* out, int64_t ld_out, pulse_bf16_t* out_t, int64_t ld_t, float pad_one, void* stream) {
   PULSE_REQUIRE(x && (out || out_t), "pulse_normalize_to_bf16: null buffer");
   PULSE_REQUIRE(rows > 0 && cols > 0 && ld_out >= cols && ldx >= cols, "pulse_normalize_to_bf16: bad shape");
   PULSE_REQUIRE((mean == nullptr) == (rstd == nullptr), "pulse_normalize_to_bf16: mean and rstd go together");
@@ -561,13 +671,13 @@ extern "C" int pulse_normalize_to_bf16(const float* x, int64_t ldx, int64_t rows
     if (gy > rows / 8) gy = static_cast<unsigned>(rows / 8);
     if (gy < 1) gy = 1;
     normalize_moments_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, nullptr);
+        x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, nullptr, pad_one);
     PULSE_LAUNCH_OK("normalize_moments_kernel");
     return PULSE_OK;
   }
   const long long tiles = ((ld_out + 31) / 32) * ((rows + 31) / 32);
   normalize_kernel<<<grid_for(tiles, 1, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, reinterpret_cast<__nv_bfloat16*>(out_t), ld_t);
+      x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, reinterpret_cast<__nv_bfloat16*>(out_t), ld_t, pad_one);
   PULSE_LAUNCH_OK("normalize_kernel");
   return PULSE_OK;
 }
@@ -581,7 +691,7 @@ extern "C" int pulse_column_moments(const float* x, int64_t ldx, int64_t rows, i
 }
 
 extern "C" int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* mean, const float* rstd,
-                                       pulse_bf16_t* out, int64_t ld_out, double* sums, void* stream) {
+                                       pulse_bf16_t* out, int64_t ld_out, double* sums, float pad_one, void* stream) {
   PULSE_REQUIRE(x && mean && rstd && out && sums, "pulse_normalize_moments: null buffer");
   PULSE_REQUIRE(rows > 0 && cols > 0 && ld_out >= cols && ldx >= cols, "pulse_normalize_moments: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -589,7 +699,7 @@ extern "C" int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows
                       (reinterpret_cast<uintptr_t>(out) % 4 == 0) && (reinterpret_cast<uintptr_t>(mean) % 8 == 0) &&
                       (reinterpret_cast<uintptr_t>(rstd) % 8 == 0);
   if (!paired) {  // odd widths / unaligned views: the two single-purpose kernels (same results, two passes)
-    const int rc = pulse_normalize_to_bf16(x, ldx, rows, cols, mean, rstd, out, ld_out, nullptr, 0, stream);
+    const int rc = pulse_normalize_to_bf16(x, ldx, rows, cols, mean, rstd, out, ld_out, nullptr, 0, pad_one, stream);
     if (rc != PULSE_OK) return rc;
     return pulse_column_moments(x, ldx, rows, cols, sums, stream);
   }
@@ -597,7 +707,7 @@ extern "C" int pulse_normalize_moments(const float* x, int64_t ldx, int64_t rows
   unsigned gy = (2 * kSMs + gx - 1) / gx;  // two 256-thread CTAs per SM, 8 x 8-byte loads in flight per thread
   if (gy > rows / 8) gy = static_cast<unsigned>(rows / 8);
   if (gy < 1) gy = 1;
-  normalize_moments_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, sums);
+  normalize_moments_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ldx, rows, cols, mean, rstd, reinterpret_cast<__nv_bfloat16*>(out), ld_out, sums, pad_one);
   PULSE_LAUNCH_OK("normalize_moments_kernel");
   return PULSE_OK;
 }
@@ -645,8 +755,10 @@ extern "C" int pulse_ppo_loss(const pulse_ppo_loss_args_t* args, int64_t rows, v
   PULSE_REQUIRE(args != nullptr && rows > 0, "pulse_ppo_loss: bad argument");
   const pulse_ppo_loss_args_t& a = *args;
   PULSE_REQUIRE(a.mu && a.value && a.actions && a.old_neglogp && a.advantages && a.returns && a.logstd, "pulse_ppo_loss: null input");
-  PULSE_REQUIRE(a.num_actions > 0, "pulse_ppo_loss: num_actions");
-  ppo_loss_kernel<<<static_cast<unsigned>((rows * 32 + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  PULSE_REQUIRE(a.num_actions > 0 && a.num_actions <= 128, "pulse_ppo_loss: num_actions outside [1,128]");
+  long long blocks = (rows + 7) / 8;            // 8 warps per block, one row per warp at a time
+  if (blocks > 8LL * kSMs) blocks = 8LL * kSMs; // all resident: 2048 threads per SM
+  ppo_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, rows);
   PULSE_LAUNCH_OK("ppo_loss_kernel");
   return PULSE_OK;
 }
@@ -686,15 +798,21 @@ extern "C" int pulse_sum_squares(const float* x, int64_t count, double* sumsq, v
   return PULSE_OK;
 }
 
-extern "C" int pulse_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
-                               const double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step,
-                               pulse_bf16_t* params_bf16, void* stream) {
+extern "C" int pulse_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                               double* grad_sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step,
+                               pulse_bf16_t* params_bf16, uint32_t flags, uint32_t* block_counter, void* stream) {
   PULSE_REQUIRE(params && grads && exp_avg && exp_avg_sq && count > 0 && step != nullptr, "pulse_adam_step: bad argument");
-  bump_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step);
-  PULSE_LAUNCH_OK("bump_step_kernel");
-  adam_kernel<<<grid_for(count, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, count, grad_sumsq,
-                                                                                       max_norm, lr, beta1, beta2, eps, step,
-                                                                                       reinterpret_cast<__nv_bfloat16*>(params_bf16));
+  PULSE_REQUIRE((flags & ~3u) == 0, "pulse_adam_step: bad flags");
+  PULSE_REQUIRE(!(flags & PULSE_ADAM_SELF_CONTAINED) || block_counter != nullptr, "pulse_adam_step: the self-contained mode needs block_counter");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool self = (flags & PULSE_ADAM_SELF_CONTAINED) != 0;
+  if (!self) {
+    bump_step_kernel<<<1, 1, 0, st>>>(step);
+    PULSE_LAUNCH_OK("bump_step_kernel");
+  }
+  adam_kernel<<<grid_for(count, 256 * 4), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, count, grad_sumsq, max_norm, lr, beta1, beta2, eps, step,
+                                                        reinterpret_cast<__nv_bfloat16*>(params_bf16), (flags & PULSE_ADAM_ZERO_GRADS) ? 1 : 0, step,
+                                                        self ? block_counter : nullptr, self ? grad_sumsq : nullptr);
   PULSE_LAUNCH_OK("adam_kernel");
   return PULSE_OK;
 }
@@ -714,6 +832,64 @@ extern "C" int pulse_relu_mask_scale(const pulse_bf16_t* h, int64_t ldh, int64_t
   relu_mask_scale_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(h), ldh, rows, cols, w, reinterpret_cast<__nv_bfloat16*>(out), ldo);
   PULSE_LAUNCH_OK("relu_mask_scale_kernel");
+  return PULSE_OK;
+}
+
+// Weight regularisers of the AMP discriminator (amp_agent.py:905-908, :932-937) for up to four weight blocks in ONE launch:
+// g[r, c] += coef * w[r, c] over the [rows, cols] sub-block of a [rows, ld] matrix (the bias column / zero padding of an augmented
+// layer stay out of it) and the fp64 sums of squares the logged loss terms need.
+namespace pulse {
+namespace {
+__global__ void __launch_bounds__(256) weight_reg_kernel(const pulse_weight_reg_t d) {
+  double sq = 0.0;
+  const pulse_weight_block_t& b = d.block[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = (b.cols % 4) == 0 && (b.ld % 4) == 0 && (reinterpret_cast<uintptr_t>(b.w) % 16) == 0 &&
+                   (b.g == nullptr || (reinterpret_cast<uintptr_t>(b.g) % 16) == 0);
+  if (vec) {   // thread = (row, 4 columns): independent 16-byte read-modify-writes, many in flight per thread
+    const long long c4 = b.cols / 4, total = b.rows * c4;
+    for (long long i = t0; i < total; i += stride) {
+      const long long r = i / c4, c = (i - r * c4) * 4;
+      const float4 w = *reinterpret_cast<const float4*>(b.w + r * b.ld + c);
+      if (b.g != nullptr) {
+        float4 g = *reinterpret_cast<float4*>(b.g + r * b.ld + c);
+        g.x += b.coef * w.x; g.y += b.coef * w.y; g.z += b.coef * w.z; g.w += b.coef * w.w;
+        *reinterpret_cast<float4*>(b.g + r * b.ld + c) = g;
+      }
+      sq += static_cast<double>(fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, w.w * w.w))));
+    }
+  } else {
+    const long long total = b.rows * b.cols;
+    for (long long i = t0; i < total; i += stride) {
+      const long long r = i / b.cols, c = i - r * b.cols;
+      const float w = b.w[r * b.ld + c];
+      if (b.g != nullptr) b.g[r * b.ld + c] += b.coef * w;
+      sq += static_cast<double>(w * w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
+  __shared__ double part_s[8];
+  if ((threadIdx.x & 31) == 0) part_s[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += part_s[k];
+    if (b.sumsq != nullptr) atomicAdd(b.sumsq, t);
+    if (b.sumsq2 != nullptr) atomicAdd(b.sumsq2, t);
+  }
+}
+}  // namespace
+}  // namespace pulse
+
+extern "C" int pulse_weight_reg(const pulse_weight_reg_t* desc, void* stream) {
+  PULSE_REQUIRE(desc != nullptr && desc->count >= 1 && desc->count <= 4, "pulse_weight_reg: 1..4 blocks");
+  for (int i = 0; i < desc->count; ++i) {
+    const pulse_weight_block_t& b = desc->block[i];
+    PULSE_REQUIRE(b.w != nullptr && b.rows > 0 && b.cols > 0 && b.ld >= b.cols, "pulse_weight_reg: bad block %d", i);
+  }
+  weight_reg_kernel<<<dim3(4 * kSMs, static_cast<unsigned>(desc->count)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*desc);
+  PULSE_LAUNCH_OK("weight_reg_kernel");
   return PULSE_OK;
 }
 

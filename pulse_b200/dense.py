@@ -30,7 +30,8 @@ def gemm_nt(a, b, **kw) -> None:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None, act=None,
          gate: Optional[torch.Tensor] = None, gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
          out_t: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
-         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, sumsq: Optional[torch.Tensor] = None) -> None:
+         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, sumsq: Optional[torch.Tensor] = None,
+         relu_mask: Optional[torch.Tensor] = None, gate_mask: Optional[torch.Tensor] = None) -> None:
     """D[M,N] = epilogue(sum_k A(m,k) B(n,k)).  a is [M,K] (K-major) or, with a_mn, [K,M] (MN-major: the reduction index
     is the row); likewise b is [N,K] or, with b_mn, [K,N].  No operand is ever transposed in memory."""
     lib = _lib.load()
@@ -85,6 +86,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if sumsq.dtype != torch.float64 or sumsq.numel() < 1:
             raise _lib.PulseError("sumsq must be an fp64 accumulator")
         ep.sumsq = sumsq.data_ptr()
+    for name, t in (("relu_mask", relu_mask), ("gate_mask", gate_mask)):      # ReLU masks as bit words, [ceil(N/32), >= M] int32, chunk-major
+        if t is not None:
+            if t.dtype != torch.int32 or t.dim() != 2 or t.stride(1) != 1 or t.shape[0] * 32 < N or t.shape[1] < M:
+                raise _lib.PulseError(f"{name} must be int32 [ceil(N/32), >= M] with contiguous rows, got {t.dtype} {tuple(t.shape)}")
+            if name == "relu_mask":
+                ep.relu_mask, ep.ld_rmask = t.data_ptr(), t.stride(0)
+            else:
+                ep.gate_mask, ep.ld_gmask = t.data_ptr(), t.stride(0)
     flags = (_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0)
     with torch.cuda.device(a.device):
         _lib.check(lib.pulse_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, C.byref(ep), split_k, flags,
@@ -94,7 +103,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 def _prepare(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None, act=None,
          gate: Optional[torch.Tensor] = None, gate_mode=None, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
          out_t: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
-         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, sumsq: Optional[torch.Tensor] = None) -> tuple:
+         colsum: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, sumsq: Optional[torch.Tensor] = None,
+         relu_mask: Optional[torch.Tensor] = None, gate_mask: Optional[torch.Tensor] = None) -> tuple:
     """Argument checks + epilogue descriptor of one problem of a grouped launch (same rules as gemm(), which stays the
     validated single-problem path and is deliberately left untouched)."""
     _check_bf16(a, "a")
@@ -148,6 +158,14 @@ def _prepare(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
         if sumsq.dtype != torch.float64 or sumsq.numel() < 1:
             raise _lib.PulseError("sumsq must be an fp64 accumulator")
         ep.sumsq = sumsq.data_ptr()
+    for name, t in (("relu_mask", relu_mask), ("gate_mask", gate_mask)):      # ReLU masks as bit words, [ceil(N/32), >= M] int32, chunk-major
+        if t is not None:
+            if t.dtype != torch.int32 or t.dim() != 2 or t.stride(1) != 1 or t.shape[0] * 32 < N or t.shape[1] < M:
+                raise _lib.PulseError(f"{name} must be int32 [ceil(N/32), >= M] with contiguous rows, got {t.dtype} {tuple(t.shape)}")
+            if name == "relu_mask":
+                ep.relu_mask, ep.ld_rmask = t.data_ptr(), t.stride(0)
+            else:
+                ep.gate_mask, ep.ld_gmask = t.data_ptr(), t.stride(0)
     flags = (_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0)
     return ep, M, N, K, flags, split_k
 

@@ -74,6 +74,8 @@ class FlatParams:
         self.params_bf16 = torch.zeros(self._numel, device=self.device, dtype=torch.bfloat16)
         self.sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self._adam_sync = torch.zeros(1, device=self.device, dtype=torch.int32)   # last-block counter of the self-contained Adam launch
+        self.clean = True                                                          # gradients are all zero
 
     def sync_bf16(self):
         """bf16 mirror <- fp32 masters (after init / checkpoint load; the Adam kernel keeps it current afterwards)."""
@@ -97,32 +99,46 @@ class FlatParams:
 
     def zero_grad(self):
         self.grads.zero_()
+        self.clean = True
 
-    def adam_step(self, lr: float, max_norm: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
-        """nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam step (amp_agent.py:725-750), two launches, no host sync."""
+    def begin_backward(self):
+        """Called once per minibatch before gradients are accumulated: clears the buffer only if the last accumulation was not followed by
+        an optimizer step (adam_step leaves the gradients zeroed -- the kernel clears what it consumed)."""
+        if not self.clean:
+            self.grads.zero_()
+        self.clean = False
+
+    def adam_step(self, lr: float, max_norm: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, zero_grads: bool = True):
+        """nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam step (amp_agent.py:725-750): the gradient-norm pass and ONE Adam launch that
+        also advances the device-side step counter, re-zeroes the norm accumulator and clears the consumed gradients; no host sync."""
         lib = _lib.load()
         with torch.cuda.device(self.device):
             st = _lib.current_stream(self.device)
             sumsq_ptr = None
             if max_norm and max_norm > 0:
-                self.sumsq.zero_()
                 _lib.check(lib.pulse_sum_squares(self.grads.data_ptr(), self._numel, self.sumsq.data_ptr(), st), "pulse_sum_squares")
                 sumsq_ptr = self.sumsq.data_ptr()
             _lib.check(lib.pulse_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                            self._numel, sumsq_ptr, float(max_norm or 0.0), lr, betas[0], betas[1], eps, self.step.data_ptr(),
-                                           self.params_bf16.data_ptr(), st),
+                                           self.params_bf16.data_ptr(), 3 if zero_grads else 2, self._adam_sync.data_ptr(), st),
                        "pulse_adam_step")
+        self.clean = bool(zero_grads)
 
 
 class Dense:
-    """One Linear layer: W [N, Kp] (K padded with zero columns, see pad_k), b [N]."""
+    """One Linear layer.  Plain: W [N, Kp] (K padded with zero columns, see pad_k) and b [N] as separate slots.
+    Bias-augmented (`aug`): ONE slot W [N, Kp] with Kp = pad_k(K + 1) whose column K holds the bias; the operand it multiplies carries
+    1.0 in its column K (written by the normalise kernels / set once in the activation buffers), so the bias add of the forward pass
+    and the bias gradient of the backward pass (column K of dW = dY^T [X | 1]) are done by the tensor cores -- no bias loads in the
+    forward epilogue, no column sums in the dgrad epilogue (both ran on the shared-memory pipe the UMMA operand reads saturate)."""
 
-    def __init__(self, flat: FlatParams, in_features: int, out_features: int, act: Optional[str]):
-        self.K, self.N, self.act = in_features, out_features, act
-        self.Kp, self.Np = pad_k(in_features), pad_k(out_features)
+    def __init__(self, flat: FlatParams, in_features: int, out_features: int, act: Optional[str], aug: bool = False):
+        self.K, self.N, self.act, self.aug = in_features, out_features, act, aug
+        self.Kp = pad_k(in_features + 1) if aug else pad_k(in_features)
+        self.Np = pad_k(out_features + 1) if aug else pad_k(out_features)    # width of this layer's OUTPUT buffer (= the next layer's Kp)
         self.flat = flat
         self.w_idx = flat.reserve(out_features, self.Kp)
-        self.b_idx = flat.reserve(out_features)
+        self.b_idx = None if aug else flat.reserve(out_features)
 
     # views (valid after flat.finalize())
     @property
@@ -131,7 +147,7 @@ class Dense:
 
     @property
     def bias(self):
-        return self.flat.view(self.b_idx)
+        return self.weight[:, self.K] if self.aug else self.flat.view(self.b_idx)
 
     @property
     def w_bf16(self):
@@ -143,7 +159,12 @@ class Dense:
 
     @property
     def bias_grad(self):
-        return self.flat.view(self.b_idx, "grads")
+        return self.weight_grad[:, self.K] if self.aug else self.flat.view(self.b_idx, "grads")
+
+    @property
+    def pad_start(self):
+        """first column of the weight matrix that must stay exactly zero"""
+        return self.K + (1 if self.aug else 0)
 
     def init_default(self, gen: Optional[torch.Generator] = None):
         """torch.nn.Linear default init (kaiming_uniform(a=sqrt(5)) -> U(-1/sqrt(K), 1/sqrt(K)) for W and b)."""
@@ -168,23 +189,35 @@ class MLP:
     hidden_acts: per-hidden-layer override (None = a Linear with no activation, e.g. the last Linear of `z_mlp` that feeds the
     `z_mu` / `z_logvar` heads, amp_network_z_builder.py:492-497).  input_grad_cols > 0: backward() also returns the gradient
     w.r.t. the first `input_grad_cols` input columns (the latent window of the PULSE decoder input).
-    in_perm: internal input column i holds reference input column in_perm[i] (checkpoint import / export of layer 0)."""
+    in_perm: internal input column i holds reference input column in_perm[i] (checkpoint import / export of layer 0).
+    aug: bias-augmented layers (see Dense) -- the caller's input operand must carry 1.0 in column `in_features`.
+    ReLU layers save their activation masks as bit words in the forward epilogue (train=True) and the backward pass gates with those."""
 
     def __init__(self, flat: FlatParams, in_features: int, units: Sequence[int], head: Optional[int], act: str = "relu",
-                 hidden_acts: Optional[Sequence[Optional[str]]] = None, input_grad_cols: int = 0, in_perm: Optional[torch.Tensor] = None):
+                 hidden_acts: Optional[Sequence[Optional[str]]] = None, input_grad_cols: int = 0, in_perm: Optional[torch.Tensor] = None,
+                 aug: bool = False):
         self.flat = flat
         self.act = act
+        self.aug = aug
         sizes = [in_features] + list(units)
         acts = list(hidden_acts) if hidden_acts is not None else [act] * len(units)
         if len(acts) != len(units):
             raise _lib.PulseError("hidden_acts must have one entry per hidden layer")
-        self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], acts[i]) for i in range(len(units))]
+        self.layers: List[Dense] = [Dense(flat, sizes[i], sizes[i + 1], acts[i], aug) for i in range(len(units))]
         if head is not None:
-            self.layers.append(Dense(flat, sizes[-1], head, None))
-        self.in_features, self.Kp0 = in_features, pad_k(in_features)
+            self.layers.append(Dense(flat, sizes[-1], head, None, aug))
+        self.in_features, self.Kp0 = in_features, self.layers[0].Kp
         self.input_grad_cols = input_grad_cols
         self.in_perm = in_perm
         self._ws: Dict[int, dict] = {}
+        self._scratch = None
+        self._zero = None
+
+    def _zero_bias(self) -> torch.Tensor:
+        """read-only zeros: the `bias` argument of the fused single-output-head kernel when the bias lives in the weight row"""
+        if self._zero is None:
+            self._zero = torch.zeros(8, device=self.flat.device)
+        return self._zero
 
     def init_default(self, gen=None):
         for l in self.layers:
@@ -199,13 +232,17 @@ class MLP:
         if key not in self._ws:
             dev = self.flat.device
             bf = lambda r, c: torch.zeros(r, c, device=dev, dtype=torch.bfloat16)
-            ws = {"act": [], "pre": [], "dact": [], "split": []}
+            ws = {"act": [], "pre": [], "dact": [], "split": [], "mask": []}
             for i, l in enumerate(self.layers):
                 last = i == len(self.layers) - 1
-                ws["act"].append(None if last else bf(M, l.Np))
+                a = None if last else bf(M, l.Np)
+                if a is not None and self.aug:
+                    a[:, l.N] = 1.0                    # the ones column the next (bias-augmented) layer multiplies its bias column with
+                ws["act"].append(a)
                 if train:
                     ws["pre"].append(bf(M, l.Np) if (l.act == "silu") else None)
                     ws["dact"].append(None if last else bf(M, l.Np))      # gradient w.r.t. this layer's OUTPUT
+                    ws["mask"].append(torch.zeros((l.N + 31) // 32, M, device=dev, dtype=torch.int32) if (l.act == "relu" and not last) else None)
                     tiles = ((l.N + 127) // 128) * ((l.Kp + 255) // 256)   # 128 x 256 output tiles
                     ws["split"].append(pick_split(tiles, (M + 63) // 64))
             hn = self.layers[-1].N     # fp32 head output: rows padded to a multiple of 4 floats so the epilogue's 16-byte stores apply (N = 69)
@@ -215,15 +252,49 @@ class MLP:
             self._ws[key] = ws
         return self._ws[key]
 
+    def _dummy(self, n: int) -> torch.Tensor:
+        """fp32 scratch the fused single-output-head kernels may add bias gradients into when the layers are bias-augmented (the weight
+        gradients already contain them); never read."""
+        if self._scratch is None or self._scratch.numel() < n:
+            self._scratch = torch.zeros(max(n, 8), device=self.flat.device)
+        return self._scratch
+
     def _head1(self, i: int) -> bool:
         """Layer i is a single-output head on top of a ReLU layer narrow enough for the fused GEMV kernels."""
         l = self.layers[i]
         return i == len(self.layers) - 1 and i > 0 and l.N == 1 and self.layers[i - 1].act == "relu" and l.Kp <= 2048
 
+    # ---- per-layer GEMM arguments, shared by the single-problem path below and the grouped (lock-step) path ----------------------
+    def _fwd_problem(self, i: int, h: torch.Tensor, ws: dict, train: bool):
+        l = self.layers[i]
+        kw = dict(bias=None if self.aug else l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)
+        if train and ws["mask"][i] is not None:
+            kw["relu_mask"] = ws["mask"][i]
+        return h[:, :l.Kp], l.w_bf16, kw
+
+    def _wgrad_problem(self, i: int, dy: torch.Tensor, x_in: torch.Tensor, ws: dict):
+        l = self.layers[i]
+        # dW [N, Kp] += dY^T . X, both operands MN-major (reduction over the batch rows), fp32 atomics across split-K; with augmented
+        # layers X carries the ones column, so column K of dW IS the bias gradient
+        return dy[:, :l.N], x_in[:, :l.Kp], dict(a_mn=True, b_mn=True, out_f32=l.weight_grad, accumulate=True, split_k=ws["split"][i])
+
+    def _dgrad_problem(self, i: int, dy: torch.Tensor, ws: dict):
+        """dX [M, K] = dY [M, N] . W [N, K] (W read MN-major), gated by act'(.) of the layer below."""
+        l, prev = self.layers[i], self.layers[i - 1]
+        kw = dict(b_mn=True, out=ws["dact"][i - 1])
+        if prev.act == "relu" and ws["mask"][i - 1] is not None:
+            kw["gate_mask"] = ws["mask"][i - 1]
+        elif prev.act is not None:
+            kw.update(gate=ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1], gate_mode=prev.act)
+        if not self.aug:   # plain layers: the epilogue also accumulates the bias gradient of the layer below (column sums of dX)
+            kw["colsum"] = self.flat.view_padded(prev.b_idx, "grads", prev.Np)
+        w = l.w_bf16[:, :prev.N] if self.aug else l.w_bf16       # augmented: never differentiate through the bias column
+        return dy[:, :l.N], w, kw
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, train: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x: bf16 [M, Kp0] (normalised, zero padded).  Returns fp32 [M, head] (view of a reused workspace buffer, or `out`).
-        With train=True the activations (and SiLU pre-activations) needed by backward() are kept."""
+        """x: bf16 [M, Kp0] (normalised, zero padded; column `in_features` = 1.0 for augmented nets).  Returns fp32 [M, head] (view of a
+        reused workspace buffer, or `out`).  With train=True the activations / ReLU masks / SiLU pre-activations backward() needs are kept."""
         M = x.shape[0]
         ws = self._workspace(M, train)
         if out is not None:
@@ -232,56 +303,61 @@ class MLP:
         for i, l in enumerate(self.layers):
             last = i == len(self.layers) - 1
             if last and self._head1(i):
-                # [M,K] x [K,1]: no tensor-core shape -- one HBM pass over h (pulse_head1_forward)
+                # [M,K] x [K,1]: no tensor-core shape -- one HBM pass over h (pulse_head1_forward); augmented: the bias is w[K] * h[:, K]
+                bias = self._zero_bias() if self.aug else l.bias
                 with torch.cuda.device(self.flat.device):
-                    _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), l.bias.data_ptr(),
+                    _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), bias.data_ptr(),
                                                                ws["out"].data_ptr(), ws["out"].stride(0),
                                                                _lib.current_stream(self.flat.device)), "pulse_head1_forward")
             elif last:
-                gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
+                gemm_nt(h[:, :l.Kp], l.w_bf16, bias=None if self.aug else l.bias, act=None, out_f32=ws["out"])
             else:
-                gemm_nt(h, l.w_bf16, bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)
+                a, b, kw = self._fwd_problem(i, h, ws, train)
+                gemm_nt(a, b, **kw)
                 h = ws["act"][i]
         if train:
             self._ws[(M, True)]["x"] = x
         return ws["out"]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dout: torch.Tensor, M: int) -> None:
-        """dout bf16 [M, pad8(head)]: gradient of the loss w.r.t. the head output.  ADDS dW, db of every layer into the
-        flat gradient buffer (the caller zeroes it once per minibatch with flat.zero_grad())."""
+    def _backward_head(self, ws: dict, dout: torch.Tensor, M: int):
+        """Head layer: returns (dy, top) = gradient w.r.t. the output of layer `top` still to be propagated."""
         lib = _lib.load()
-        ws = self._ws[(M, True)]
         dev = self.flat.device
-        dy = dout
         head = self.layers[-1]
         top = len(self.layers) - 1
         if self._head1(top):
             # single-output head: bias gradient, weight gradient, gated input gradient and the bias gradient of the layer
             # below in ONE pass over the last hidden activation (replaces a column sum and three degenerate GEMMs)
             prev, h, dh = self.layers[top - 1], ws["act"][top - 1], ws["dact"][top - 1]
+            if self.aug:
+                hb, pb = self._dummy(prev.Np + 8), self._dummy(prev.Np + 8)[8:]
+            else:
+                hb, pb = head.bias_grad, self.flat.view_padded(prev.b_idx, "grads", prev.Np)
             with torch.cuda.device(dev):
-                _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), M, head.Kp, dy.data_ptr(), dy.stride(0), head.w_bf16.data_ptr(),
-                                                    dh.data_ptr(), dh.stride(0), head.weight_grad.data_ptr(), head.bias_grad.data_ptr(),
-                                                    self.flat.view_padded(prev.b_idx, "grads", prev.Np).data_ptr(), _lib.current_stream(dev)),
-                           "pulse_head1_backward")
-            dy, top = dh, top - 1
-        else:
+                _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), M, head.Kp, dout.data_ptr(), dout.stride(0), head.w_bf16.data_ptr(),
+                                                    dh.data_ptr(), dh.stride(0), head.weight_grad.data_ptr(), hb.data_ptr(), pb.data_ptr(),
+                                                    _lib.current_stream(dev)), "pulse_head1_backward")
+            return dh, top - 1
+        if not self.aug:
             with torch.cuda.device(dev):  # bias gradient of the head: column sums of dout
-                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
+                _lib.check(lib.pulse_column_sum_bf16(dout.data_ptr(), dout.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
                            "pulse_column_sum_bf16")
+        return dout, top
+
+    def backward(self, dout: torch.Tensor, M: int) -> None:
+        """dout bf16 [M, pad8(head)]: gradient of the loss w.r.t. the head output.  ADDS dW, db of every layer into the
+        flat gradient buffer (the caller zeroes it once per minibatch with flat.zero_grad())."""
+        ws = self._ws[(M, True)]
+        dy, top = self._backward_head(ws, dout, M)
         for i in reversed(range(top + 1)):
             l = self.layers[i]
             x_in = ws["x"] if i == 0 else ws["act"][i - 1]
-            # wgrad: dW [N, Kp] += dY^T . X, both operands MN-major (reduction over the batch rows), fp32 atomics across split-K
-            gemm(dy[:, :l.N], x_in[:, :l.Kp], a_mn=True, b_mn=True, out_f32=l.weight_grad, accumulate=True, split_k=ws["split"][i])
+            a, b, kw = self._wgrad_problem(i, dy, x_in, ws)
+            gemm(a, b, **kw)
             if i > 0:
-                prev = self.layers[i - 1]
-                # dgrad: dX [M, K] = dY [M, N] . W [N, K] (W read MN-major), gated by act'(.) of the layer below; the epilogue
-                # also accumulates that layer's bias gradient (column sums of dX)
-                gate = None if prev.act is None else (ws["pre"][i - 1] if prev.act == "silu" else ws["act"][i - 1])
-                gemm(dy[:, :l.N], l.w_bf16, b_mn=True, gate=gate, gate_mode=prev.act, out=ws["dact"][i - 1],
-                     colsum=self.flat.view_padded(prev.b_idx, "grads", prev.Np))
+                a, b, kw = self._dgrad_problem(i, dy, ws)
+                gemm(a, b, **kw)
                 dy = ws["dact"][i - 1]
             elif self.input_grad_cols:
                 # gradient w.r.t. the leading input columns only: dX[:, :c] = dY . W[:, :c]
@@ -319,15 +395,17 @@ class MLP:
 
 
 def normalize_to_bf16(x: torch.Tensor, mean: Optional[torch.Tensor], rstd: Optional[torch.Tensor], out: torch.Tensor,
-                      out_t: Optional[torch.Tensor] = None) -> None:  # out_t: optional transposed copy (not used by the MLPs any more)
-    """RunningMeanStd eval path (running_mean_std.py:69-95) fused with the bf16 cast / zero pad / transpose."""
+                      out_t: Optional[torch.Tensor] = None, pad_one: float = 0.0) -> None:  # out_t: optional transposed copy (not used by the MLPs any more)
+    """RunningMeanStd eval path (running_mean_std.py:69-95) fused with the bf16 cast / zero pad / transpose.  pad_one = 1.0 writes the
+    "ones" column of a bias-augmented operand into the first pad column."""
     lib = _lib.load()
     rows, cols = x.shape
     if x.dtype != torch.float32 or x.stride(1) != 1:
         raise _lib.PulseError("normalize_to_bf16: x must be fp32 with contiguous rows")
     with torch.cuda.device(x.device):
         _lib.check(lib.pulse_normalize_to_bf16(x.data_ptr(), x.stride(0), rows, cols, _lib.ptr(mean), _lib.ptr(rstd), out.data_ptr(), out.stride(0),
-                                               _lib.ptr(out_t), out_t.stride(0) if out_t is not None else 0, _lib.current_stream(x.device)),
+                                               _lib.ptr(out_t), out_t.stride(0) if out_t is not None else 0, float(pad_one),
+                                               _lib.current_stream(x.device)),
                    "pulse_normalize_to_bf16")
 
 
@@ -346,23 +424,20 @@ def forward_lockstep(mlps: Sequence["MLP"], xs: Sequence[torch.Tensor], train: b
     wss = [m._workspace(M, train) for m in mlps]
     hs = list(xs)
     for i in range(depth - 1):
-        probs = []
-        for m, ws, h in zip(mlps, wss, hs):
-            l = m.layers[i]
-            probs.append((h, l.w_bf16, dict(bias=l.bias, act=l.act, out=ws["act"][i], preact=ws["pre"][i] if train else None)))
-        gemm_grouped(probs)
+        gemm_grouped([m._fwd_problem(i, h, ws, train) for m, ws, h in zip(mlps, wss, hs)])
         hs = [ws["act"][i] for ws in wss]
     outs = []
     for m, ws, h, x in zip(mlps, wss, hs, xs):       # heads: the single-net code of MLP.forward (GEMV kernel or fp32-output GEMM)
         i = depth - 1
         l = m.layers[i]
         if m._head1(i):
+            bias = m._zero_bias() if m.aug else l.bias
             with torch.cuda.device(m.flat.device):
-                _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), l.bias.data_ptr(),
+                _lib.check(_lib.load().pulse_head1_forward(h.data_ptr(), h.stride(0), M, l.Kp, l.w_bf16.data_ptr(), bias.data_ptr(),
                                                            ws["out"].data_ptr(), ws["out"].stride(0), _lib.current_stream(m.flat.device)),
                            "pulse_head1_forward")
         else:
-            gemm_nt(h, l.w_bf16, bias=l.bias, act=None, out_f32=ws["out"])
+            gemm_nt(h[:, :l.Kp], l.w_bf16, bias=None if m.aug else l.bias, act=None, out_f32=ws["out"])
         if train:
             m._ws[(M, True)]["x"] = x
         outs.append(ws["out"])
@@ -372,25 +447,11 @@ def forward_lockstep(mlps: Sequence["MLP"], xs: Sequence[torch.Tensor], train: b
 def backward_lockstep(mlps: Sequence["MLP"], douts: Sequence[torch.Tensor], M: int) -> None:
     """ADDS the weight / bias gradients of every net into its flat gradient buffer (see MLP.backward)."""
     from .dense import gemm_grouped
-    lib = _lib.load()
     depth = len(mlps[0].layers)
     wss = [m._ws[(M, True)] for m in mlps]
     dys, tops = [], []
     for m, ws, dy in zip(mlps, wss, douts):           # heads first, per net (MLP.backward's head handling)
-        dev = m.flat.device
-        head, top = m.layers[-1], depth - 1
-        if m._head1(top):
-            prev, h, dh = m.layers[top - 1], ws["act"][top - 1], ws["dact"][top - 1]
-            with torch.cuda.device(dev):
-                _lib.check(lib.pulse_head1_backward(h.data_ptr(), h.stride(0), M, head.Kp, dy.data_ptr(), dy.stride(0), head.w_bf16.data_ptr(),
-                                                    dh.data_ptr(), dh.stride(0), head.weight_grad.data_ptr(), head.bias_grad.data_ptr(),
-                                                    m.flat.view_padded(prev.b_idx, "grads", prev.Np).data_ptr(), _lib.current_stream(dev)),
-                           "pulse_head1_backward")
-            dy, top = dh, top - 1
-        else:
-            with torch.cuda.device(dev):
-                _lib.check(lib.pulse_column_sum_bf16(dy.data_ptr(), dy.stride(0), M, head.N, head.bias_grad.data_ptr(), _lib.current_stream(dev)),
-                           "pulse_column_sum_bf16")
+        dy, top = m._backward_head(ws, dy, M)
         dys.append(dy)
         tops.append(top)
     for i in reversed(range(depth)):
@@ -400,15 +461,12 @@ def backward_lockstep(mlps: Sequence["MLP"], douts: Sequence[torch.Tensor], M: i
         wg, dg = [], []
         for j in live:
             m, ws, dy = mlps[j], wss[j], dys[j]
-            l = m.layers[i]
             x_in = ws["x"] if i == 0 else ws["act"][i - 1]
-            wg.append((dy[:, :l.N], x_in[:, :l.Kp], dict(a_mn=True, b_mn=True, out_f32=l.weight_grad, accumulate=True, split_k=ws["split"][i])))
+            wg.append(m._wgrad_problem(i, dy, x_in, ws))
             if i > 0:
-                prev = m.layers[i - 1]
-                if prev.act != "relu":
+                if m.layers[i - 1].act != "relu":
                     raise _lib.PulseError("backward_lockstep groups ReLU nets only (the grouped dgrad kernel is the ReLU-gate specialisation)")
-                dg.append((dy[:, :l.N], l.w_bf16, dict(b_mn=True, gate=ws["act"][i - 1], gate_mode="relu", out=ws["dact"][i - 1],
-                                                        colsum=m.flat.view_padded(prev.b_idx, "grads", prev.Np))))
+                dg.append(m._dgrad_problem(i, dy, ws))
         gemm_grouped(wg)
         if dg:
             gemm_grouped(dg)

@@ -32,6 +32,7 @@ class RunningMeanStdB200:
         self.count = torch.ones((), dtype=torch.float64, device=device)
         self._sums = torch.zeros(2 * size, dtype=torch.float64, device=device)
         self.frozen = False
+        self.pad_one = 0.0     # 1.0: the first pad column of the normalised bf16 operand is the "ones" column of a bias-augmented first layer
         self.mean_f32 = torch.zeros(size, dtype=torch.float32, device=device)
         self.rstd_f32 = torch.ones(size, dtype=torch.float32, device=device)
         self._refresh()
@@ -64,12 +65,12 @@ class RunningMeanStdB200:
         lib = _lib.load()
         with torch.cuda.device(self.device):
             _lib.check(lib.pulse_normalize_moments(x.data_ptr(), x.stride(0), x.shape[0], self.size, self.mean_f32.data_ptr(),
-                                                   self.rstd_f32.data_ptr(), out.data_ptr(), out.stride(0), self._sums.data_ptr(),
+                                                   self.rstd_f32.data_ptr(), out.data_ptr(), out.stride(0), self._sums.data_ptr(), self.pad_one,
                                                    _lib.current_stream(self.device)), "pulse_normalize_moments")
             self._merge(lib, x.shape[0])
 
     def normalize_into(self, x: torch.Tensor, out: torch.Tensor, out_t: Optional[torch.Tensor] = None) -> None:
-        normalize_to_bf16(x, self.mean_f32, self.rstd_f32, out, out_t)
+        normalize_to_bf16(x, self.mean_f32, self.rstd_f32, out, out_t, pad_one=self.pad_one)
 
     def unnormalize(self, y: torch.Tensor) -> torch.Tensor:
         """forward(unnorm=True) (:84-87): clamp to +-5 then scale back (value de-normalisation)."""
@@ -88,8 +89,9 @@ class PPOPolicy:
         self.obs_size, self.A = obs_size, num_actions
         self.lr, self.e_clip, self.critic_coef, self.bounds_coef, self.grad_norm = lr, e_clip, critic_coef, bounds_coef, grad_norm
         self.flat = FlatParams(self.device)
-        self.actor = MLP(self.flat, obs_size, units, num_actions, act)
-        self.critic = MLP(self.flat, obs_size, units, 1, act)
+        # bias-augmented layers (nets.Dense): bias add and bias gradients are done by the tensor cores, the epilogues carry neither
+        self.actor = MLP(self.flat, obs_size, units, num_actions, act, aug=True)
+        self.critic = MLP(self.flat, obs_size, units, 1, act, aug=True)
         self.disc = None
         if with_disc:  # one optimizer / one grad-norm clip over actor + critic + discriminator, as in the reference
             from .amp import AmpDiscriminator
@@ -102,8 +104,9 @@ class PPOPolicy:
             self.disc.mlp.init_default(gen)
         self.logstd = torch.full((num_actions,), logstd, device=self.device)  # fixed_sigma, const_initializer (im.yaml:21-25)
         self.obs_rms = RunningMeanStdB200(obs_size, self.device)
+        self.obs_rms.pad_one = 1.0             # the normalised observation operand carries the first layers' ones column
         self.value_rms = RunningMeanStdB200(1, self.device) if normalize_value else None
-        self.Kp = pad_k(obs_size)
+        self.Kp = self.actor.Kp0
         self._bufs: Dict[tuple, dict] = {}
         self.stats = torch.zeros(6, dtype=torch.float64, device=self.device)
         self.lib = _lib.load()
@@ -203,7 +206,7 @@ class PPOPolicy:
 
     # ------------------------------------------------------------------ update side
     def train_minibatch(self, obs, actions, old_neglogp, advantages, returns, old_mu=None, update_obs_rms: bool = True,
-                        world_size: int = 1, amp=None) -> torch.Tensor:
+                        world_size: int = 1, amp=None, keep_grads: bool = False) -> torch.Tensor:
         """One calc_gradients step (amp_agent.py:605-760, PPO branch without the discriminator term).
         `returns` are already value-normalised (prepare_dataset, common_agent.py:372-374).  Returns the fp64
         stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
@@ -216,7 +219,7 @@ class PPOPolicy:
         if self._side is None:
             self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         s_critic, s_disc = self._side
-        self.flat.zero_grad()                                # weight / bias gradients are accumulated with atomics
+        self.flat.begin_backward()                                # weight / bias gradients are accumulated with atomics
         self.stats.zero_()
         if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
             s_disc.wait_stream(main)
@@ -259,7 +262,7 @@ class PPOPolicy:
         if world_size > 1:
             from .dist_utils import average_gradients
             average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)
-        self.flat.adam_step(self.lr, max_norm=self.grad_norm)  # also writes the bf16 operand mirror
+        self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
         return self.stats
 
     # ------------------------------------------------------------------ checkpoint keys (rl_games layout)

@@ -187,7 +187,7 @@ class PulseVAE:
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         side = self._side
-        self.flat.zero_grad()
+        self.flat.begin_backward()
         self.stats.zero_()
         out = self.eval_actor(obs, noise, train=True, update_obs_rms=update_obs_rms)        # encoder -> z -> decoder
         side.wait_stream(main)

@@ -65,7 +65,7 @@ def test_ppo_minibatch_grouped_matches_three_stream_path(monkeypatch):
     for flag in ("0", "1"):
         monkeypatch.setenv("PULSE_GROUPED", flag)
         pol = PPOPolicy(device=DEV, seed=5)
-        stats = pol.train_minibatch(obs, act, nlp, adv, ret, update_obs_rms=False).clone()
+        stats = pol.train_minibatch(obs, act, nlp, adv, ret, update_obs_rms=False, keep_grads=True).clone()
         torch.cuda.synchronize()
         results.append((stats, pol.flat.grads.clone(), pol.flat.params.clone()))
     torch.testing.assert_close(results[1][0], results[0][0], atol=1e-6, rtol=1e-6)
