@@ -233,11 +233,11 @@ def workload_config(a, world, envs_total):
                    "GAE + returns + adv-norm (K11,K12)", "value/return normalisation (running stats)",
                    f"{MINI_EPOCHS} mini-epochs x minibatches: obs-RMS update, actor/critic fwd, PPO loss, bwd (dgrad+wgrad), "
                    "discriminator loss on 3x4096 AMP rows: BCE + logit reg + weight decay + ANALYTIC gradient penalty (K14), "
-                   "NCCL grad all-reduce (N>1), grad-norm clip + Adam incl. bf16 operand mirror (K13,K15,K16)",
+                   "NCCL gradient averaging per network chain on its own stream / communicator, overlapped with the other chains (N>1), "
+                   "grad-norm clip + Adam incl. bf16 operand mirror (K13,K15,K16); per mini-epoch KL average and per-epoch RunningMeanStd sync across "
+                   "ranks (N>1; common_agent.py:126-127, amp_agent.py:523-524)",
                    "AMP demo fetch (MotionLib query + AMP obs), demo / replay ring updates and per-minibatch draws"],
         "not_yet": ["physics (gym.simulate + refresh/set tensor calls): excluded on every arm",
-                    "per-epoch cross-rank RunningMeanStd sync + KL average (hvd.sync_stats / average_value, common_agent.py:126-127, amp_agent.py:524)"
-                    if world > 1 else "cross-rank statistics sync: n/a at 1 GPU",
                     "rl_games bookkeeping outside the arithmetic: episode reward / length meters, tensorboard / wandb logging, checkpoint writes",
                     "AMP replay-buffer insertion uses a fixed-size random subset (amp_replay_keep_prob) instead of a Bernoulli mask"],
         "physics": "excluded (Isaac Gym not installable; simulator state tensors are synthetic, resident in HBM)",
@@ -419,8 +419,13 @@ def main():
             us.record()
             phase_events.append((r0, r1, us))
         for _ in range(MINI_EPOCHS):
+            policy.reset_stats()                           # loss / KL statistics accumulate over the mini-epoch's minibatches
             for i in range(num_mb):
                 run(("upd", i), update_mb, i)
+            if world > 1:                                  # av_kls = hvd.average_value(av_kls) per mini-epoch (amp_agent.py:523-524)
+                dist.all_reduce(policy.stats, op=dist.ReduceOp.AVG)
+        if world > 1:                                      # hvd.sync_stats once per epoch (common_agent.py:126-127)
+            policy.sync_stats(world)
         if record:
             ue.record()
             update_events.append((us, ue))

@@ -10,8 +10,9 @@ logging, checkpoint cadence and the experience buffer, Isaac Gym keeps the physi
     class HumanoidImDistillB200(HumanoidImDistillB200Mixin, HumanoidImB200Mixin, HumanoidImDistill): pass
 
 These classes only route tensors to `PPOPolicy` / `PulseVAE` / `TeacherPNN` / `ReachTaskB200`; every number is computed by
-the CUDA library (no CPU fallback).  They cannot be exercised in this repository's tests because rl_games and Isaac Gym are
-not installable here; the objects they delegate to are what the GPU parity tests cover.
+the CUDA library (no CPU fallback).  rl_games and Isaac Gym are not installable here: tests/test_gpu_boundary.py mixes
+these classes in front of stand-in base classes (tests/standins.py) that carry the reference's attribute / method contract, and
+tests/test_boundary_cpu.py checks that contract against the unmodified reference sources where /root/reference exists.
 
 Reference methods mirrored:
   CommonAgent.get_action_values   phc/learning/common_agent.py:262-288
@@ -36,16 +37,33 @@ from .rollout import discount_values
 from .vae import PulseVAE, TeacherPNN, pd_targets
 
 
+def _mlp_shape(seq) -> tuple:
+    """(hidden units, activation name) of an nn.Sequential of Linear / activation modules (what network_builder._build_mlp makes)."""
+    units = [int(m.out_features) for m in seq if hasattr(m, "out_features")]
+    acts = [type(m).__name__.lower() for m in seq if not hasattr(m, "out_features")]
+    act = "silu" if any(a == "silu" for a in acts) else "relu"
+    return tuple(units), act
+
+
 class AMPAgentB200Mixin:
-    """Agent side.  Expects the reference agent's attributes (`vec_env`, `horizon_length`, `normalize_value`, `e_clip`,
-    `critic_coef`, `bounds_loss_coef`, `grad_norm`, `last_lr`, `_amp_minibatch_size`, `only_kin_loss`, `multi_gpu`, ...)."""
+    """Agent side.  Expects the reference agent's attributes (`vec_env`, `model`, `optimizer`, `horizon_length`, `normalize_value`, `e_clip`,
+    `critic_coef`, `bounds_loss_coef`, `grad_norm`, `last_lr`, `_amp_minibatch_size`, `only_kin_loss`, `multi_gpu`, `running_mean_std`,
+    `value_mean_std`, `_amp_input_mean_std`, ...).
+
+    Ownership of state (so that rl_games' checkpoint cadence keeps working, common_agent.py:142-150):
+      * network weights, Adam moments, observation / AMP-input normalisers: trained INSIDE the device library (`self._pulse`); every
+        `get_weights / get_stats_weights / get_full_state_weights` first writes them back into `self.model`, `self.running_mean_std`,
+        `self._amp_input_mean_std` and `self.optimizer.state`, so `save()` serialises what was trained;
+      * value normaliser: `self.value_mean_std` stays the owner (the reference's `prepare_dataset` updates it, common_agent.py:372-374)
+        and is mirrored into the library after every `prepare_dataset`;
+      * `set_weights / set_stats_weights / set_full_state_weights` (restore) rebuild the device-side copy from the loaded modules."""
 
     def _pulse_policy(self):
         """Build the device-side networks lazily from the reference model's parameters (same checkpoint keys)."""
         if getattr(self, "_pulse", None) is None:
             task = self.vec_env.env.task
-            sd = {k: v.detach() for k, v in self.model.state_dict().items()}
             dev = self.ppo_device
+            net = self.model.a2c_network
             if getattr(task, "z_type", None) == "vae" and getattr(task, "distill", False):
                 self._pulse = PulseVAE(self_obs_size=task.get_self_obs_size(), task_obs_size=task.get_task_obs_size(),
                                        num_actions=task.get_action_size(), latent=int(task.cfg["env"].get("embedding_size", 32)), device=dev,
@@ -54,12 +72,106 @@ class AMPAgentB200Mixin:
                                        ar1_coefficient=float(task.ar1_coefficient), use_ar1_prior=bool(task.use_ar1_prior),
                                        use_vae_prior_regu=bool(task.use_vae_prior_regu), horizon=int(self.horizon_length))
             else:
-                self._pulse = PPOPolicy(obs_size=self.obs_shape[0], num_actions=self.actions_num, device=dev, lr=float(self.last_lr),
-                                        e_clip=float(self.e_clip), critic_coef=float(self.critic_coef), bounds_coef=float(self.bounds_loss_coef),
-                                        grad_norm=float(self.grad_norm), normalize_value=bool(self.normalize_value), with_disc=True,
-                                        amp_obs_size=int(self._amp_observation_space.shape[0]))
-            self._pulse.load_state_dict(sd)
+                units, act = _mlp_shape(net.actor_mlp)                                   # im.yaml / pulse_z_task.yaml / im_big.yaml alike
+                disc_units, _ = _mlp_shape(net._disc_mlp)
+                self._pulse = PPOPolicy(obs_size=self.obs_shape[0], num_actions=self.actions_num, units=units, act=act, device=dev,
+                                        lr=float(self.last_lr), e_clip=float(self.e_clip), critic_coef=float(self.critic_coef),
+                                        bounds_coef=float(self.bounds_loss_coef), grad_norm=float(self.grad_norm),
+                                        normalize_value=bool(self.normalize_value), with_disc=True,
+                                        amp_obs_size=int(self._amp_observation_space.shape[0]), disc_units=disc_units)
+            self._pulse_load_from_model()
         return self._pulse
+
+    # ------------------------------------------------------------------ state exchange with the reference objects
+    def _pulse_stats_modules(self):
+        return (("running_mean_std", getattr(self, "running_mean_std", None)), ("reward_mean_std", getattr(self, "value_mean_std", None)),
+                ("amp_input_mean_std", getattr(self, "_amp_input_mean_std", None)))
+
+    def _pulse_load_from_model(self) -> None:
+        pol = self._pulse
+        sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+        for sec, mod in self._pulse_stats_modules():
+            if mod is not None:
+                for k, v in mod.state_dict().items():
+                    sd[f"{sec}.{k}"] = v.detach()
+        pol.load_state_dict(sd)
+        if isinstance(pol, PPOPolicy) and getattr(self, "optimizer", None) is not None:
+            named = dict(self.model.named_parameters())
+            state = {n: self.optimizer.state[p] for n, p in named.items() if p in self.optimizer.state and len(self.optimizer.state[p])}
+            pol.load_optimizer_state(state)
+
+    def _pulse_write_back(self) -> None:
+        """Device-side training state -> the reference objects rl_games serialises."""
+        pol = getattr(self, "_pulse", None)
+        if pol is None:
+            return
+        sd = pol.state_dict()
+        own = self.model.state_dict()
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own:
+                    own[k].copy_(v.to(own[k].device, own[k].dtype))
+            for sec, mod in self._pulse_stats_modules():
+                if mod is None or (sec == "reward_mean_std" and isinstance(pol, PPOPolicy)):
+                    continue                             # the value normaliser is owned by the reference module (see class docstring)
+                st = mod.state_dict()
+                for k in ("running_mean", "running_var", "count"):
+                    if f"{sec}.{k}" in sd and k in st:
+                        st[k].copy_(sd[f"{sec}.{k}"].to(st[k].device, st[k].dtype).reshape(st[k].shape))
+            if isinstance(pol, PPOPolicy) and getattr(self, "optimizer", None) is not None:
+                opt_state = pol.optimizer_state()
+                for n, p in self.model.named_parameters():
+                    if n in opt_state:
+                        tgt = self.optimizer.state[p]
+                        for k, v in opt_state[n].items():
+                            tgt[k] = v.to(p.device) if k != "step" else v.to("cpu")
+
+    def _pulse_mirror_value_stats(self) -> None:
+        pol, mod = getattr(self, "_pulse", None), getattr(self, "value_mean_std", None)
+        if pol is None or mod is None or getattr(pol, "value_rms", None) is None:
+            return
+        st = mod.state_dict()
+        pol.value_rms.running_mean.copy_(st["running_mean"].double().reshape(-1))
+        pol.value_rms.running_var.copy_(st["running_var"].double().reshape(-1))
+        pol.value_rms.count.copy_(st["count"].double().reshape(()))
+        pol.value_rms._refresh()
+
+    def get_stats_weights(self):
+        self._pulse_write_back()
+        return super().get_stats_weights()
+
+    def get_weights(self):
+        self._pulse_write_back()
+        return super().get_weights()
+
+    def get_full_state_weights(self):
+        self._pulse_write_back()
+        return super().get_full_state_weights()
+
+    def set_stats_weights(self, weights):
+        super().set_stats_weights(weights)
+        self._pulse = None                               # rebuilt from the restored modules at the next use
+
+    def set_weights(self, weights):
+        super().set_weights(weights)
+        self._pulse = None
+
+    def set_full_state_weights(self, weights):
+        super().set_full_state_weights(weights)
+        self._pulse = None
+
+    def prepare_dataset(self, batch_dict):
+        out = super().prepare_dataset(batch_dict)        # normalises values / returns and merges them into value_mean_std (common_agent.py:372-374)
+        self._pulse_mirror_value_stats()
+        return out
+
+    def train_epoch(self):
+        info = super().train_epoch()
+        if getattr(self, "multi_gpu", False) and torch.distributed.is_initialized():   # hvd.sync_stats (common_agent.py:126-127)
+            pol = self._pulse_policy()
+            if isinstance(pol, PPOPolicy):
+                pol.sync_stats(torch.distributed.get_world_size())
+        return info
 
     # ------------------------------------------------------------------ rollout side
     def get_action_values(self, obs):
@@ -105,12 +217,14 @@ class AMPAgentB200Mixin:
         n = self._amp_minibatch_size
         M = input_dict["obs"].shape[0]
         pol.lr = float(self.last_lr)
+        pol.reset_stats()                                    # per-minibatch statistics, as the reference logs them
         stats = pol.train_minibatch(input_dict["obs"], input_dict["actions"], input_dict["old_logp_actions"], input_dict["advantages"],
                                     input_dict["returns"], old_mu=input_dict["mu"], world_size=world,
                                     amp=(input_dict["amp_obs"][0:n], input_dict["amp_obs_replay"][0:n], input_dict["amp_obs_demo"][0:n]))
         s = stats / M                                        # fp64 on the device; .item() only where the reference logs
         self.train_result.update({"actor_loss": s[0], "critic_loss": s[1], "b_loss": s[2], "kl": s[3], "actor_clip_frac": s[4],
                                   "entropy": torch.zeros((), device=stats.device), "last_lr": self.last_lr, "lr_mul": 1.0})
+        self.train_result.update(pol.disc.loss_tensors(n))   # disc_loss, disc_agent_acc, ... (AMPAgent._assemble_train_info reads them)
 
     def _optimize_kin(self, batch_dict):
         """batch_dict['obs_orig']: raw observations of the minibatch (normalised inside, as `_preproc_obs` does);

@@ -128,6 +128,18 @@ class AmpDiscriminator:
         return {"disc_loss": loss, "disc_grad_penalty": gp, "disc_logit_loss": float(s[5]), "disc_agent_acc": float(s[2]) / (2 * B),
                 "disc_demo_acc": float(s[3]) / B}
 
+    def loss_tensors(self, B: int) -> Dict[str, torch.Tensor]:
+        """The entries `AMPAgent._disc_loss` returns (amp_agent.py:939-952) as DEVICE tensors from the statistics of the last
+        loss_backward call (no host synchronisation; the mean logits are read from the logits that call left in the workspace)."""
+        s = self.stats
+        c = 2.0 * self.disc_coef * self.grad_penalty / B
+        gp = s[4] / (c * c) / B
+        bce = 0.5 * (s[0] / (2 * B) + s[1] / B)
+        logits = self.mlp._ws[(3 * B, True)]["out"]
+        return {"disc_loss": bce + self.logit_reg * s[5] + self.grad_penalty * gp + self.weight_decay * s[6], "disc_grad_penalty": gp,
+                "disc_logit_loss": s[5].clone(), "disc_agent_acc": s[2] / (2 * B), "disc_demo_acc": s[3] / B,
+                "disc_agent_logit": logits[:2 * B].mean(), "disc_demo_logit": logits[2 * B:].mean()}
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
         sd = {f"a2c_network.{k}": v for k, v in self.mlp.state_dict("_disc_mlp", "_disc_logits").items()}
         sd["amp_input_mean_std.running_mean"] = self.rms.running_mean.clone()

@@ -58,3 +58,30 @@ def sync_running_stats(mean: torch.Tensor, var: torch.Tensor, count: torch.Tenso
         return
     for t in (mean, var, count):
         average_gradients(t, world)
+
+
+class ChainReducer:
+    """Gradient averaging that OVERLAPS with the backward pass: the flat gradient buffer holds the actor, critic and discriminator slices
+    back to back, and each network's backward chain runs on its own CUDA stream (ppo.PPOPolicy.train_minibatch) -- so each slice is
+    all-reduced on ITS stream as soon as that chain has produced it, through its own communicator (one NCCL communicator serialises its
+    collectives; three let the critic's and the discriminator's reductions run under the remaining GEMMs).  Only the reduction of the chain
+    that finishes last is exposed.  Replaces the single 22 MB all-reduce after all chains joined (round 1: 24 x 136 us per iteration at
+    8 GPUs, none of it overlapped) -- Horovod's DistributedOptimizer also reduces gradients as they become ready (amp_agent.py:735-742)."""
+
+    def __init__(self, world: int, num_chains: int = 3):
+        self.world = world
+        self.groups = [None]
+        if world > 1:
+            for _ in range(num_chains - 1):        # every rank creates the groups in the same order
+                self.groups.append(dist.new_group(ranks=list(range(world))))
+
+    def reduce(self, grads_slice: torch.Tensor, chain: int) -> None:
+        """Average `grads_slice` over the ranks on the CURRENT stream's timeline (chain 0 = default communicator)."""
+        if self.world <= 1:
+            return
+        g = self.groups[chain % len(self.groups)]
+        if grads_slice.is_cuda:
+            dist.all_reduce(grads_slice, op=dist.ReduceOp.AVG, group=g)
+        else:
+            dist.all_reduce(grads_slice, op=dist.ReduceOp.SUM, group=g)
+            grads_slice.div_(self.world)

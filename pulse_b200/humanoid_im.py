@@ -359,7 +359,9 @@ class HumanoidImB200Mixin:
                     self_obs_buf=self.self_obs_buf, rew_buf=self.rew_buf, reward_raw=self.reward_raw,
                     reset_buf=self.reset_buf, terminate_buf=self._terminate_buf, pass_time=self._pulse_pass_time,
                     ref_body_pos=self.ref_body_pos, ref_body_vel=self.ref_body_vel, ref_body_rot=self.ref_body_rot,
-                    ref_dof_pos=self.ref_dof_pos)
+                    ref_dof_pos=self.ref_dof_pos,
+                    # HumanoidImGetup: recovering envs are masked inside the kernel (humanoid_im_getup.py:203-210 never runs behind this mixin)
+                    recovery_counter=getattr(self, "_recovery_counter", None))
 
     def _compute_reward(self, actions):
         args = self._pulse_args()
@@ -396,13 +398,18 @@ class HumanoidImB200Mixin:
             args["env_ids"] = env_ids.to(torch.int64).contiguous()
         self._pulse.step(flags=_lib.STEP_OBS, **args)
 
+    def _pulse_amp_fused(self, env_ids) -> bool:
+        """The fused AMP launch (history shift + current observation) covers the whole-batch call of the default configuration; one
+        predicate for BOTH overrides below, so the shift is skipped exactly when the fused launch performs it."""
+        return env_ids is None and getattr(self, "amp_obs_v", 1) == 1 and bool(getattr(self, "_has_dof_subset", True))
+
     def _update_hist_amp_obs(self, env_ids=None):
-        if env_ids is None:
+        if self._pulse_amp_fused(env_ids):
             return  # folded into _compute_amp_observations (one launch does shift + write)
         super()._update_hist_amp_obs(env_ids)
 
     def _compute_amp_observations(self, env_ids=None):
-        if env_ids is not None or getattr(self, "amp_obs_v", 1) != 1 or not getattr(self, "_has_dof_subset", True):
+        if not self._pulse_amp_fused(env_ids):
             return super()._compute_amp_observations(env_ids)
         if not self._pulse_ready:
             self._pulse_setup()

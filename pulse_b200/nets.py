@@ -97,6 +97,12 @@ class FlatParams:
     def numel(self):
         return self._numel
 
+    def slot_span(self, first_idx: int, last_idx: int):
+        """[start, end) element range of the flat buffers covered by slots first_idx .. last_idx (alignment padding included)."""
+        start = self._shapes[first_idx][0]
+        end = self._shapes[last_idx + 1][0] if last_idx + 1 < len(self._shapes) else self._numel
+        return start, end
+
     def zero_grad(self):
         self.grads.zero_()
         self.clean = True
@@ -212,6 +218,11 @@ class MLP:
         self._ws: Dict[int, dict] = {}
         self._scratch = None
         self._zero = None
+
+    def param_span(self):
+        """[start, end) of this network's parameters / gradients inside the flat buffers (its layers are reserved back to back)."""
+        idx = [i for l in self.layers for i in (l.w_idx, l.b_idx) if i is not None]
+        return self.flat.slot_span(min(idx), max(idx))
 
     def _zero_bias(self) -> torch.Tensor:
         """read-only zeros: the `bias` argument of the fused single-output-head kernel when the bias lives in the weight row"""

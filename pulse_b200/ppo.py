@@ -196,6 +196,30 @@ class PPOPolicy:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_bump_counter(self.rng_offset.data_ptr(), int(steps), _lib.current_stream(self.device)), "pulse_bump_counter")
 
+    def _reducer(self, world_size: int):
+        if world_size <= 1:
+            return None
+        if getattr(self, "_chain_reducer", None) is None:
+            from .dist_utils import ChainReducer
+            self._chain_reducer = ChainReducer(world_size, 3)
+        return self._chain_reducer
+
+    def reset_stats(self) -> None:
+        """The loss statistics ACCUMULATE over train_minibatch calls (sum over rows; one mini-epoch's mean KL = stats[3] / rows seen):
+        clear them where the reference starts a new list (amp_agent.py:496-505)."""
+        self.stats.zero_()
+
+    def sync_stats(self, world_size: int) -> None:
+        """`hvd.sync_stats` once per epoch (common_agent.py:126-127) [3P-memory: HorovodWrapper averages every running-statistics
+        tensor]: observation, value and AMP-input normalisers."""
+        if world_size <= 1:
+            return
+        from .dist_utils import sync_running_stats
+        for rms in (self.obs_rms, self.value_rms, self.disc.rms if self.disc is not None else None):
+            if rms is not None:
+                sync_running_stats(rms.running_mean, rms.running_var, rms.count, world_size)
+                rms._refresh()
+
     def critic_values(self, obs: torch.Tensor) -> torch.Tensor:
         """_eval_critic (common_agent.py:552-562)."""
         M = obs.shape[0]
@@ -209,7 +233,8 @@ class PPOPolicy:
                         world_size: int = 1, amp=None, keep_grads: bool = False) -> torch.Tensor:
         """One calc_gradients step (amp_agent.py:605-760, PPO branch without the discriminator term).
         `returns` are already value-normalised (prepare_dataset, common_agent.py:372-374).  Returns the fp64
-        stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp] (divide by M)."""
+        stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp], ACCUMULATED since reset_stats() (divide by the
+        rows seen)."""
         M = obs.shape[0]
         b = self._buf(M, True)
         # Three independent chains -- actor, critic, discriminator -- run on three streams (fork/join with events, so
@@ -219,12 +244,15 @@ class PPOPolicy:
         if self._side is None:
             self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         s_critic, s_disc = self._side
-        self.flat.begin_backward()                                # weight / bias gradients are accumulated with atomics
-        self.stats.zero_()
+        self.flat.begin_backward()                                # weight / bias gradients are accumulated by bulk reductions / atomics
+        reducer = self._reducer(world_size)                  # multi-GPU: every chain averages ITS gradient slice on its own stream
         if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
             s_disc.wait_stream(main)
             with torch.cuda.stream(s_disc):
                 self.disc.loss_backward(*amp)
+                if reducer is not None:
+                    d0, d1 = self.disc.mlp.param_span()
+                    reducer.reduce(self.flat.grads[d0:d1], 2)
         if update_obs_rms:                                   # normalise with the statistics BEFORE this batch, then merge it
             self.obs_rms.normalize_update(obs, b["x"])       # (running_mean_std.py:91-107, train mode), one pass over obs
         else:
@@ -255,35 +283,103 @@ class PPOPolicy:
             s_critic.wait_stream(main)
             with torch.cuda.stream(s_critic):
                 self.critic.backward(b["dv"], M)
+                if reducer is not None:
+                    c0, c1 = self.critic.param_span()
+                    reducer.reduce(self.flat.grads[c0:c1], 1)
             self.actor.backward(b["dmu"], M)
+            if reducer is not None:
+                a0, a1 = self.actor.param_span()
+                reducer.reduce(self.flat.grads[a0:a1], 0)
             main.wait_stream(s_critic)
+        if grouped and reducer is not None:                  # lock-step path: actor + critic slices are adjacent, one reduction
+            a0, _ = self.actor.param_span()
+            _, c1 = self.critic.param_span()
+            reducer.reduce(self.flat.grads[a0:c1], 0)
         if amp is not None:
             main.wait_stream(s_disc)
-        if world_size > 1:
-            from .dist_utils import average_gradients
-            average_gradients(self.flat.grads, world_size)  # one NCCL all-reduce (AVG) on the flat bucket (NVLink / NVLS)
         self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
         return self.stats
 
     # ------------------------------------------------------------------ checkpoint keys (rl_games layout)
+    def _rms_pairs(self):
+        """(checkpoint section, normaliser): A2CBase.get_stats_weights [rl_games] + AMPAgent.get_stats_weights (amp_agent.py:181-189)."""
+        out = [("running_mean_std", self.obs_rms)]
+        if self.value_rms is not None:
+            out.append(("reward_mean_std", self.value_rms))
+        if self.disc is not None:
+            out.append(("amp_input_mean_std", self.disc.rms))
+        return out
+
+    def _named_layers(self):
+        """(reference parameter prefix, Dense) in the order `ModelAMPContinuous.named_parameters()` yields them is NOT needed: every
+        consumer goes by name."""
+        out = []
+        nets = [(self.actor, "actor_mlp", "mu"), (self.critic, "critic_mlp", "value")]
+        if self.disc is not None:
+            nets.append((self.disc.mlp, "_disc_mlp", "_disc_logits"))
+        for mlp, prefix, head in nets:
+            for i, l in enumerate(mlp.layers[:-1]):
+                out.append((f"a2c_network.{prefix}.{2 * i}", l))
+            out.append((f"a2c_network.{head}", mlp.layers[-1]))
+        return out
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Model parameters under the reference's checkpoint keys (network_loader.py:81-99 reads them) + the three normalisers under
+        `<section>.running_mean|running_var|count`."""
         sd = {}
-        sd.update({f"a2c_network.{k}": v for k, v in self.actor.state_dict("actor_mlp", "mu").items()})
-        sd.update({f"a2c_network.{k}": v for k, v in self.critic.state_dict("critic_mlp", "value").items()})
+        for name, l in self._named_layers():
+            sd[name + ".weight"] = l.weight[:, :l.K].clone()
+            sd[name + ".bias"] = l.bias.clone()
         sd["a2c_network.sigma"] = self.logstd.clone()
-        sd["running_mean_std.running_mean"] = self.obs_rms.running_mean.clone()
-        sd["running_mean_std.running_var"] = self.obs_rms.running_var.clone()
-        sd["running_mean_std.count"] = self.obs_rms.count.clone()
+        for sec, rms in self._rms_pairs():
+            sd[f"{sec}.running_mean"], sd[f"{sec}.running_var"], sd[f"{sec}.count"] = rms.running_mean.clone(), rms.running_var.clone(), rms.count.clone()
         return sd
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
-        strip = {k[len("a2c_network."):]: v for k, v in sd.items() if k.startswith("a2c_network.")}
-        self.actor.load_state_dict(strip, "actor_mlp", "mu")
-        self.critic.load_state_dict(strip, "critic_mlp", "value")
-        if "sigma" in strip:
-            self.logstd.copy_(strip["sigma"].to(self.device))
-        if "running_mean_std.running_mean" in sd:
-            self.obs_rms.running_mean.copy_(sd["running_mean_std.running_mean"].to(self.device).double())
-            self.obs_rms.running_var.copy_(sd["running_mean_std.running_var"].to(self.device).double())
-            self.obs_rms.count.copy_(sd["running_mean_std.count"].to(self.device).double())
-            self.obs_rms._refresh()
+        for name, l in self._named_layers():
+            if name + ".weight" in sd:
+                l.set_weights(sd[name + ".weight"].to(self.device), sd[name + ".bias"].to(self.device))
+        if "a2c_network.sigma" in sd:
+            self.logstd.copy_(sd["a2c_network.sigma"].to(self.device))
+        for sec, rms in self._rms_pairs():
+            if f"{sec}.running_mean" in sd:
+                rms.running_mean.copy_(sd[f"{sec}.running_mean"].to(self.device).double().reshape(-1))
+                rms.running_var.copy_(sd[f"{sec}.running_var"].to(self.device).double().reshape(-1))
+                if f"{sec}.count" in sd:
+                    rms.count.copy_(torch.as_tensor(sd[f"{sec}.count"]).to(self.device).double().reshape(()))
+                rms._refresh()
+
+    def optimizer_state(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """torch.optim.Adam state per reference parameter name: {'exp_avg', 'exp_avg_sq'} in the parameter's shape, plus 'step'."""
+        out = {}
+        step = self.flat.step.clone().float().reshape(())
+        for name, l in self._named_layers():
+            m, v = self.flat.view(l.w_idx, "exp_avg"), self.flat.view(l.w_idx, "exp_avg_sq")
+            out[name + ".weight"] = {"exp_avg": m[:, :l.K].clone(), "exp_avg_sq": v[:, :l.K].clone(), "step": step.clone()}
+            if l.aug:
+                out[name + ".bias"] = {"exp_avg": m[:, l.K].clone(), "exp_avg_sq": v[:, l.K].clone(), "step": step.clone()}
+            else:
+                out[name + ".bias"] = {"exp_avg": self.flat.view(l.b_idx, "exp_avg").clone(), "exp_avg_sq": self.flat.view(l.b_idx, "exp_avg_sq").clone(),
+                                       "step": step.clone()}
+        return out
+
+    def load_optimizer_state(self, state: Dict[str, Dict[str, torch.Tensor]]) -> None:
+        step = None
+        for name, l in self._named_layers():
+            for kind in ("weight", "bias"):
+                st = state.get(f"{name}.{kind}")
+                if st is None or "exp_avg" not in st:
+                    continue
+                m, v = self.flat.view(l.w_idx, "exp_avg"), self.flat.view(l.w_idx, "exp_avg_sq")
+                if kind == "weight":
+                    m[:, :l.K].copy_(st["exp_avg"].to(self.device))
+                    v[:, :l.K].copy_(st["exp_avg_sq"].to(self.device))
+                elif l.aug:
+                    m[:, l.K].copy_(st["exp_avg"].to(self.device))
+                    v[:, l.K].copy_(st["exp_avg_sq"].to(self.device))
+                else:
+                    self.flat.view(l.b_idx, "exp_avg").copy_(st["exp_avg"].to(self.device))
+                    self.flat.view(l.b_idx, "exp_avg_sq").copy_(st["exp_avg_sq"].to(self.device))
+                step = st.get("step", step)
+        if step is not None:
+            self.flat.step.fill_(int(float(step)))

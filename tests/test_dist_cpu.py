@@ -59,3 +59,34 @@ def test_gradient_and_stats_averaging_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _chain_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pulse_b200.dist_utils import ChainReducer
+        red = ChainReducer(world, 3)
+        flat = torch.arange(30, dtype=torch.float32) * (rank + 1)          # three back-to-back "network" slices
+        spans = ((0, 8), (8, 20), (20, 30))
+        for chain in (2, 1, 0):                                            # any issue order, as the chains finish
+            a, b = spans[chain]
+            red.reduce(flat[a:b], chain)
+        ok = torch.allclose(flat, torch.arange(30, dtype=torch.float32) * (sum(range(1, world + 1)) / world))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chain_reducer_averages_every_slice_world2():
+    """Per-chain gradient averaging (one communicator per backward chain) == one all-reduce over the whole flat buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_chain_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,165 @@
+"""The drop-in layer EXECUTED: `HumanoidImB200Mixin` and `AMPAgentB200Mixin` mixed in front of stand-in base classes that carry the
+reference's attribute / method contract (tests/standins.py; checked against the reference sources by tests/test_boundary_cpu.py).
+
+  task  : Humanoid.post_physics_step -> _compute_reward -> _compute_reset -> _compute_observations -> AMP history + observation
+          (humanoid.py:1315-1346, humanoid_amp.py:194-210) against the oracle; the getup recovery masking (humanoid_im_getup.py:203-210)
+  agent : get_action_values / _eval_critic / _calc_amp_rewards / discount_values / prepare_dataset / calc_gradients through the mixin,
+          then a checkpoint ROUND TRIP through `self.model.state_dict()` / `optimizer.state_dict()` / the normaliser modules
+          (common_agent.py:142-150 saves exactly those)."""
+import copy
+
+import pytest
+import torch
+
+from tests.helpers import exact_step_inputs, exact_tables
+from tests.standins import StandInAMPAgent, StandInHumanoidIm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mlib(tb):
+    from pulse_b200.motion_lib import MotionLibB200
+    return MotionLibB200.from_tables({k: getattr(tb, k) for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa", "lengths", "num_frames", "dt",
+                                                                   "length_starts")}, device=DEV)
+
+
+@pytest.mark.parametrize("getup", [False, True])
+def test_task_mixin_post_physics_step_matches_oracle(getup):
+    from oracle import pulse_oracle as po
+    from pulse_b200.humanoid_im import HumanoidImB200Mixin
+
+    class HumanoidImB200(HumanoidImB200Mixin, StandInHumanoidIm):
+        pass
+
+    n = 389
+    tb = exact_tables(41, seed=8)
+    z, _ = exact_step_inputs(tb, n, seed=9)
+    task = HumanoidImB200(_mlib(tb), z, DEV, getup=getup)
+    rec = None
+    if getup:
+        g = torch.Generator().manual_seed(1)
+        rec = (torch.rand(n, generator=g) < 0.25).int() * 40
+        task._recovery_counter.copy_(rec.to(DEV))
+    amp0 = torch.randn(n, 10, 196, device=DEV)
+    task._amp_obs_buf.copy_(amp0)
+    task.post_physics_step()
+    torch.cuda.synchronize()
+    ref = po.humanoid_im_step(tb, po.ImStepConfig(), z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"], z["start_times"],
+                              z["start_offset"], z["global_offset"], z["cycle_counter"], z["reset_buf_in"], recovery_counter=rec)
+    assert torch.equal(task.reset_buf.cpu(), ref["reset_buf"]) and torch.equal(task._terminate_buf.cpu(), ref["terminate_buf"])
+    assert torch.equal(task.progress_buf.cpu(), ref["progress_buf"] if getup else z["progress_buf"])
+    torch.testing.assert_close(task.obs_buf.cpu(), ref["obs_buf"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.self_obs_buf.cpu(), ref["obs_buf"][:, :358], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.rew_buf.cpu(), ref["rew_buf"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.reward_raw.cpu(), ref["reward_raw"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.ref_body_pos.cpu(), ref["ref_body_pos"], atol=1e-5, rtol=0)
+    amp_ref = po.amp_obs_step(amp0.cpu(), z["body_state"], z["dof_pos"], z["dof_vel"])
+    torch.testing.assert_close(task._amp_obs_buf.cpu(), amp_ref, atol=1e-4, rtol=0)
+    assert task.extras["amp_obs"].shape == (n, 1960)
+    # reset-time observation of a subset through the same override (humanoid.py:574-587 -> _compute_observations(env_ids))
+    ids = torch.tensor([3, 77, 388], device=DEV)
+    before = task.obs_buf.clone()
+    task.obs_buf[ids] = -7.0
+    task._compute_observations(ids)
+    torch.cuda.synchronize()
+    if not getup:       # recovering envs take their observation one step earlier in the fused call; the subset call re-queries at progress + 1
+        torch.testing.assert_close(task.obs_buf, before, atol=1e-6, rtol=0)
+
+
+def _agent(seed=0, **kw):
+    from pulse_b200.agent_mixins import AMPAgentB200Mixin
+
+    class IMAmpAgentB200(AMPAgentB200Mixin, StandInAMPAgent):
+        pass
+
+    return IMAmpAgentB200(task=None, device=DEV, seed=seed, **kw)
+
+
+def _minibatch(agent, M=2048, seed=5):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    obs = torch.randn(M, 934, device=DEV, generator=g)
+    res = agent.get_action_values({"obs": obs})
+    n = agent._amp_minibatch_size
+    amp = [torch.randn(n, 1960, device=DEV, generator=g) for _ in range(3)]
+    return {"obs": obs, "actions": res["actions"].clone(), "old_logp_actions": res["neglogpacs"].clone(), "mu": res["mus"].clone(),
+            "advantages": torch.randn(M, device=DEV, generator=g), "returns": torch.randn(M, device=DEV, generator=g),
+            "amp_obs": amp[0], "amp_obs_replay": amp[1], "amp_obs_demo": amp[2]}, res
+
+
+def test_agent_mixin_methods_and_checkpoint_round_trip():
+    agent = _agent(seed=1)
+    agent._amp_minibatch_size = 512
+    init = copy.deepcopy(agent.model.state_dict())
+    batch, res = _minibatch(agent)
+    M = batch["obs"].shape[0]
+    assert res["actions"].shape == (M, 69) and res["values"].shape == (M, 1) and res["neglogpacs"].shape == (M,) and res["rnn_states"] is None
+    v = agent._eval_critic({"obs": batch["obs"]})
+    torch.testing.assert_close(v, res["values"], atol=1e-5, rtol=1e-5)           # same critic, same (identity) value statistics
+    r = agent._calc_amp_rewards(batch["amp_obs"].view(16, 32, 1960))
+    assert r["disc_rewards"].shape == (16, 32, 1) and bool((r["disc_rewards"] >= 0).all())
+    T, N = 8, 64
+    adv = agent.discount_values(torch.zeros(T, N, device=DEV), torch.randn(T, N, 1, device=DEV), torch.randn(T, N, 1, device=DEV), torch.randn(T, N, 1, device=DEV))
+    assert adv.shape == (T, N, 1)
+    # prepare_dataset keeps value_mean_std the owner and mirrors it into the device library
+    agent.prepare_dataset({"values": torch.randn(4096, 1, device=DEV) * 3 + 1, "returns": torch.randn(4096, 1, device=DEV) * 3 + 1})
+    pol = agent._pulse_policy()
+    torch.testing.assert_close(pol.value_rms.running_mean, agent.value_mean_std.running_mean.reshape(-1))
+    torch.testing.assert_close(pol.value_rms.running_var, agent.value_mean_std.running_var.reshape(-1))
+    assert float(pol.value_rms.count) == float(agent.value_mean_std.count) == 1 + 2 * 4096
+    # two training steps through calc_gradients
+    for _ in range(2):
+        agent.calc_gradients(batch)
+    tr = agent.train_result
+    for k in ("actor_loss", "critic_loss", "b_loss", "kl", "actor_clip_frac", "disc_loss", "disc_agent_acc", "disc_demo_acc", "disc_agent_logit",
+              "disc_demo_logit", "disc_grad_penalty", "disc_logit_loss"):
+        assert k in tr and torch.isfinite(torch.as_tensor(tr[k]).float()).all(), k
+    # ---- save: what rl_games serialises must be the TRAINED state ---------------------------------------------------------------
+    w = copy.deepcopy(agent.get_full_state_weights())
+    sd = w["model"]
+    assert not torch.equal(sd["a2c_network.actor_mlp.0.weight"], init["a2c_network.actor_mlp.0.weight"])       # trained, not the initial weights
+    assert not torch.equal(sd["a2c_network._disc_mlp.2.bias"], init["a2c_network._disc_mlp.2.bias"])
+    torch.testing.assert_close(sd["a2c_network.mu.weight"], pol.actor.layers[-1].weight[:, :512], atol=0, rtol=0)
+    assert float(w["running_mean_std"]["count"]) == 1 + 2 * M and float(w["amp_input_mean_std"]["count"]) == 1 + 2 * 3 * 512
+    st = w["optimizer"]["state"]
+    assert len(st) > 0 and all(float(s["step"]) == 2 for s in st.values()) and any(float(s["exp_avg"].abs().max()) > 0 for s in st.values())
+    # ---- restore into a fresh agent and continue: identical to continuing in the original ------------------------------------------
+    other = _agent(seed=99)
+    other._amp_minibatch_size = 512
+    other.get_action_values({"obs": batch["obs"]})            # builds its device copy from DIFFERENT weights first
+    other.set_full_state_weights(w)
+    pol2 = other._pulse_policy()
+    assert pol2 is not pol
+    torch.testing.assert_close(pol2.flat.params, pol.flat.params, atol=0, rtol=0)
+    torch.testing.assert_close(pol2.flat.exp_avg, pol.flat.exp_avg, atol=0, rtol=0)
+    torch.testing.assert_close(pol2.flat.exp_avg_sq, pol.flat.exp_avg_sq, atol=0, rtol=0)
+    assert int(pol2.flat.step) == 2
+    torch.testing.assert_close(pol2.obs_rms.running_var, pol.obs_rms.running_var, atol=0, rtol=0)
+    torch.testing.assert_close(pol2.disc.rms.running_mean, pol.disc.rms.running_mean, atol=0, rtol=0)
+    torch.testing.assert_close(pol2.value_rms.running_mean, pol.value_rms.running_mean, atol=0, rtol=0)
+    agent.calc_gradients(batch)
+    other.calc_gradients(batch)
+    torch.cuda.synchronize()
+    # same arithmetic from the same state; the weight-gradient reductions add in a different order run to run (fp32, ~1e-7 relative)
+    torch.testing.assert_close(pol2.flat.params, pol.flat.params, atol=1e-6, rtol=1e-5)
+    assert float((pol2.flat.params - pol.flat.params).abs().max()) < 1e-4
+
+
+def test_agent_mixin_reads_network_shape_from_the_model():
+    """pulse_z_task.yaml-style policy (2048-1024-512 SiLU): units / activation come from the model, not from defaults."""
+    import tests.standins as si
+    agent = _agent(seed=3, obs=361, actions=32, units=(2048, 1024, 512), amp=1960, disc_units=(1024, 512))
+    agent.model.a2c_network.actor_mlp = si.mlp((361, 2048, 1024, 512), torch.nn.SiLU).to(DEV)
+    agent.model.a2c_network.critic_mlp = si.mlp((361, 2048, 1024, 512), torch.nn.SiLU).to(DEV)
+    pol = agent._pulse_policy()
+    assert [l.N for l in pol.actor.layers] == [2048, 1024, 512, 32] and pol.actor.act == "silu" and pol.obs_size == 361
+    res = agent.get_action_values({"obs": torch.randn(256, 361, device=DEV)})
+    x = torch.clamp(torch.randn(1), -5, 5)  # noqa: F841
+    ref_mu = agent.model.a2c_network.mu(agent.model.a2c_network.actor_mlp(torch.clamp(_last_obs(agent, res), -5, 5)))
+    torch.testing.assert_close(res["mus"], ref_mu, atol=3e-2, rtol=3e-2)
+
+
+def _last_obs(agent, res):
+    """the observation batch of the last get_action_values call, normalised with the (identity) statistics"""
+    pol = agent._pulse_policy()
+    return pol._buf(res["mus"].shape[0], False)["x"][:, :pol.obs_size].float()
