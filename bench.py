@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS)
     ap.add_argument("--median-frames", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "vae", "reach"],
+                    help="ppo = the headline (BASELINE configs[3], the default the driver runs); vae = configs[2] PULSE VAE distillation, "
+                         "8192 envs; reach = configs[4] latent reach task (1024 envs per GPU): single-GPU records of the secondary workloads")
     return ap.parse_args()
 
 
@@ -264,8 +267,126 @@ def mlp_flops_per_env_step():
     return 2.0 * (rollout + update)
 
 
+SECONDARY = {
+    "vae": ("env-steps/sec, PULSE VAE distillation (encoder + prior + decoder MLP), 8192 humanoid envs, 1 B200 (BASELINE configs[2])", 8192),
+    "reach": ("env-steps/sec, latent-space reach task with the frozen PULSE decoder, 1024 envs per B200 (BASELINE configs[4]: 8192 envs on 8 GPUs)", 1024),
+}
+
+
+def cpu_secondary_rate(workload, threads):
+    """CPU port (oracle) of one minibatch update + one env step of a secondary workload on a bounded sample, extrapolated to an iteration."""
+    import torch
+    from oracle import pulse_oracle as po
+    from tests.helpers import VAE_FULL, synthetic_step_inputs, synthetic_tables, vae_full_fixture, vae_param_list
+    torch.set_num_threads(threads)
+    n = 512
+    tb = synthetic_tables(n, seed=0)
+    z = synthetic_step_inputs(tb, n, seed=1)
+    cfg = po.ImStepConfig()
+    t0 = time.perf_counter()
+    po.humanoid_im_step(tb, cfg, z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"], z["start_times"], z["start_offset"],
+                        z["global_offset"], z["cycle_counter"], z["reset_buf_in"])
+    t_step = (time.perf_counter() - t0) / n                         # seconds per env-step of the obs / reward / reset path
+    if workload == "vae":
+        sd, batch, _ = vae_full_fixture()
+        nets = po.VaeNets.from_state_dict(sd, VAE_FULL["S"])
+        params = [p.requires_grad_(True) for p in vae_param_list(nets).values()]
+        opt = torch.optim.Adam(params, lr=5e-4)
+        rows = batch["obs"].shape[0]
+
+        def upd():
+            opt.zero_grad(set_to_none=True)
+            r = po.vae_kin_loss(nets, batch["obs"], batch["noise"], batch["gt_action"], batch["progress"], VAE_FULL["T"])
+            r["kin_loss"].backward()
+            torch.nn.utils.clip_grad_norm_(params, 50.0)
+            opt.step()
+        upd()
+        t0 = time.perf_counter()
+        upd()
+        t_upd = (time.perf_counter() - t0) / rows                    # seconds per row of one _optimize_kin minibatch
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            po.vae_eval_actor(nets, batch["obs"], batch["noise"])
+            t_fwd = (time.perf_counter() - t0) / rows
+        per_env_step = t_step + 2 * t_fwd + MINI_EPOCHS * t_upd      # rollout: student forward + teacher of comparable size
+        return 1.0 / per_env_step, f"{rows}-row _optimize_kin minibatch (im_z_fit.yaml nets, fwd + autograd bwd + Adam) + encoder/decoder forward + {n}-env step path"
+    lin = lambda i, o: torch.nn.Linear(i, o)
+    mk = lambda i, o: torch.nn.Sequential(lin(i, 2048), torch.nn.SiLU(), lin(2048, 1024), torch.nn.SiLU(), lin(1024, 512), torch.nn.SiLU(), lin(512, o))
+    actor, critic = mk(361, 32), mk(361, 1)
+    params = list(actor.parameters()) + list(critic.parameters())
+    opt = torch.optim.Adam(params, lr=2e-5)
+    rows = 2048
+    obs, act = torch.randn(rows, 361), torch.randn(rows, 32)
+    logstd = torch.full((32,), -2.9)
+    adv, ret, nlp = torch.randn(rows), torch.randn(rows), torch.randn(rows) + 20
+
+    def upd():
+        opt.zero_grad(set_to_none=True)
+        out = po.ppo_total_loss(actor(obs), critic(obs).squeeze(1), nlp, adv, ret, act, logstd)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 50.0)
+        opt.step()
+    upd()
+    t0 = time.perf_counter()
+    upd()
+    t_upd = (time.perf_counter() - t0) / rows
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        actor(obs); critic(obs); critic(obs)
+        t_fwd = (time.perf_counter() - t0) / rows
+    per_env_step = 0.4 * t_step + 3 * t_fwd + MINI_EPOCHS * t_upd   # reach obs is the 358-float self observation part of the step path
+    return 1.0 / per_env_step, f"{rows}-row PPO minibatch of the pulse_z_task.yaml policy (fwd + autograd bwd + Adam) + policy/critic/decoder-sized forwards + step path"
+
+
+def run_secondary(a):
+    import torch
+    metric, envs = SECONDARY[a.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                                        # single-GPU records: the other ranks of a torchrun launch exit without work
+    if a.impl == "reference":
+        threads = min(os.cpu_count() or 1, 32)
+        vals = []
+        for i in range(a.warmup + a.steps):
+            rate, sample = cpu_secondary_rate(a.workload, threads)
+            if i >= a.warmup:
+                vals.append(rate)
+        value = sum(vals) / len(vals)
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": "env-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * HORIZON * envs / value, "extrapolated": True, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": metric, "envs": envs},
+                "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    from tools import bench_pulse
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ns = argparse.Namespace(envs=envs if a.envs == TOTAL_ENVS else a.envs, steps=a.steps, warmup=a.warmup)
+    sampler = ClockSampler(0)
+    sampler.start()
+    out = bench_pulse.bench_vae(ns, dev) if a.workload == "vae" else bench_pulse.bench_reach(ns, dev)
+    clocks = sampler.stop()
+    line = {"metric": metric, "value": out["value"], "unit": "env-steps/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": out["ms_per_iteration"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 GEMM operands, fp32 accumulate / master weights / observations", "data": "synthetic",
+            "config": {"workload": out["workload"], "envs": ns.envs, "horizon": HORIZON, "minibatch": MINIBATCH, "mini_epochs": MINI_EPOCHS,
+                       "phases": out["phases"], "not_yet": out.get("not_run", []) + ["physics (excluded on every arm)"], "l2": out["l2"]},
+            "e2e": out["e2e"], "gpu_launches": out["gpu_launches"], "cuda_graphs": out["cuda_graphs"], "clocks": clocks,
+            "roofline": dict(out["roofline_update"], kernel="gemm_bf16_kernel family (update phase)", traffic=None),
+            "phases_ms": {"rollout": out["rollout_ms"], "update": out["update_ms"]}, "mlp_mflop_per_env_step": out["mflop_per_env_step"]}
+    if not a.no_cpu_baseline:
+        threads = min(os.cpu_count() or 1, 32)
+        rate, sample = cpu_secondary_rate(a.workload, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "extrapolated": True,
+                                "sample": sample}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
+    if a.workload != "ppo":
+        return run_secondary(a)
     if a.impl == "reference":
         return run_reference(a)
     import torch

@@ -98,10 +98,22 @@ __global__ void __launch_bounds__(128) amp_row_kernel(const pulse_amp_row_args_t
   const bool fresh = a.fresh != nullptr && a.fresh[e] != 0;
   const float* prev = fresh ? a.fresh_rows + e * (long long)a.num_steps * kAmp : a.prev + e * a.ld_prev;
   {
+    // (steps-1)*49 16-byte units per env (441 for 10 steps): all loads of the warp are issued before the first store (16 in flight per lane)
     const float4* src = reinterpret_cast<const float4*>(prev);
     float4* dst = reinterpret_cast<float4*>(out + kAmp);
     const int nvec = hist / 4;
-    for (int c = lane; c < nvec; c += 32) dst[c] = src[c];
+    float4 regs[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) regs[i] = __ldcs(src + c);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) __stcs(dst + c, regs[i]);
+    }
+    for (int c = lane + 512; c < nvec; c += 32) dst[c] = src[c];   // more than 11 history steps
   }
   if (fresh && lane == 0) a.fresh[e] = 0;
   // ---- current observation (same arithmetic as amp_obs_kernel) ---------------------------------------------------------------

@@ -14,6 +14,7 @@ communicator once per minibatch on the flat gradient buffer, replacing Horovod's
 """
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -246,6 +247,9 @@ class PPOPolicy:
         s_critic, s_disc = self._side
         self.flat.begin_backward()                                # weight / bias gradients are accumulated by bulk reductions / atomics
         reducer = self._reducer(world_size)                  # multi-GPU: every chain averages ITS gradient slice on its own stream
+        single = reducer is not None and os.environ.get("PULSE_GRAD_REDUCE", "chain") == "single"   # A/B: one all-reduce after the join
+        if single:
+            reducer = None
         if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
             s_disc.wait_stream(main)
             with torch.cuda.stream(s_disc):
@@ -297,6 +301,9 @@ class PPOPolicy:
             reducer.reduce(self.flat.grads[a0:c1], 0)
         if amp is not None:
             main.wait_stream(s_disc)
+        if single:
+            from .dist_utils import average_gradients
+            average_gradients(self.flat.grads, world_size)
         self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
         return self.stats
 

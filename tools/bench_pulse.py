@@ -32,6 +32,7 @@ def timed_iterations(iteration, steps, warmup, dev):
     for _ in range(warmup):
         flush.fill_(1)
         iteration(False)
+        iteration(False)
     torch.cuda.synchronize()
     total = 0.0
     for _ in range(steps):
@@ -55,8 +56,10 @@ class Graphs:
         if not self.enabled:
             return fn(*args)
         g = self.g.get(key)
-        if g is None:
-            fn(*args)
+        if g is None:                # first use: eager; second use: capture (records only) + replay -- nothing executes twice
+            self.g[key] = False
+            return fn(*args)
+        if g is False:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool):
@@ -100,7 +103,14 @@ def bench_vae(a, dev):
     graphs = Graphs(os.environ.get("PULSE_NO_GRAPHS", "0") != "1")
     ev = []
 
+    host = {k: z[k].cpu().pin_memory() for k in ("body_state", "dof_state", "dof_force")}
+    h_rew = torch.empty(n).pin_memory()
+    io = {"on": False, "h2d": sum(v.numel() * 4 for v in host.values()), "d2h": n * 4}
+
     def rollout_step(t):
+        if io["on"]:
+            for k, v in host.items():
+                z[k].copy_(v, non_blocking=True)
         res = vae.act(obses[:, t])                                            # encoder + decoder + critic_z + critic (K17)
         values[t].copy_(res["values"])
         gt_actions[:, t].copy_(teacher.gt_action(obses[:, t]))                # frozen PNN + composer (K19), HumanoidImDistill.step
@@ -110,6 +120,8 @@ def bench_vae(a, dev):
         nxt = obses[:, t + 1] if t + 1 < T else obs_carry
         comp.step(obs_buf=nxt, rew_buf=rewards[t], **step_kw)                 # K1-K5
         comp.amp_obs(body_state=z["body_state"], dof_pos=z["dof_pos"], dof_vel=z["dof_vel"], amp_obs_buf=amp_buf)   # K6
+        if io["on"]:
+            h_rew.copy_(rewards[t], non_blocking=True)
 
     def update_mb(i):
         r0, r1 = i * MINIBATCH, (i + 1) * MINIBATCH
@@ -119,7 +131,7 @@ def bench_vae(a, dev):
         z["progress_buf"].copy_(progress0)
         obses[:, 0].copy_(obs_carry)
         for t in range(T):
-            graphs.run(("roll", t), rollout_step, t)
+            graphs.run(("roll", t, io["on"]), rollout_step, t)
         if record:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -138,6 +150,9 @@ def bench_vae(a, dev):
     graphs.enabled = en
     ms = timed_iterations(iteration, a.steps, a.warmup, dev)
     u_ms = sum(s.elapsed_time(e) for s, e in ev) / len(ev)
+    io["on"] = True
+    ms_e2e = timed_iterations(iteration, max(2, a.steps // 2), 1, dev)
+    io["on"] = False
     enc = macs([960, 1536, 1024, 512, 160, 64])
     pri = macs([384, 1536, 1024, 512, 64])
     dec = macs([448, 3096, 2048, 1024, 69])
@@ -154,6 +169,8 @@ def bench_vae(a, dev):
     return {
         "workload": "PULSE VAE distillation (BASELINE configs[2]): %d envs, horizon 32, im_z_fit.yaml nets, minibatch 16384, 6 mini-epochs" % n,
         "value": T * n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_iteration": ms, "update_ms": u_ms, "rollout_ms": ms - u_ms,
+        "e2e": {"value": T * n / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * io["h2d"], "d2h_bytes_per_step": T * io["d2h"],
+                "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "cuda_graphs": graphs.enabled,
         "mflop_per_env_step": 2e-6 * (roll + MINI_EPOCHS * upd),
         "roofline_update": {"bound": "tensor", "achieved": upd_flops / (u_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
@@ -201,7 +218,14 @@ def bench_reach(a, dev):
     graphs = Graphs(os.environ.get("PULSE_NO_GRAPHS", "0") != "1")
     ev = []
 
+    host = {"body": body.cpu().pin_memory(), "contact": contact.cpu().pin_memory()}
+    h_rew = torch.empty(n).pin_memory()
+    io = {"on": False, "h2d": sum(v.numel() * 4 for v in host.values()), "d2h": n * 4}
+
     def rollout_step(t):
+        if io["on"]:
+            body.copy_(host["body"], non_blocking=True)
+            contact.copy_(host["contact"], non_blocking=True)
         obses[:, t].copy_(task.obs_buf)
         res = policy.act(obses[:, t])                                          # latent policy (K20 caller)
         actions[:, t].copy_(res["actions"]); mus[:, t].copy_(res["mus"]); neglogp[:, t].copy_(res["neglogpacs"]); values[t].copy_(res["values"])
@@ -213,13 +237,15 @@ def bench_reach(a, dev):
         rewards[t].copy_(task.rew_buf); dones[t].copy_(task.reset_buf)
         nv = policy.critic_values(task.obs_buf)
         next_values[t].copy_(nv * (1.0 - task._terminate_buf.unsqueeze(1).float()))
+        if io["on"]:
+            h_rew.copy_(rewards[t], non_blocking=True)
 
     def post_rollout():
         adv, ret = discount_values(dones, values, rewards.unsqueeze(-1), next_values, normalize_advantage=True)
-        policy.value_rms.update(values.view(T, n).t().reshape(T * n, 1))
-        policy.value_rms.update(ret.view(-1, 1))
+        policy.value_rms.update(values.view(T * n, 1))
         adv_buf.copy_(adv)
-        ret_buf.copy_(policy.value_rms.normalize_values(ret.view(-1, 1)).view(-1))
+        ret_buf.copy_(policy.value_rms.normalize_values(ret.view(-1, 1)).view(-1))   # statistics include the values batch, not yet the returns
+        policy.value_rms.update(ret.view(-1, 1))
 
     def update_mb(i):
         r0, r1 = i * mb_rows, (i + 1) * mb_rows
@@ -228,7 +254,7 @@ def bench_reach(a, dev):
     def iteration(record):
         progress.copy_(progress0)
         for t in range(T):
-            graphs.run(("roll", t), rollout_step, t)
+            graphs.run(("roll", t, io["on"]), rollout_step, t)
         graphs.run(("post",), post_rollout)
         if record:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -248,6 +274,9 @@ def bench_reach(a, dev):
     graphs.enabled = en
     ms = timed_iterations(iteration, a.steps, a.warmup, dev)
     u_ms = sum(s.elapsed_time(e) for s, e in ev) / len(ev)
+    io["on"] = True
+    ms_e2e = timed_iterations(iteration, max(2, a.steps // 2), 1, dev)
+    io["on"] = False
     pol = macs([384, 2048, 1024, 512, 32])
     crit = macs([384, 2048, 1024, 512, 1])
     zdec = macs([384, 1536, 1024, 512, 64]) + macs([448, 3096, 2048, 1024, 69])
@@ -258,6 +287,8 @@ def bench_reach(a, dev):
     return {
         "workload": "latent-space reach task (BASELINE configs[4]): %d envs on this GPU, frozen PULSE prior + decoder, pulse_z_task.yaml policy" % n,
         "value": T * n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_iteration": ms, "update_ms": u_ms, "rollout_ms": ms - u_ms,
+        "e2e": {"value": T * n / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * io["h2d"], "d2h_bytes_per_step": T * io["d2h"],
+                "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "cuda_graphs": graphs.enabled, "mflop_per_env_step": 2e-6 * (pol + 2 * crit + zdec + MINI_EPOCHS * upd),
         "roofline_update": {"bound": "tensor", "achieved": upd_flops / (u_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                             "frac": upd_flops / (u_ms * 1e-3) / 1e12 / peak_tf},
