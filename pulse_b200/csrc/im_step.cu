@@ -72,13 +72,19 @@ struct PlanEntry {           // planner -> issuer
   int nslots;
 };
 
-// Per env: [slot0 | slot1 | slot2 | body]; the obs row is staged over the same bytes once they are consumed.
-constexpr int kEnvBlock = (kSlots + 1) * kFrame;
+// Per env: three frame-record slots (936 floats) and, in a SEPARATE array, the rigid-body state (312 floats); the obs row is staged over
+// the frame slots once they are consumed.  Round 1 kept [slot0 | slot1 | slot2 | body] in one 1248-float block: 1248 = 0 (mod 32 banks), so
+// the 8 lanes of a warp that belong to the next env hit the banks of the first env's lanes on EVERY record read (ncu: 1.93 M conflicts,
+// 46 % of the stall cycles on shared-memory scoreboards).  With lane = (env k, body j) a stride-3 read of a frame record is conflict-free
+// across the env boundary iff the env stride is 8 (mod 32) -- 936 is; the stride-13 body-state read needs 24 (mod 32) -- 312 is.
+constexpr int kFrameBlock = kSlots * kFrame;   // 936
 struct __align__(16) Stage {
-  float env[kEnvs][kEnvBlock];
+  float fr[kEnvs][kFrameBlock];
+  float body[kEnvs][kFrame];
   EnvParams prm[kEnvs];
 };
-static_assert((kObs + 3) <= kEnvBlock, "obs staging must fit inside the env block");
+static_assert((kObs + 2) <= kFrameBlock, "obs staging (alignment phase <= 2) must fit inside the frame slots");
+static_assert(kFrameBlock % 32 == 8 && kFrame % 32 == 24, "bank-conflict-free env strides");
 
 struct __align__(16) CtaSmem {
   Stage stage[kStages];
@@ -279,11 +285,11 @@ __device__ __forceinline__ void issue_group(const pulse_motionlib_desc_t& lib, c
   __syncwarp();                                    // the expectation is posted before any copy can complete
   if (v) {
     const PlanEntry& E = plan[lane];
-    float* blk = sg.env[lane];
+    float* blk = sg.fr[lane];
 #pragma unroll
     for (int m = 0; m < kSlots; ++m)
       if (m < ns) bulk_g2s(blk + m * kFrame, lib.frame_rec + E.slot_row[m] * kFrame, kFrameBytes, full);
-    if (body_bulk) bulk_g2s(blk + kSlots * kFrame, E.body_src, kFrameBytes, full);
+    if (body_bulk) bulk_g2s(sg.body[lane], E.body_src, kFrameBytes, full);
   }
 }
 
@@ -395,9 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
 
     const EnvParams P = sg.prm[k];
     const bool valid = P.valid != 0;
-    float* blk = sg.env[k];
+    float* blk = sg.fr[k];
     // rigid-body state: shared memory when it came through the bulk path, else straight from global
-    const float* body = (P.body_bulk || !valid) ? blk + kSlots * kFrame : a.body_state + P.env * a.body_env_stride;
+    const float* body = (P.body_bulk || !valid) ? sg.body[k] : a.body_state + P.env * a.body_env_stride;
     const float* bj = body + j * PULSE_BODY_STATE_W;
     const Vec3 p = {bj[0], bj[1], bj[2]};
     const Quat q = {bj[3], bj[4], bj[5], bj[6]};
@@ -452,7 +458,9 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
       const Yaw yr = make_yaw(Quat{0.0f, 0.0f, -hs, hc});
       orow = a.obs_buf + P.env * a.obs_stride;
       ophase = static_cast<int>((reinterpret_cast<uintptr_t>(orow) >> 2) & 3);
-      float* o = blk + ophase;  // global 16-byte boundaries coincide with shared ones
+      // global 16-byte boundaries coincide with shared ones; a row starting 3 floats past a boundary would need 937 staging floats:
+      // it is written straight to global memory instead (never the case for [N, 934]-strided buffers: 934 k = 0 or 2 mod 4)
+      float* o = ophase == 3 ? orow : blk + ophase;
       // self observation (humanoid.py:1675-1731)
       if (j == 0) o[0] = p_root.z;
       else st3(o + 1 + 3 * (j - 1), yaw_rot(yr, p - p_root));
@@ -497,15 +505,17 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
     if (valid && do_obs) {
       const int head = (4 - ophase) & 3;         // floats before the first 16-byte boundary
       const int nmid = ((kObs - head) / 4) * 4;  // floats in the aligned middle
-      const float* o = blk + ophase;
-      if (j == 0) {
-        bulk_s2g(orow + head, o + head, static_cast<unsigned>(nmid) * 4u);
-        bulk_commit();
-      } else if (j <= 3) {
-        if (j - 1 < head) orow[j - 1] = o[j - 1];
-      } else if (j <= 6) {
-        const int i = head + nmid + (j - 4);
-        if (i < kObs) orow[i] = o[i];
+      const float* o = ophase == 3 ? orow : blk + ophase;
+      if (ophase != 3) {
+        if (j == 0) {
+          bulk_s2g(orow + head, o + head, static_cast<unsigned>(nmid) * 4u);
+          bulk_commit();
+        } else if (j <= 3) {
+          if (j - 1 < head) orow[j - 1] = o[j - 1];
+        } else if (j <= 6) {
+          const int i = head + nmid + (j - 4);
+          if (i < kObs) orow[i] = o[i];
+        }
       }
       if (a.self_obs_buf != nullptr) {
         float* srow = a.self_obs_buf + P.env * PULSE_SELF_OBS;
@@ -565,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) im_step_kernel(const pulse_motion
       }
       if (a.pass_time != nullptr) a.pass_time[ee] = (Q.t_rew >= Q.mlen) ? 1 : 0;
     }
-    if (valid && do_obs && j == 0) bulk_wait_read();  // the stage's bytes are free once the store has read them
+    if (valid && do_obs && j == 0 && ophase != 3) bulk_wait_read();  // the stage's bytes are free once the store has read them
     // No third team barrier: each thread releases the stage when IT is done with it.  red[] columns 0..23,
     // fallen[] and root[] are next written only after this thread passed the second team_sync above, and the
     // column sums / flags are next overwritten only after the next group's first team_sync.

@@ -247,7 +247,11 @@ class PPOPolicy:
         s_critic, s_disc = self._side
         self.flat.begin_backward()                                # weight / bias gradients are accumulated by bulk reductions / atomics
         reducer = self._reducer(world_size)                  # multi-GPU: every chain averages ITS gradient slice on its own stream
-        single = reducer is not None and os.environ.get("PULSE_GRAD_REDUCE", "chain") == "single"   # A/B: one all-reduce after the join
+        # Measured at 2 GPUs (profiles/r02_grad_reduce_ab.txt): reducing every chain's slice on its own stream ("chain") is SLOWER than one
+        # all-reduce after the join (72.2 vs 69.8 ms update phase): the persistent GEMMs own all 148 SMs and walk a static tile schedule,
+        # so NCCL's CTAs either wait for a GEMM to drain or delay the CTAs of the next one -- the collective is not hidden, it is
+        # interleaved.  Default: one all-reduce; PULSE_GRAD_REDUCE=chain keeps the per-chain variant for experiments.
+        single = reducer is not None and os.environ.get("PULSE_GRAD_REDUCE", "single") != "chain"
         if single:
             reducer = None
         if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
