@@ -378,6 +378,9 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const pulse_
     int dev = 0;
     PULSE_CUDA_OK(cudaGetDevice(&dev));
     PULSE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // PULSE_GEMM_SMS=n: leave SMs free for a concurrent collective (the persistent grid otherwise owns the whole GPU)
+    const char* e = getenv("PULSE_GEMM_SMS");
+    if (e != nullptr && atoi(e) >= 2 && atoi(e) < num_sms) num_sms = atoi(e) & ~1;
   }
   // persistent: one CTA (or CTA pair) per SM (pair of SMs) loops over the work items
   const long long total = static_cast<long long>((n + BN - 1) / BN) * ((m + BM * CTAS - 1) / (BM * CTAS)) * splits;
