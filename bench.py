@@ -499,10 +499,25 @@ def main():
         ps.finish()            # disc rewards, reward mix, GAE, advantage + value / return normalisation (rollout.py)
         done_frac.add_(ps.dones.mean())
 
-    def update_mb(i):
+    def mb_inputs(i):
+        r0 = i * MINIBATCH
+        return obs_f[r0:r0 + MINIBATCH], (amp_f[r0:r0 + AMP_MB], replay_mb[i], demo_mb[i])   # amp_obs[0:amp_minibatch_size] (amp_agent.py:621-628)
+
+    # The weight-independent head of a minibatch (observation / AMP normalisation with their running-statistics updates) is prepared
+    # one minibatch ahead on a side stream, in the reference's order, into the other operand slot (PULSE_PREFETCH=0: inline).
+    prefetching = os.environ.get("PULSE_PREFETCH", "1") != "0" and num_mb % 2 == 0
+
+    def prepare_first():
+        policy.prepare_inputs(*mb_inputs(0), slot=0)
+
+    def update_mb(i, last=False):
         r0, r1 = i * MINIBATCH, (i + 1) * MINIBATCH
-        policy.train_minibatch(obs_f[r0:r1], act_f[r0:r1], nlp_f[r0:r1], ps.adv[r0:r1], ps.ret[r0:r1], old_mu=mu_f[r0:r1], world_size=world,
-                               amp=(amp_f[r0:r0 + AMP_MB], replay_mb[i], demo_mb[i]))   # amp_obs[0:amp_minibatch_size] (amp_agent.py:621-628)
+        obs_i, amp_i = mb_inputs(i)
+        kw = {}
+        if prefetching:
+            kw = dict(slot=i & 1, prepared=True, prefetch=None if last else mb_inputs((i + 1) % num_mb))
+        policy.train_minibatch(obs_i, act_f[r0:r1], nlp_f[r0:r1], ps.adv[r0:r1], ps.ret[r0:r1], old_mu=mu_f[r0:r1], world_size=world,
+                               amp=amp_i, **kw)
 
     # ---- CUDA graphs: every launch sequence with fixed buffers is captured once and replayed -----------------
     graphs = {}
@@ -539,10 +554,13 @@ def main():
         if record:
             us.record()
             phase_events.append((r0, r1, us))
-        for _ in range(MINI_EPOCHS):
+        if prefetching:
+            run(("prepare_first",), prepare_first)
+        for ep in range(MINI_EPOCHS):
             policy.reset_stats()                           # loss / KL statistics accumulate over the mini-epoch's minibatches
             for i in range(num_mb):
-                run(("upd", i), update_mb, i)
+                last = prefetching and ep == MINI_EPOCHS - 1 and i == num_mb - 1      # nothing left to prepare
+                run(("upd", i, last), update_mb, i, last)
             if world > 1:                                  # av_kls = hvd.average_value(av_kls) per mini-epoch (amp_agent.py:523-524)
                 dist.all_reduce(policy.stats, op=dist.ReduceOp.AVG)
         if world > 1:                                      # hvd.sync_stats once per epoch (common_agent.py:126-127)
@@ -640,6 +658,7 @@ def main():
             "resets_per_env_step": resets_per_step,
             "gemm_switches": {"cta_pairs": os.environ.get("PULSE_GEMM_PAIR", "1") != "0", "pdl": os.environ.get("PULSE_GEMM_PDL", "1") != "0",
                               "grouped_launches": os.environ.get("PULSE_GROUPED", "0") == "1"},
+            "update_input_prefetch": bool(prefetching),
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/im_step_traffic.json)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,

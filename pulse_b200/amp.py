@@ -56,7 +56,8 @@ class AmpDiscriminator:
             dev, bf = self.device, torch.bfloat16
             L1, L2, _ = self.mlp.layers
             self._bufs[B] = {
-                "x": torch.zeros(3 * B, self.Kp, device=dev, dtype=bf), "dlogit": torch.zeros(3 * B, 8, device=dev, dtype=bf),
+                "x": torch.zeros(2, 3 * B, self.Kp, device=dev, dtype=bf),       # two slots: the next minibatch's operand can be prepared early
+                "dlogit": torch.zeros(3 * B, 8, device=dev, dtype=bf),
                 "g2": torch.zeros(B, L2.Np, device=dev, dtype=bf), "g1": torch.zeros(B, L1.Np, device=dev, dtype=bf),
                 "Gb": torch.zeros(B, self.Kp, device=dev, dtype=bf),
                 "du": torch.zeros(B, L1.Np, device=dev, dtype=bf), "scratch": torch.zeros(B, L2.Np, device=dev, dtype=bf),
@@ -65,22 +66,32 @@ class AmpDiscriminator:
             }
         return self._bufs[B]
 
-    def loss_backward(self, amp_agent: torch.Tensor, amp_replay: torch.Tensor, amp_demo: torch.Tensor, update_rms: bool = True) -> torch.Tensor:
-        """ADDS disc_coef * d(disc_loss)/d(params) into the flat gradient buffer.  Returns the fp64 stats tensor
-        [sum softplus(l) agent, sum softplus(-l) demo, #agent l<0, #demo l>0, sum G^2 (G = c*gx), sum w_logit^2, sum all w^2, 0]."""
+    def prepare_inputs(self, amp_agent: torch.Tensor, amp_replay: torch.Tensor, amp_demo: torch.Tensor, update_rms: bool = True, slot: int = 0) -> None:
+        """_preproc_amp_obs in train mode for the three batches of one minibatch, in the reference's order: normalise with the current
+        statistics, then merge the batch (amp_agent.py:1004-1007).  Depends on no weight, so a caller may run it for minibatch i+1
+        while minibatch i is still in its backward pass / gradient all-reduce (operand `slot` = the other one)."""
         B = amp_agent.shape[0]
         if amp_replay.shape[0] != B or amp_demo.shape[0] != B:
             raise _lib.PulseError("agent / replay / demo AMP batches must have the same number of rows")
-        b = self._buf(B)
-        lib, dev = self.lib, self.device
-        L1, L2, L3 = self.mlp.layers
-        x = b["x"]
-        # _preproc_amp_obs in train mode: normalise with the current statistics, then merge the batch (amp_agent.py:1004-1007)
+        x = self._buf(B)["x"][slot]
         for k, src in enumerate((amp_agent, amp_replay, amp_demo)):
             if update_rms:
                 self.rms.normalize_update(src, x[k * B:(k + 1) * B])
             else:
                 self.rms.normalize_into(src, x[k * B:(k + 1) * B])
+
+    def loss_backward(self, amp_agent: torch.Tensor, amp_replay: torch.Tensor, amp_demo: torch.Tensor, update_rms: bool = True,
+                      slot: int = 0, prepared: bool = False) -> torch.Tensor:
+        """ADDS disc_coef * d(disc_loss)/d(params) into the flat gradient buffer.  Returns the fp64 stats tensor
+        [sum softplus(l) agent, sum softplus(-l) demo, #agent l<0, #demo l>0, sum G^2 (G = c*gx), sum w_logit^2, sum all w^2, 0].
+        `prepared`: prepare_inputs(..., slot=slot) already ran for these batches."""
+        B = amp_agent.shape[0]
+        if not prepared:
+            self.prepare_inputs(amp_agent, amp_replay, amp_demo, update_rms, slot)
+        b = self._buf(B)
+        lib, dev = self.lib, self.device
+        L1, L2, L3 = self.mlp.layers
+        x = b["x"][slot]
         logits = self.mlp.forward(x, train=True)                      # [3B, 1]: agent, replay, demo
         self.stats.zero_()
         with torch.cuda.device(dev):

@@ -120,12 +120,14 @@ class PPOPolicy:
         key = (M, train)
         if key not in self._bufs:
             dev = self.device
-            b = {"x": torch.zeros(M, self.Kp, device=dev, dtype=torch.bfloat16)}
+            b = {}
             if train:
+                b["x2"] = torch.zeros(2, M, self.Kp, device=dev, dtype=torch.bfloat16)     # two operand slots (prepare_inputs)
                 Ap = pad8(self.A)
                 b.update(dmu=torch.zeros(M, Ap, device=dev, dtype=torch.bfloat16), dv=torch.zeros(M, 8, device=dev, dtype=torch.bfloat16))
             else:
-                b.update(actions=torch.zeros(M, self.A, device=dev), neglogp=torch.zeros(M, device=dev))
+                b.update(x=torch.zeros(M, self.Kp, device=dev, dtype=torch.bfloat16), actions=torch.zeros(M, self.A, device=dev),
+                         neglogp=torch.zeros(M, device=dev))
             self._bufs[key] = b
         return self._bufs[key]
 
@@ -230,21 +232,46 @@ class PPOPolicy:
         return self.value_rms.unnormalize(value) if self.value_rms is not None else value
 
     # ------------------------------------------------------------------ update side
+    def prepare_inputs(self, obs, amp=None, update_obs_rms: bool = True, slot: int = 0) -> None:
+        """The weight-independent head of calc_gradients for one minibatch: observation normalisation in train mode (statistics
+        BEFORE this batch, then merge it: running_mean_std.py:91-107) and `_preproc_amp_obs` of the three AMP batches, into
+        operand slot `slot`.  train_minibatch(prefetch=...) runs it for the NEXT minibatch on a side stream, off the critical
+        path (under the backward GEMMs, or under the gradient all-reduce on several GPUs)."""
+        b = self._buf(obs.shape[0], True)
+        if update_obs_rms:
+            self.obs_rms.normalize_update(obs, b["x2"][slot])
+        else:
+            self.obs_rms.normalize_into(obs, b["x2"][slot])
+        if amp is not None:
+            self.disc.prepare_inputs(*amp, slot=slot)
+
     def train_minibatch(self, obs, actions, old_neglogp, advantages, returns, old_mu=None, update_obs_rms: bool = True,
-                        world_size: int = 1, amp=None, keep_grads: bool = False) -> torch.Tensor:
+                        world_size: int = 1, amp=None, keep_grads: bool = False, slot: int = 0, prepared: bool = False,
+                        prefetch=None) -> torch.Tensor:
         """One calc_gradients step (amp_agent.py:605-760, PPO branch without the discriminator term).
         `returns` are already value-normalised (prepare_dataset, common_agent.py:372-374).  Returns the fp64
         stats tensor [sum a_loss, sum c_loss, sum b_loss, sum kl, clipped, sum neglogp], ACCUMULATED since reset_stats() (divide by the
-        rows seen)."""
+        rows seen).
+        `slot` / `prepared`: the normalised operands of this minibatch live in slot `slot`; `prepared=True` says prepare_inputs()
+        already filled it.  `prefetch=(obs_next, amp_next)`: prepare_inputs() of the NEXT minibatch into slot `1 - slot` on a side
+        stream (same order of running-statistics updates as the reference: batch i+1 after batch i)."""
         M = obs.shape[0]
         b = self._buf(M, True)
+        x = b["x2"][slot]
         # Three independent chains -- actor, critic, discriminator -- run on three streams (fork/join with events, so
         # the whole minibatch still captures into ONE CUDA graph): the persistent GEMMs of one chain fill the partial
         # last wave of another, and the HBM-bound normalise / moments / loss kernels overlap with tensor-core work.
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-        s_critic, s_disc = self._side
+            self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_critic, s_disc, s_pref = self._side
+        pref_at = os.environ.get("PULSE_PREFETCH_AT", "reduce" if world_size > 1 else "start") if prefetch is not None else None
+
+        def fork_prefetch():
+            s_pref.wait_stream(main)
+            with torch.cuda.stream(s_pref):
+                self.prepare_inputs(prefetch[0], prefetch[1], update_obs_rms, 1 - slot)
+
         self.flat.begin_backward()                                # weight / bias gradients are accumulated by bulk reductions / atomics
         reducer = self._reducer(world_size)                  # multi-GPU: every chain averages ITS gradient slice on its own stream
         # Measured at 2 GPUs (profiles/r02_grad_reduce_ab.txt): reducing every chain's slice on its own stream ("chain") is SLOWER than one
@@ -254,27 +281,27 @@ class PPOPolicy:
         single = reducer is not None and os.environ.get("PULSE_GRAD_REDUCE", "single") != "chain"
         if single:
             reducer = None
+        if not prepared:
+            self.prepare_inputs(obs, None, update_obs_rms, slot)
+        if pref_at == "start":
+            fork_prefetch()
         if amp is not None:                                  # (agent, replay, demo) AMP observation batches: disc_coef * disc_loss
             s_disc.wait_stream(main)
             with torch.cuda.stream(s_disc):
-                self.disc.loss_backward(*amp)
+                self.disc.loss_backward(*amp, slot=slot, prepared=prepared)
                 if reducer is not None:
                     d0, d1 = self.disc.mlp.param_span()
                     reducer.reduce(self.flat.grads[d0:d1], 2)
-        if update_obs_rms:                                   # normalise with the statistics BEFORE this batch, then merge it
-            self.obs_rms.normalize_update(obs, b["x"])       # (running_mean_std.py:91-107, train mode), one pass over obs
-        else:
-            self.obs_rms.normalize_into(obs, b["x"])
         from .dense import grouped_enabled
         grouped = grouped_enabled()    # PULSE_GROUPED=1: actor + critic in lock step through grouped launches (experimental, default off)
         if grouped:
             from .nets import backward_lockstep, forward_lockstep
-            mu, value = forward_lockstep((self.actor, self.critic), (b["x"], b["x"]), train=True)
+            mu, value = forward_lockstep((self.actor, self.critic), (x, x), train=True)
         else:
             s_critic.wait_stream(main)
             with torch.cuda.stream(s_critic):
-                value = self.critic.forward(b["x"], train=True)
-            mu = self.actor.forward(b["x"], train=True)
+                value = self.critic.forward(x, train=True)
+            mu = self.actor.forward(x, train=True)
             main.wait_stream(s_critic)
         a = _lib.PpoLossArgs(
             mu=mu.data_ptr(), ld_mu=mu.stride(0), value=value.data_ptr(), ld_value=value.stride(0), actions=actions.data_ptr(),
@@ -285,6 +312,8 @@ class PPOPolicy:
             stats=self.stats.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_ppo_loss(C.byref(a), M, _lib.current_stream(self.device)), "pulse_ppo_loss")
+        if pref_at == "loss":
+            fork_prefetch()
         if grouped:
             backward_lockstep((self.actor, self.critic), (b["dmu"], b["dv"]), M)
         else:
@@ -305,10 +334,14 @@ class PPOPolicy:
             reducer.reduce(self.flat.grads[a0:c1], 0)
         if amp is not None:
             main.wait_stream(s_disc)
+        if pref_at == "reduce":
+            fork_prefetch()
         if single:
             from .dist_utils import average_gradients
             average_gradients(self.flat.grads, world_size)
         self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
+        if pref_at is not None:
+            main.wait_stream(s_pref)
         return self.stats
 
     # ------------------------------------------------------------------ checkpoint keys (rl_games layout)

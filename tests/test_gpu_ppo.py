@@ -5,6 +5,8 @@ Tolerances: the GEMMs run bf16 x bf16 -> fp32 (north_star: 'losses within 1e-3')
 import ctypes as C
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -242,3 +244,50 @@ def test_single_output_head_kernels(rows, k):
     torch.testing.assert_close(dw, 1 + (d[:, None] * h.float()).sum(0), atol=1e-4, rtol=1e-4)   # ADDS into the gradient buffers
     torch.testing.assert_close(db, 1 + d.sum().reshape(1), atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(dbp, 1 + dh_ref.sum(0), atol=1e-4, rtol=1e-4)
+
+
+def test_prefetched_minibatch_sequence_equals_inline_sequence():
+    """train_minibatch(prepared=True, prefetch=next) -- the next minibatch's normalisation + running-statistics updates prepared
+    on a side stream into the other operand slot -- must leave the same weights, normalisers and loss statistics as the inline
+    sequence (same order of statistics updates as calc_gradients: batch i, then batch i+1)."""
+    from pulse_b200.ppo import PPOPolicy
+    g = torch.Generator(device=DEV).manual_seed(11)
+    M, B, n = 1024, 512, 4
+    obs = [torch.randn(M, 934, device=DEV, generator=g) * (1 + k) for k in range(n)]
+    eps = [torch.randn(M, 69, device=DEV, generator=g) for _ in range(n)]
+    adv = [torch.randn(M, device=DEV, generator=g) for _ in range(n)]
+    ret = [torch.randn(M, device=DEV, generator=g) for _ in range(n)]
+    amp = [tuple(torch.randn(B, 1960, device=DEV, generator=g) * (1 + 0.5 * k) for _ in range(3)) for k in range(n)]
+    results = []
+    for mode in ("inline", "start", "loss", "reduce"):
+        pol = PPOPolicy(device=DEV, seed=5, with_disc=True)
+        act, mu, nlp = [], [], []
+        for i in range(n):                           # rollout-consistent actions / neglogp / mus (probability ratios near 1)
+            out = pol.act(obs[i], eps=eps[i])
+            act.append(out["actions"].clone()), mu.append(out["mus"].clone()), nlp.append(out["neglogpacs"].clone())
+        if mode != "inline":
+            os.environ["PULSE_PREFETCH_AT"] = mode
+            pol.prepare_inputs(obs[0], amp[0], slot=0)
+        try:
+            for rep in range(2):                     # two passes over the minibatches, like two mini-epochs
+                for i in range(n):
+                    kw = {}
+                    if mode != "inline":
+                        last = rep == 1 and i == n - 1
+                        kw = dict(slot=i & 1, prepared=True, prefetch=None if last else (obs[(i + 1) % n], amp[(i + 1) % n]))
+                    pol.train_minibatch(obs[i], act[i], nlp[i], adv[i], ret[i], old_mu=mu[i], amp=amp[i], **kw)
+        finally:
+            os.environ.pop("PULSE_PREFETCH_AT", None)
+        torch.cuda.synchronize()
+        results.append((pol.flat.params.clone(), pol.obs_rms.running_mean.clone(), pol.obs_rms.count.clone(),
+                        pol.disc.rms.running_var.clone(), pol.stats.clone(), pol.disc.stats.clone()))
+    base = results[0]
+    for mode, res in zip(("start", "loss", "reduce"), results[1:]):
+        for k, (a, b) in enumerate(zip(base, res)):
+            if k == 0:               # weights: the fp32 reductions of the weight gradients are order-dependent in the last bits, and
+                d = (a - b).abs()    # Adam turns a sign flip of a ~0 gradient into 2 * lr; 8 steps at lr 2e-5 bound the worst case
+                assert d.mean().item() < 1e-6 and d.max().item() < 5e-4, (mode, d.mean().item(), d.max().item())
+            elif k in (4, 5):        # loss sums
+                torch.testing.assert_close(a, b, atol=1e-6, rtol=2e-4, msg=lambda m: f"{mode} item {k}: {m}")
+            else:                    # running statistics: the same kernels on the same data in the same order (fp64 atomics: last bits)
+                torch.testing.assert_close(a, b, atol=0.0, rtol=1e-11, msg=lambda m: f"{mode} item {k}: {m}")

@@ -67,15 +67,15 @@ def main():
         print(f"{name:34s} {us:8.2f} us   floor {nbytes / hbm / 1e3:6.2f} us   {nbytes / us / 1e3:8.1f} GB/s")
 
     bx = pol._buf(M, True)
-    case("obs normalize_update (+merge)", lambda: pol.obs_rms.normalize_update(obs, bx["x"]), M * 934 * 4 + M * pol.Kp * 2)
-    case("obs normalize_into", lambda: pol.obs_rms.normalize_into(obs, bx["x"]), M * 934 * 4 + M * pol.Kp * 2)
+    case("obs normalize_update (+merge)", lambda: pol.obs_rms.normalize_update(obs, bx["x2"][0]), M * 934 * 4 + M * pol.Kp * 2)
+    case("obs normalize_into", lambda: pol.obs_rms.normalize_into(obs, bx["x2"][0]), M * 934 * 4 + M * pol.Kp * 2)
     bd = pol.disc._buf(B)
-    case("amp normalize_update x3 (+merge)", lambda: [pol.disc.rms.normalize_update(s_, bd["x"][k * B:(k + 1) * B]) for k, s_ in enumerate(amp)],
+    case("amp normalize_update x3 (+merge)", lambda: [pol.disc.rms.normalize_update(s_, bd["x"][0][k * B:(k + 1) * B]) for k, s_ in enumerate(amp)],
          3 * (B * 1960 * 4 + B * pol.disc.Kp * 2))
     ws = pol.critic._ws[(M, True)]
     h2, dh = ws["act"][1], ws["dact"][1]
     head = pol.critic.layers[-1]
-    case("head1_forward (critic)", lambda: pol.critic.forward(bx["x"], train=True) if False else _lib.check(lib.pulse_head1_forward(
+    case("head1_forward (critic)", lambda: pol.critic.forward(bx["x2"][0], train=True) if False else _lib.check(lib.pulse_head1_forward(
         h2.data_ptr(), h2.stride(0), M, head.Kp, head.w_bf16.data_ptr(), pol.critic._zero_bias().data_ptr(), ws["out"].data_ptr(), ws["out"].stride(0), st()), "h1f"),
          M * head.Kp * 2)
     case("head1_backward (critic)", lambda: pol.critic._backward_head(ws, bx["dv"], M), 2 * M * head.Kp * 2)

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--amp-rows", type=int, default=4096)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--prefetch", default="none", choices=("none", "start", "loss", "reduce"),
+                    help="prepare the next minibatch's normalised operands on a side stream, forked at this point of the step")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
@@ -36,8 +38,16 @@ def main():
     adv, ret = torch.randn(M, device=dev, generator=g), torch.randn(M, device=dev, generator=g)
     amp = tuple(torch.randn(B, 1960, device=dev, generator=g) for _ in range(3))
 
+    if a.prefetch != "none":
+        import os
+        os.environ["PULSE_PREFETCH_AT"] = a.prefetch
+        pol.prepare_inputs(obs, amp, slot=0)
+
     def step():
-        pol.train_minibatch(obs, act, nlp, adv, ret, old_mu=mu, amp=amp)
+        if a.prefetch == "none":
+            pol.train_minibatch(obs, act, nlp, adv, ret, old_mu=mu, amp=amp)
+        else:       # timing only: slot 0 keeps its prepared operands, the prefetch refills slot 1 every step
+            pol.train_minibatch(obs, act, nlp, adv, ret, old_mu=mu, amp=amp, slot=0, prepared=True, prefetch=(obs, amp))
 
     for _ in range(3):
         step()
