@@ -398,6 +398,47 @@ class HumanoidImB200Mixin:
             args["env_ids"] = env_ids.to(torch.int64).contiguous()
         self._pulse.step(flags=_lib.STEP_OBS, **args)
 
+    def _reset_envs(self, env_ids):
+        """Humanoid._reset_envs + HumanoidAMP._reset_envs (humanoid.py:574-587, humanoid_amp.py:347-356) for the reference-state
+        initialisations (`StateInit.Random` / `Start`): `_reset_actors` -> `_reset_ref_state_init` -> `_sample_ref_state` ->
+        `_set_env_state` (humanoid_im.py:921-989, humanoid_amp.py:468-488, :565-597) and `_init_amp_obs` (:519-563) are ONE
+        `pulse_reset_ref_state` launch writing the simulator views and `_amp_obs_buf` in place.  What stays the reference's: the
+        start-time draws come from `torch.rand(env_ids.shape)` exactly as `sample_time_interval` makes them (motion_lib_base.py:411-420:
+        the process RNG stream is consumed identically), `_reset_env_tensors` (the gym indexed setters, humanoid.py:589-609),
+        `_refresh_sim_tensors` with its `_reset_rb_*` restore (humanoid_amp.py:598-620) and `_compute_observations(env_ids)`.
+        Default / Hybrid state initialisation is handed back to the reference."""
+        name = getattr(getattr(self, "_state_init", None), "name", None)
+        if len(env_ids) == 0 or name not in ("Random", "Start"):
+            return super()._reset_envs(env_ids)
+        if not self._pulse_ready:
+            self._pulse_setup()
+        from .flags_compat import flags_test
+        env_ids = env_ids.to(torch.int64).contiguous()
+        self._reset_default_env_ids = []
+        self._state_reset_happened = True
+        if getattr(self, "_pulse_phase", None) is None or self._pulse_phase.shape[0] != self.num_envs:
+            self._pulse_phase = torch.zeros(self.num_envs, device=self.device)
+        if name == "Start" or flags_test():                    # motion_times = 0 (humanoid_im.py:971-977)
+            self._pulse_phase.zero_()
+        else:
+            self._pulse_phase[env_ids] = torch.rand(env_ids.shape, device=self.device)
+        self._pulse.reset_envs(env_ids=env_ids, phase=self._pulse_phase, motion_ids=self._sampled_motion_ids,
+                               motion_start_times=self._motion_start_times, motion_start_offset=self._motion_start_times_offset,
+                               global_offset=self._global_offset, progress_buf=self.progress_buf, cycle_counter=self._cycle_counter,
+                               terminate_buf=self._terminate_buf, root_states=self._humanoid_root_states, dof_pos=self._dof_pos,
+                               dof_vel=self._dof_vel, rigid_body_state=self._rigid_body_state_reshaped,
+                               contact_forces=self._contact_forces, amp_obs_buf=self._amp_obs_buf)
+        self._reset_ref_env_ids = env_ids
+        self._reset_ref_motion_ids = self._sampled_motion_ids[env_ids]
+        self._reset_ref_motion_times = self._motion_start_times[env_ids]
+        # gym's refresh rewrites the rigid-body tensor from the simulator: the reference keeps clones and restores them after it
+        self._reset_rb_pos, self._reset_rb_rot = self._rigid_body_pos[env_ids].clone(), self._rigid_body_rot[env_ids].clone()
+        self._reset_rb_vel, self._reset_rb_ang_vel = self._rigid_body_vel[env_ids].clone(), self._rigid_body_ang_vel[env_ids].clone()
+        self._reset_env_tensors(env_ids)
+        self._refresh_sim_tensors()
+        self._compute_observations(env_ids)
+        # _init_amp_obs: rows 0 .. steps-1 of `_amp_obs_buf[env_ids]` were written by the launch above (row 0 from the state just set)
+
     def _pulse_amp_fused(self, env_ids) -> bool:
         """The fused AMP launch (history shift + current observation) covers the whole-batch call of the default configuration; one
         predicate for BOTH overrides below, so the shift is skipped exactly when the fused launch performs it."""

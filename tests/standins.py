@@ -20,9 +20,13 @@ CONTRACT = {
                                          "_full_body_reward", "_track_bodies_id", "cycle_motion", "resample_motions", "_sample_time"],
         "phc/env/tasks/humanoid.py": ["_rigid_body_state_reshaped", "_dof_vel", "_dof_pos", "dof_force_tensor", "progress_buf", "obs_buf",
                                       "self_obs_buf", "rew_buf", "reset_buf", "_terminate_buf", "max_episode_length", "_enable_early_termination",
-                                      "self_obs_v", "_humanoid_root_states", "post_physics_step", "_has_dof_subset"],
+                                      "self_obs_v", "_humanoid_root_states", "post_physics_step", "_has_dof_subset", "_reset_envs",
+                                      "_reset_env_tensors", "_rigid_body_pos", "_rigid_body_rot", "_rigid_body_vel", "_rigid_body_ang_vel",
+                                      "_contact_forces", "_humanoid_actor_ids"],
         "phc/env/tasks/humanoid_amp.py": ["_update_hist_amp_obs", "_compute_amp_observations", "_amp_obs_buf", "_num_amp_obs_steps", "_motion_lib",
-                                          "amp_obs_v"],
+                                          "amp_obs_v", "_state_init", "_reset_default_env_ids", "_reset_ref_env_ids", "_reset_ref_motion_ids",
+                                          "_reset_ref_motion_times", "_state_reset_happened", "_reset_rb_pos", "_reset_rb_rot", "_reset_rb_vel",
+                                          "_reset_rb_ang_vel", "_refresh_sim_tensors"],
         "phc/env/tasks/humanoid_im_getup.py": ["_recovery_counter"],
     },
     # names of the reference AGENT the mixin reads, overrides or calls through super()
@@ -201,6 +205,17 @@ class StandInHumanoidIm:
         if getup:
             self._recovery_counter = torch.zeros(n, device=dev, dtype=torch.int)     # humanoid_im_getup.py:61
         self.extras, self.actions = {}, None
+        # reset side (humanoid.py:196-243, humanoid_amp.py:95-110)
+        rb = self._rigid_body_state_reshaped[:, :24]
+        self._rigid_body_pos, self._rigid_body_rot = rb[..., 0:3], rb[..., 3:7]
+        self._rigid_body_vel, self._rigid_body_ang_vel = rb[..., 7:10], rb[..., 10:13]
+        self._contact_forces = torch.ones(n, 26, 3, device=dev)
+        self._humanoid_actor_ids = (2 * torch.arange(n, device=dev)).to(torch.int32)         # 2 actors per env
+        self._state_init = types.SimpleNamespace(name="Random")                              # HumanoidAMP.StateInit.Random
+        self._state_reset_happened = False
+        self._reset_default_env_ids, self._reset_ref_env_ids = [], []
+        self.gym_calls = []
+        self._sim_rigid_body_state = self._rigid_body_state_reshaped.clone()                 # what gym's refresh writes back
 
     def post_physics_step(self):
         self.progress_buf += 1                       # humanoid.py:1317
@@ -224,3 +239,26 @@ class StandInHumanoidIm:
 
     def resample_motions(self):
         pass
+
+    def _reset_envs(self, env_ids):
+        raise AssertionError("reference reset path reached: the mixin should have served StateInit.Random")
+
+    def _reset_env_tensors(self, env_ids):           # humanoid.py:589-609 (the gym setters are recorded instead of executed)
+        env_ids_int32 = self._humanoid_actor_ids[env_ids]
+        self.gym_calls.append(("set_actor_root_state_tensor_indexed", env_ids_int32.clone(), len(env_ids_int32)))
+        self.gym_calls.append(("set_dof_state_tensor_indexed", env_ids_int32.clone(), len(env_ids_int32)))
+        self.progress_buf[env_ids] = 0
+        self.reset_buf[env_ids] = 0
+        self._terminate_buf[env_ids] = 0
+        self._contact_forces[env_ids] = 0
+
+    def _refresh_sim_tensors(self):                  # humanoid_amp.py:598-620
+        self._rigid_body_state_reshaped.copy_(self._sim_rigid_body_state)      # gym.refresh_rigid_body_state_tensor: the simulator's (stale) bodies
+        if self._state_reset_happened and "_reset_rb_pos" in self.__dict__:
+            env_ids = self._reset_ref_env_ids
+            if len(env_ids) > 0:
+                self._rigid_body_pos[env_ids] = self._reset_rb_pos
+                self._rigid_body_rot[env_ids] = self._reset_rb_rot
+                self._rigid_body_vel[env_ids] = self._reset_rb_vel
+                self._rigid_body_ang_vel[env_ids] = self._reset_rb_ang_vel
+                self._state_reset_happened = False

@@ -67,6 +67,63 @@ def test_task_mixin_post_physics_step_matches_oracle(getup):
         torch.testing.assert_close(task.obs_buf, before, atol=1e-6, rtol=0)
 
 
+def test_task_mixin_reset_envs_matches_oracle():
+    """`_reset_envs(env_ids)` through the mixin (one fused launch + the reference's own gym setters / refresh / observation call) against
+    the oracle's restatement of the reference's reset chain, with the start-time draws taken from torch's generator exactly as
+    `sample_time_interval` takes them."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.humanoid_im import HumanoidImB200Mixin
+
+    class HumanoidImB200(HumanoidImB200Mixin, StandInHumanoidIm):
+        pass
+
+    n = 389
+    tb = exact_tables(41, seed=8)
+    z, _ = exact_step_inputs(tb, n, seed=9)
+    task = HumanoidImB200(_mlib(tb), z, DEV)
+    g = torch.Generator().manual_seed(2)
+    task._amp_obs_buf.copy_(torch.randn(n, 10, 196, generator=g).to(DEV))
+    task.obs_buf.copy_(torch.randn(n, 934, generator=g).to(DEV))
+    task._humanoid_root_states.copy_(torch.randn(n, 13, generator=g).to(DEV))
+    task._terminate_buf.copy_((torch.rand(n, generator=g) < 0.3).long().to(DEV))
+    env_ids = torch.nonzero(torch.rand(n, generator=g) < 0.2).flatten().to(DEV)
+    st = {"motion_ids": task._sampled_motion_ids, "start_times": task._motion_start_times, "start_offset": task._motion_start_times_offset,
+          "global_offset": task._global_offset, "cycle_counter": task._cycle_counter, "progress_buf": task.progress_buf,
+          "reset_buf": task.reset_buf, "terminate_buf": task._terminate_buf, "root_states": task._humanoid_root_states,
+          "dof_pos": task._dof_pos, "dof_vel": task._dof_vel, "body_state": task._rigid_body_state_reshaped[:, :24],
+          "contact_forces": task._contact_forces[:, :24], "amp_obs_buf": task._amp_obs_buf, "obs_buf": task.obs_buf,
+          "dof_force": task.dof_force_tensor}
+    st = {k: v.detach().cpu().clone().contiguous() for k, v in st.items()}
+    torch.manual_seed(77)
+    draws = torch.rand(env_ids.shape, device=DEV)                     # what sample_time_interval would draw for these envs
+    phase = torch.zeros(n)
+    phase[env_ids.cpu()] = draws.cpu()
+    torch.manual_seed(77)
+    task._reset_envs(env_ids)
+    torch.cuda.synchronize()
+    exp = po.reset_envs(tb, po.ImStepConfig(), st, env_ids.cpu(), phase)
+    ids = env_ids.cpu()
+    assert torch.equal(task.progress_buf.cpu(), exp["progress_buf"]) and torch.equal(task.reset_buf.cpu(), exp["reset_buf"])
+    assert torch.equal(task._terminate_buf.cpu(), exp["terminate_buf"]) and torch.equal(task._cycle_counter.cpu(), exp["cycle_counter"])
+    torch.testing.assert_close(task._motion_start_times.cpu(), exp["start_times"], atol=0, rtol=0)
+    torch.testing.assert_close(task._motion_start_times_offset.cpu(), exp["start_offset"], atol=0, rtol=0)
+    torch.testing.assert_close(task._global_offset.cpu(), exp["global_offset"], atol=0, rtol=0)
+    torch.testing.assert_close(task._humanoid_root_states.cpu(), exp["root_states"], atol=1e-5, rtol=0)
+    torch.testing.assert_close(task._dof_pos.cpu(), exp["dof_pos"], atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(task._dof_vel.cpu(), exp["dof_vel"], atol=1e-4, rtol=0)
+    # the rigid bodies of the reset envs survive gym's refresh through the reference's _reset_rb_* restore; the others are the simulator's
+    torch.testing.assert_close(task._rigid_body_state_reshaped[:, :24].cpu(), exp["body_state"], atol=1e-5, rtol=0)
+    assert float(task._contact_forces[env_ids].abs().max()) == 0.0 and float(task._contact_forces.sum()) == 3 * 26 * (n - len(ids))
+    torch.testing.assert_close(task._amp_obs_buf.cpu(), exp["amp_obs_buf"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.obs_buf.cpu(), exp["obs_buf"], atol=1e-4, rtol=0)
+    assert [c[0] for c in task.gym_calls] == ["set_actor_root_state_tensor_indexed", "set_dof_state_tensor_indexed"]
+    assert torch.equal(task.gym_calls[0][1].cpu(), (2 * ids).to(torch.int32)) and task.gym_calls[0][2] == len(ids)
+    assert torch.equal(task._reset_ref_motion_times.cpu(), exp["start_times"][ids]) and task._state_reset_happened is False
+    # an empty list and the non-reference initialisations go back to the reference implementation
+    with pytest.raises(AssertionError, match="reference reset path"):
+        task._reset_envs(env_ids[:0])
+
+
 def _agent(seed=0, **kw):
     from pulse_b200.agent_mixins import AMPAgentB200Mixin
 
