@@ -659,6 +659,9 @@ def main():
             "gemm_switches": {"cta_pairs": os.environ.get("PULSE_GEMM_PAIR", "1") != "0", "pdl": os.environ.get("PULSE_GEMM_PDL", "1") != "0",
                               "grouped_launches": os.environ.get("PULSE_GROUPED", "0") == "1"},
             "update_input_prefetch": bool(prefetching),
+            "optimizer_step": ("one peer-memory kernel per rank: reduce-scatter over NVLink + norm clip + sharded Adam + push of masters / bf16 operands"
+                               + (" (multimem)" if policy.flat.peer and policy.flat.peer["multicast"] else "")) if (world > 1 and policy.flat.peer)
+                              else ("ncclAllReduce(AVG) + sum_squares + adam" if world > 1 else "sum_squares + adam (single GPU)"),
             "roofline": {"kernel": "im_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/im_step_traffic.json)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,

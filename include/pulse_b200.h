@@ -474,6 +474,41 @@ int pulse_sum_squares(const float* x, int64_t count, double* sumsq, void* stream
 int pulse_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t count, double* grad_sumsq,
                     float max_norm, float lr, float beta1, float beta2, float eps, int32_t* step, pulse_bf16_t* params_bf16, uint32_t flags,
                     uint32_t* block_counter, void* stream);
+/* Multi-GPU optimizer step over NVLink peer memory (csrc/peer_adam.cu): the reference's Horovod gradient averaging
+ * (hvd.DistributedOptimizer, amp_agent.py:735-742) + clip_grad_norm_ + torch.optim.Adam (amp_agent.py:725-750) as ONE kernel per rank --
+ * reduce-scatter of the flat gradient buffers by peer loads (or multimem.ld_reduce), exchange of the slice norms, Adam on the rank's
+ * slice (sharded moments), push of the new fp32 masters + bf16 operands into every rank's buffers (peer stores or multimem.st), clearing
+ * of the gradients.  Replaces pulse_sum_squares + pulse_adam_step + the NCCL all-reduce when the ranks' buffers are peer-mapped.
+ *   grads / params / params_bf16 / signals [p]: rank p's buffer as mapped into THIS process ([rank] = the local one).  A signal block
+ *   is PULSE_PEER_SIGNAL_BYTES of zero-initialised memory: uint32 flags[3][PULSE_PEER_MAX] then double norms[PULSE_PEER_MAX].
+ *   mc_*: multicast aliases of the same buffers (NVLS), or NULL.  exp_avg / exp_avg_sq: local, full size; only this rank's slice
+ *   [rank * ceil(count/4/world) * 4, ...) is read or written.  step: device Adam step counter (incremented).  epoch: device uint32[1]
+ *   call counter, zero-initialised, same value on every rank.  cta_partials: double[PULSE_PEER_MAX_GRID]; grid_bar: uint64[1] zero-
+ *   initialised; grid: CTAs (0 = one per SM) -- must not change between calls that share grid_bar.
+ * Every rank must make the call (it waits for its peers, bounded by timeout_ms, then the launch fails); count is a multiple of 4. */
+#define PULSE_PEER_MAX 8
+#define PULSE_PEER_MAX_GRID 256
+#define PULSE_PEER_SIGNAL_BYTES (3 * PULSE_PEER_MAX * 4 + PULSE_PEER_MAX * 8)
+typedef struct {
+  int32_t rank, world;
+  float* grads[PULSE_PEER_MAX];
+  float* params[PULSE_PEER_MAX];
+  pulse_bf16_t* params_bf16[PULSE_PEER_MAX];
+  uint32_t* signals[PULSE_PEER_MAX];
+  const float* mc_grads; float* mc_params; pulse_bf16_t* mc_params_bf16;
+  float* exp_avg; float* exp_avg_sq;
+  int64_t count;
+  float max_norm, lr, beta1, beta2, eps;
+  int32_t grid;
+  uint32_t timeout_ms;                     /* bound of every wait on a peer (0 = 20000) */
+  uint32_t reserved;
+  int32_t* step;
+  uint32_t* epoch;
+  double* cta_partials;
+  unsigned long long* grid_bar;
+} pulse_peer_adam_args_t;
+int pulse_peer_reduce_adam(const pulse_peer_adam_args_t* args, void* stream);
+
 /* refresh the bf16 operand copies of one weight matrix W fp32 [n, k] (contiguous):
  *   w_bf16 [n, ld_k] (K-major, forward / wgrad-free) and wt_bf16 [k, ld_n] (transposed, dgrad operand); pads zeroed. */
 int pulse_refresh_weight_bf16(const float* w, int64_t n, int64_t k, pulse_bf16_t* w_bf16, int64_t ld_k, pulse_bf16_t* wt_bf16,

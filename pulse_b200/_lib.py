@@ -176,6 +176,21 @@ class LoaderArgs(C.Structure):
     ]
 
 
+PEER_MAX, PEER_MAX_GRID, PEER_SIGNAL_BYTES = 8, 256, 3 * 8 * 4 + 8 * 8
+
+
+class PeerAdamArgs(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32),
+        ("grads", C.c_void_p * PEER_MAX), ("params", C.c_void_p * PEER_MAX), ("params_bf16", C.c_void_p * PEER_MAX),
+        ("signals", C.c_void_p * PEER_MAX),
+        ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p), ("mc_params_bf16", C.c_void_p),
+        ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("count", C.c_int64),
+        ("max_norm", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grid", C.c_int32),
+        ("timeout_ms", C.c_uint32), ("reserved", C.c_uint32), ("step", C.c_void_p), ("epoch", C.c_void_p), ("cta_partials", C.c_void_p), ("grid_bar", C.c_void_p),
+    ]
+
+
 ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 Z_SAMPLE, Z_MEAN, Z_RESIDUAL = 0, 1, 2
@@ -230,6 +245,7 @@ SIGNATURES = {
     "pulse_sum_squares": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pulse_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "pulse_peer_reduce_adam": (C.c_int, [C.POINTER(PeerAdamArgs), C.c_void_p]),
     "pulse_refresh_weight_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "pulse_normalize_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64,
                                        C.c_int64, C.c_void_p]),

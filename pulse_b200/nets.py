@@ -14,6 +14,8 @@ dW = dY^T X accumulated with fp32 atomics across split-K CTAs straight into the 
 """
 import ctypes as C
 import math
+import os
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -68,14 +70,104 @@ class FlatParams:
         self._shapes.append((off, tuple(shape)))
         return len(self._shapes) - 1
 
-    def finalize(self):
+    def finalize(self, peer: Optional[bool] = None):
+        """Allocates the flat buffers.  `peer` (default: PULSE_PEER_ADAM != 0 and an initialised NCCL process group with more than one
+        rank): gradients, fp32 masters and the bf16 operands live in symmetric memory mapped into every rank of the node, so the
+        optimizer step is pulse_peer_reduce_adam (csrc/peer_adam.cu) instead of NCCL all-reduce + sum_squares + Adam; the Adam moments
+        are then SHARDED (rank r keeps slice r current; gather_moments() before reading them).  COLLECTIVE when peer mode is on: every
+        rank finalises its FlatParams objects in the same order."""
         z = lambda: torch.zeros(self._numel, device=self.device, dtype=torch.float32)
-        self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
-        self.params_bf16 = torch.zeros(self._numel, device=self.device, dtype=torch.bfloat16)
+        self.peer = None
+        if peer is None:
+            peer = os.environ.get("PULSE_PEER_ADAM", "1") != "0"
+        if peer and torch.device(self.device).type == "cuda":
+            try:
+                self._alloc_peer()
+            except Exception as e:   # no symmetric memory on this box / driver: NCCL path (same results up to summation order)
+                warnings.warn(f"pulse_b200: peer-memory optimizer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path")
+                self.peer = None
+        if self.peer is None:
+            self.params, self.grads = z(), z()
+            self.params_bf16 = torch.zeros(self._numel, device=self.device, dtype=torch.bfloat16)
+        self.exp_avg, self.exp_avg_sq = z(), z()
         self.sumsq = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
         self._adam_sync = torch.zeros(1, device=self.device, dtype=torch.int32)   # last-block counter of the self-contained Adam launch
         self.clean = True                                                          # gradients are all zero
+
+    # ------------------------------------------------------------------ peer-memory optimizer (multi-GPU)
+    def _alloc_peer(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1 or dist.get_backend() != "nccl":
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world > _lib.PEER_MAX:
+            return
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+
+        def alloc(n, dtype):
+            t = symm.empty(n, dtype=dtype, device=self.device)
+            t.zero_()
+            return t, symm.rendezvous(t, group)
+
+        grads, hg = alloc(self._numel, torch.float32)
+        params, hp = alloc(self._numel, torch.float32)
+        pbf16, hb = alloc(self._numel, torch.bfloat16)
+        sig, hs = alloc(256, torch.uint8)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                                   # every rank's buffers are zeroed before anyone can signal into them
+        a = _lib.PeerAdamArgs(rank=rank, world=world, count=self._numel)
+        for p in range(world):
+            a.grads[p], a.params[p], a.params_bf16[p], a.signals[p] = int(hg.buffer_ptrs[p]), int(hp.buffer_ptrs[p]), int(hb.buffer_ptrs[p]), int(hs.buffer_ptrs[p])
+        if int(a.grads[rank]) != grads.data_ptr() or int(a.params[rank]) != params.data_ptr():
+            raise RuntimeError("symmetric-memory handle does not describe the local tensors")
+        use_mc = os.environ.get("PULSE_PEER_MC", "0") == "1"
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (hg, hp, hb)]
+        if use_mc and all(mc):
+            a.mc_grads, a.mc_params, a.mc_params_bf16 = mc
+        self.grads, self.params, self.params_bf16 = grads, params, pbf16
+        dev = self.device
+        scratch = dict(epoch=torch.zeros(1, dtype=torch.int32, device=dev), partials=torch.zeros(_lib.PEER_MAX_GRID, dtype=torch.float64, device=dev),
+                       bar=torch.zeros(1, dtype=torch.int64, device=dev))
+        a.epoch, a.cta_partials, a.grid_bar = scratch["epoch"].data_ptr(), scratch["partials"].data_ptr(), scratch["bar"].data_ptr()
+        a.grid = int(os.environ.get("PULSE_PEER_GRID", "0"))
+        self.peer = dict(args=a, handles=(hg, hp, hb, hs), signals=sig, scratch=scratch, world=world, rank=rank, multicast=bool(a.mc_grads))
+
+    def shard_span(self):
+        """[start, end) elements of the flat buffers whose Adam moments THIS rank keeps current in peer mode."""
+        if self.peer is None:
+            return 0, self._numel
+        w, r, n4 = self.peer["world"], self.peer["rank"], self._numel // 4
+        per = (n4 + w - 1) // w
+        s0 = min(per * r, n4)
+        return 4 * s0, 4 * min(s0 + per, n4)
+
+    def peer_adam_step(self, lr: float, max_norm: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        """Gradient averaging over the ranks + clip_grad_norm_ + Adam + operand refresh + gradient clearing as one launch per rank
+        (hvd.DistributedOptimizer + amp_agent.py:725-750).  Every rank must call it (the kernel waits for its peers)."""
+        a = self.peer["args"]
+        a.exp_avg, a.exp_avg_sq, a.step = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step.data_ptr()
+        a.max_norm, a.lr, a.beta1, a.beta2, a.eps = float(max_norm or 0.0), float(lr), float(betas[0]), float(betas[1]), float(eps)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pulse_peer_reduce_adam(C.byref(a), _lib.current_stream(self.device)), "pulse_peer_reduce_adam")
+        self.clean = True
+
+    def gather_moments(self):
+        """Peer mode shards the Adam moments: bring every rank's copy up to date (checkpoints, tests).  Collective."""
+        if self.peer is None:
+            return
+        import torch.distributed as dist
+        s0, s1 = self.shard_span()
+        for buf in (self.exp_avg, self.exp_avg_sq):
+            tmp = torch.zeros_like(buf)
+            tmp[s0:s1] = buf[s0:s1]
+            dist.all_reduce(tmp)
+            buf.copy_(tmp)
 
     def sync_bf16(self):
         """bf16 mirror <- fp32 masters (after init / checkpoint load; the Adam kernel keeps it current afterwards)."""

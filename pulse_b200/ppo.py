@@ -156,17 +156,26 @@ class PPOPolicy:
                 "sigmas": torch.exp(self.logstd).expand(M, self.A)}
 
     def act_into(self, obs: torch.Tensor, *, actions: torch.Tensor, neglogp: torch.Tensor, mus: torch.Tensor, values: Optional[torch.Tensor] = None,
-                 pd: Optional[tuple] = None, eps: Optional[torch.Tensor] = None, rng_step: int = 0) -> None:
+                 pd: Optional[tuple] = None, eps: Optional[torch.Tensor] = None, rng_step: int = 0, side=None) -> None:
         """get_action_values (common_agent.py:262-288) + the experience-buffer updates of play_steps (amp_agent.py:361-378) + the PD
         targets of pre_physics_step (humanoid.py:1222-1257) with NO intermediate copies: the actor head GEMM writes `mus` (a
         [M, A] slice of the experience buffer, any row stride), `pulse_policy_post` draws the noise in-kernel (Philox; `eps`
         injects it for tests) and writes actions / neglogp / de-normalised values / PD targets through (pointer, stride).
-        pd = (offset [A], scale [A], out [M, A])."""
+        pd = (offset [A], scale [A], out [M, A]).  `side`: a second CUDA stream -- the critic's forward pass then runs beside the
+        actor's (at the per-rank env counts of a multi-GPU run neither fills the GPU)."""
         M = obs.shape[0]
         b = self._buf(M, False)
         self.obs_rms.normalize_into(obs, b["x"])
-        self.actor.forward(b["x"], out=mus)
-        value = self.critic.forward(b["x"]) if values is not None else None
+        if side is not None and values is not None:      # actor | critic on two streams (fork / join: still one CUDA-graph segment)
+            main = torch.cuda.current_stream(self.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                value = self.critic.forward(b["x"])
+            self.actor.forward(b["x"], out=mus)
+            main.wait_stream(side)
+        else:
+            self.actor.forward(b["x"], out=mus)
+            value = self.critic.forward(b["x"]) if values is not None else None
         a = _lib.PolicyPostArgs(mu=mus.data_ptr(), ld_mu=mus.stride(0), logstd=self.logstd.data_ptr(), seed=self.rng_seed,
                                 rng_offset=self.rng_offset.data_ptr(), rng_step=int(rng_step), num_actions=self.A,
                                 actions=actions.data_ptr(), ld_actions=actions.stride(0), neglogp=neglogp.data_ptr(), ld_neglogp=neglogp.stride(0))
@@ -336,10 +345,15 @@ class PPOPolicy:
             main.wait_stream(s_disc)
         if pref_at == "reduce":
             fork_prefetch()
-        if single:
-            from .dist_utils import average_gradients
-            average_gradients(self.flat.grads, world_size)
-        self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
+        if self.flat.peer is not None and world_size > 1 and not keep_grads:
+            # one kernel per rank over NVLink peer memory: reduce-scatter of the gradients, norm clip, Adam on the rank's slice, push of
+            # the new masters / bf16 operands to every rank (csrc/peer_adam.cu) -- no NCCL call on the data path
+            self.flat.peer_adam_step(self.lr, max_norm=self.grad_norm)
+        else:
+            if single:
+                from .dist_utils import average_gradients
+                average_gradients(self.flat.grads, world_size)
+            self.flat.adam_step(self.lr, max_norm=self.grad_norm, zero_grads=not keep_grads)  # also writes the bf16 operand mirror, clears the gradients
         if pref_at is not None:
             main.wait_stream(s_pref)
         return self.stats
@@ -396,6 +410,7 @@ class PPOPolicy:
     def optimizer_state(self) -> Dict[str, Dict[str, torch.Tensor]]:
         """torch.optim.Adam state per reference parameter name: {'exp_avg', 'exp_avg_sq'} in the parameter's shape, plus 'step'."""
         out = {}
+        self.flat.gather_moments()      # peer mode keeps the moments sharded over the ranks (collective; no-op otherwise)
         step = self.flat.step.clone().float().reshape(())
         for name, l in self._named_layers():
             m, v = self.flat.view(l.w_idx, "exp_avg"), self.flat.view(l.w_idx, "exp_avg_sq")

@@ -4,6 +4,7 @@ Host-side mirror of `CommonAgent.discount_values` (phc/learning/common_agent.py:
 `mb_returns = mb_advs + mb_values` (amp_agent.py:427) and `_calc_advs` (:589-599).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -79,6 +80,11 @@ class PlayStepsB200:
         self.amp_x = None
         self.host_io = None            # bench.py's end-to-end arm: (upload(t), download(t)) callables
         self.physics = None
+        # Independent pieces of a step run on a second stream (fork / join inside the captured segment): the AMP row beside the
+        # next-value critic, the critic beside the actor.  At 2048 envs per rank (8 GPUs) every kernel of the step is latency-bound
+        # (7-17 us each, profiles/r02_rollout_step_2048envs_launches.txt), so the step time is the length of the dependency chain.
+        self.fork = os.environ.get("PULSE_ROLLOUT_FORK", "1") != "0"
+        self._side = None
 
     # ------------------------------------------------------------------ the pieces of one step
     def _step_kw(self):
@@ -98,7 +104,14 @@ class PlayStepsB200:
                              actor_ids=s.get("actor_ids"), seed=self.reset_seed, offset=t, offset_dev=pol.rng_offset, obs_buf=self.obses[:, t],
                              amp_fresh=self.amp_fresh)
         pol.act_into(self.obses[:, t], actions=self.actions[:, t], neglogp=self.neglogp[:, t], mus=self.mus[:, t], values=self.values[t],
-                     pd=(self.pd[0], self.pd[1], self.pd_tar), rng_step=t)
+                     pd=(self.pd[0], self.pd[1], self.pd_tar), rng_step=t, side=self._side_stream())
+
+    def _side_stream(self):
+        if not self.fork:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        return self._side
 
     def _next_obs(self, t: int) -> torch.Tensor:
         return self.obses[:, t + 1] if t + 1 < self.T else self.obs_carry
@@ -116,9 +129,16 @@ class PlayStepsB200:
         """AMP observation row of step t (humanoid_amp.py:194-210, amp_agent.py:385) and next_values (:396-398)."""
         s = self.sim
         prev = self.amp_obs[:, t - 1] if t > 0 else self.amp_obs[:, self.T - 1]
-        self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
-                              fresh=self.amp_fresh, fresh_rows=self.amp_init)
+        side = self._side_stream()
+        main = torch.cuda.current_stream(self.dev)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
+                                  fresh=self.amp_fresh, fresh_rows=self.amp_init)
         self.policy.critic_values_into(self._next_obs(t), self.next_values[t].view(-1), terminate=self.terminate_buf)
+        if side is not None:
+            main.wait_stream(side)     # the reset of the next segment rewrites the state / flags the AMP row reads
 
     def _segment(self, t: int) -> None:
         """Everything between env step t-1 and env step t."""

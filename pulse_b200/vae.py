@@ -64,7 +64,7 @@ class PulseVAE:
             self.frozen = FlatParams(self.device)
             self.critic_z = MLP(self.frozen, self.obs_size, tu, E, "silu")               # critic_z_mlp (:557-)
             self.critic = MLP(self.frozen, S + E, du, 1, "silu", in_perm=perm)           # critic_mlp + value
-            self.frozen.finalize()
+            self.frozen.finalize(peer=False)      # never optimised: plain device memory
         gen = torch.Generator(device=self.device).manual_seed(seed)
         for m in (self.enc, self.prior, self.dec, self.critic_z, self.critic):
             if m is not None:
@@ -216,11 +216,15 @@ class PulseVAE:
             self.prior.backward(b["d_prior"], M)
         self.enc.backward(b["d_enc"], M)
         main.wait_stream(side)
-        if world_size > 1:   # the reference's kin_optimizer is not Horovod-wrapped (amp_agent.py:67); multi-GPU needs the average
-            from .dist_utils import average_gradients
-            average_gradients(self.flat.grads, world_size)
-        if step:
-            self.flat.adam_step(self.kin_lr, max_norm=self.grad_norm)
+        # the reference's kin_optimizer is not Horovod-wrapped (amp_agent.py:67); multi-GPU needs the average
+        if world_size > 1 and step and self.flat.peer is not None:
+            self.flat.peer_adam_step(self.kin_lr, max_norm=self.grad_norm)     # averaging + clip + Adam as one peer-memory kernel
+        else:
+            if world_size > 1:
+                from .dist_utils import average_gradients
+                average_gradients(self.flat.grads, world_size)
+            if step:
+                self.flat.adam_step(self.kin_lr, max_norm=self.grad_norm)
         return self.stats
 
     def losses(self, M: int) -> Dict[str, float]:
@@ -312,7 +316,7 @@ class TeacherPNN:
         self.flat = FlatParams(self.device)
         self.cols = [MLP(self.flat, obs_size, list(prim_units), num_actions, "relu") for _ in range(num_prim)]
         self.composer = MLP(self.flat, obs_size, list(composer_units), num_prim, composer_act)
-        self.flat.finalize()
+        self.flat.finalize(peer=False)      # frozen teacher: plain device memory
         gen = torch.Generator(device=self.device).manual_seed(seed)
         for m in self.cols + [self.composer]:
             m.init_default(gen)

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(lib):
     import subprocess
     import tempfile
     from pulse_b200 import _lib
-    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t), sizeof(pulse_reset_args_t), sizeof(pulse_policy_post_args_t), sizeof(pulse_amp_row_args_t));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t), sizeof(pulse_reset_args_t), sizeof(pulse_policy_post_args_t), sizeof(pulse_amp_row_args_t), sizeof(pulse_peer_adam_args_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
@@ -46,7 +46,7 @@ def test_struct_sizes_match_header(lib):
     assert sizes == [C.sizeof(_lib.MotionLibDesc), C.sizeof(_lib.MotionQuery), C.sizeof(_lib.ImStepArgs), C.sizeof(_lib.AmpObsArgs),
                      C.sizeof(_lib.GaeArgs), C.sizeof(_lib.GemmEpilogue), C.sizeof(_lib.PpoLossArgs), C.sizeof(_lib.VaeLatentArgs),
                      C.sizeof(_lib.ReachStepArgs), C.sizeof(_lib.LoaderArgs), C.sizeof(_lib.GemmProblem), C.sizeof(_lib.ResetArgs), C.sizeof(_lib.PolicyPostArgs),
-                     C.sizeof(_lib.AmpRowArgs)]
+                     C.sizeof(_lib.AmpRowArgs), C.sizeof(_lib.PeerAdamArgs)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -55,6 +55,11 @@ def test_argument_validation_without_gpu(lib):
     assert b"null" in lib.pulse_last_error()
     assert lib.pulse_motion_state(None, None, 1, None) == -1
     assert lib.pulse_gae(None, 32, 8, None) == -1
+    pa = _lib.PeerAdamArgs()
+    assert lib.pulse_peer_reduce_adam(None, None) == -1
+    assert lib.pulse_peer_reduce_adam(C.byref(pa), None) == -1 and b"world" in lib.pulse_last_error()
+    pa.world, pa.rank, pa.count = 2, 0, 6
+    assert lib.pulse_peer_reduce_adam(C.byref(pa), None) == -1 and b"multiple of 4" in lib.pulse_last_error()
     a = _lib.GaeArgs()
     assert lib.pulse_gae(C.byref(a), 0, 8, None) == -1 and b"horizon" in lib.pulse_last_error()
     d = _lib.MotionLibDesc()
