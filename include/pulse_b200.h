@@ -610,6 +610,48 @@ typedef struct {
 int pulse_reach_step(const pulse_reach_step_args_t* args, int64_t num_envs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Task observation for every observation version / tracked-body subset / number of future samples: replaces the
+ * dispatch of HumanoidIm._compute_task_obs (phc/env/tasks/humanoid_im.py:757-833) over compute_imitation_observations (:1222-1258,
+ * obs_v 1), _v2 (:1261-1301), _v3 (:1304-1326), _v6 (:1328-1378, obs_v 4 / 6), _v7 (:1381-1413), _v8 (:1415-1479, time_steps 1) and
+ * _v9 (:1482-1540) on the `_track_bodies_id` rows.  The reference states are the outputs of pulse_motion_state for the N * time_steps
+ * sample times in repeat_interleave order (row env * time_steps + t; fut_tracks, humanoid_im.py:723-729), full 24-body arrays.
+ * Not covered: zero_out_far / occlusion rewrites (:763-784), the one-hot suffix of obs_v 5, the multi-sample branches of v2 / v8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* body_state; int64_t body_env_stride;   /* [N, B>=24, 13] rigid-body state view */
+  const int32_t* track_ids;                            /* [num_track] device array of body indices < 24; [0] = 0 for versions 2 and 9 */
+  int32_t num_track, time_steps, version, upright;     /* upright = _has_upright_start */
+  const float* ref_pos; const float* ref_rot; const float* ref_vel; const float* ref_ang_vel;   /* [N * time_steps, 24, 3 | 4] */
+  const float* dof_pos; int64_t dof_env_stride, dof_elem_stride;   /* version 2: simulator dof positions (view strides) */
+  const float* ref_dof_pos;                            /* version 2: [N, 69] */
+  float* obs; int64_t obs_stride;                      /* [N, >= pulse_task_obs_size] */
+  int64_t num_envs;
+} pulse_task_obs_args_t;
+int pulse_task_obs_size(int32_t version, int32_t num_track, int32_t time_steps);   /* floats per env, -1 for an unknown version */
+int pulse_im_task_obs(const pulse_task_obs_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device.  One call per evaluation step replaces the per-step bookkeeping of
+ * IMAmpAgent._post_step_eval (phc/learning/im_amp.py:244-363: termination state :249-251, the curr_max stopping rule :252-268, :275,
+ * the per-sequence `[:(num_steps - 1)]` frame slices :283-287) and the per-frame metrics compute_metrics_lite derives from the
+ * frames the reference copies to the host every step (humanoid_im.py:664-673; smpl_sim [3P]): global / root-relative /
+ * Procrustes-aligned MPJPE, velocity and acceleration errors -- accumulated into per-env fp64 sums (metres) and frame counts.
+ *   ctrl int32[8], zeroed at the start of a chunk: [0] steps taken, [1] chunk finished (later calls are no-ops), [2..4] scratch.
+ *   terminate_state int32[N], hist float[N,2,24,3], sums double[N,5] (mpjpe_g, mpjpe_l, mpjpe_pa, vel, accel), counts int32[N,3]
+ *   (frames behind sums 0-2, 3, 4): zeroed at the start of a chunk.  bound: envs [0, bound) hold distinct clips (wrapped last chunk,
+ *   im_amp.py:254-262), otherwise num_envs.  max_steps_all = max(num_steps).  mpjpe_out float[N] (optional): extras['mpjpe'].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* body_pos; int64_t pos_env_stride, pos_body_stride;     /* body j of env e at body_pos + e*env_stride + j*body_stride */
+  const float* body_pos_gt; int64_t gt_env_stride, gt_body_stride;    /* motion_res['rg_pos'] */
+  const int64_t* terminate;    /* [N] terminate_buf */
+  const int32_t* num_steps;    /* [N] get_motion_num_steps() (motion_lib_base.py:428-432) */
+  int32_t num_envs, bound, max_steps_all, reserved;
+  int32_t* ctrl; int32_t* terminate_state; float* hist; double* sums; int32_t* counts; float* mpjpe_out;
+} pulse_eval_args_t;
+int pulse_eval_step(const pulse_eval_args_t* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * MotionLib loader on the device (parity green against the reference's tables, not yet timed).  Per clip: optional heading rotation, local rotations, forward kinematics, gaussian-filtered linear /
  * angular velocities and dof velocities (motion_lib_smpl.py:101-174, poselib skeleton3d.py:389-462, :1100-1118,
  * motion_lib_base.py:47-70) from the on-disk clip arrays concatenated over clips; fills the six fp32 tables

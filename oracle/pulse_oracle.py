@@ -304,6 +304,68 @@ def imitation_obs_v7(root_pos, root_rot, body_pos, body_vel, ref_pos, ref_vel) -
     return torch.cat([x.reshape(n, -1) for x in blocks], dim=-1)
 
 
+def remove_base_rot(q: torch.Tensor) -> torch.Tensor:
+    """humanoid.py:1617-1620: q (x) conj([.5, .5, .5, .5]) -- the SMPL rest orientation of a non-upright start."""
+    base = quat_conj(torch.tensor([[0.5, 0.5, 0.5, 0.5]], dtype=q.dtype)).expand(q.shape[0], 4)
+    return quat_mul(q, base)
+
+
+TASK_OBS_VERSIONS = (1, 2, 3, 6, 7, 8, 9)
+
+
+def imitation_obs(version: int, root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_pos, ref_rot, ref_vel, ref_ang_vel,
+                  time_steps: int = 1, upright: bool = True, dof_pos=None, ref_dof_pos=None) -> torch.Tensor:
+    """Every `compute_imitation_observations*` variant `_compute_task_obs` dispatches on (humanoid_im.py:757-833) for J tracked bodies
+    and `time_steps` future samples (fut_tracks).  body_* [B, J, .] are the SUBSET rows; ref_* [B * time_steps, J, .] in the reference's
+    `repeat_interleave(time_steps)` order (row b * T + t).
+
+      1  :1222-1258  [dp | six(drot) | dv | dw]                                   flat over (t, j)
+      2  :1261-1301  version 1 + (ref_dof_pos - dof_pos) of the tracked joints    (time_steps = 1)
+      3  :1304-1326  [dp | six(drot)]
+      6  :1328-1378  per t: [dp_t | six(drot_t) | dv_t | dw_t | R(pref_t - root) | six(hinv qref_t)]
+      7  :1381-1413  per t: [dp_t | dv_t | R(pref_t - root)]
+      8  :1415-1479  diffs of sample 0 + [R(pref - root) | six(hinv qref) | R vref | R wref]   (time_steps = 1 branch, :1472-1476)
+      9  :1482-1540  per t: [dp_t | six(drot_t) | R(v_ref_root - v_root) | R(w_ref_root - w_root) | R(pref_t - root) | six(hinv qref_t)]
+    """
+    B, J, _ = body_pos.shape
+    T = time_steps
+    if not upright:
+        root_rot = remove_base_rot(root_rot)
+    hinv = heading_quat(root_rot, inverse=True)[:, None, None, :].expand(B, T, J, 4)
+    hfwd = heading_quat(root_rot, inverse=False)[:, None, None, :].expand(B, T, J, 4)
+    rp, rr, rv, rw = ref_pos.view(B, T, J, 3), ref_rot.view(B, T, J, 4), ref_vel.view(B, T, J, 3), ref_ang_vel.view(B, T, J, 3)
+    bp, br, bv, bw = body_pos[:, None], body_rot[:, None].expand(B, T, J, 4), body_vel[:, None], body_ang_vel[:, None]
+    d_pos = quat_rotate(hinv, rp - bp)
+    d_rot6 = quat_to_six(quat_mul(quat_mul(hinv, quat_mul(rr, quat_conj(br))), hfwd))
+    d_vel = quat_rotate(hinv, rv - bv)
+    d_ang = quat_rotate(hinv, rw - bw)
+    loc_pos = quat_rotate(hinv, rp - root_pos[:, None, None, :])
+    loc_rot6 = quat_to_six(quat_mul(hinv, rr))
+    flat = lambda x: x.reshape(B, -1)
+    per_t = lambda *xs: torch.cat([x.reshape(B, T, -1) for x in xs], dim=-1).reshape(B, -1)
+    if version == 1:
+        return torch.cat([flat(d_pos), flat(d_rot6), flat(d_vel), flat(d_ang)], dim=-1)
+    if version == 2:
+        assert T == 1
+        return torch.cat([flat(d_pos), flat(d_rot6), flat(d_vel), flat(d_ang), flat(ref_dof_pos.view(B, -1) - dof_pos.view(B, -1))], dim=-1)
+    if version == 3:
+        return torch.cat([flat(d_pos), flat(d_rot6)], dim=-1)
+    if version == 6:
+        return per_t(d_pos, d_rot6, d_vel, d_ang, loc_pos, loc_rot6)
+    if version == 7:
+        return per_t(d_pos, d_vel, loc_pos)
+    if version == 8:
+        assert T == 1
+        loc_vel, loc_ang = quat_rotate(hinv, rv), quat_rotate(hinv, rw)
+        return torch.cat([flat(d_pos), flat(d_rot6), flat(d_vel), flat(d_ang), flat(loc_pos), flat(loc_rot6), flat(loc_vel), flat(loc_ang)], dim=-1)
+    if version == 9:
+        h1 = hinv[:, :, 0]
+        d_rv = quat_rotate(h1, rv[:, :, 0] - body_vel[:, None, 0])
+        d_rw = quat_rotate(h1, rw[:, :, 0] - body_ang_vel[:, None, 0])
+        return per_t(d_pos, d_rot6, d_rv, d_rw, loc_pos, loc_rot6)
+    raise ValueError(f"obs version {version}")
+
+
 REWARD_SPECS = {"k_pos": 100.0, "k_rot": 10.0, "k_vel": 0.1, "k_ang_vel": 0.1,
                 "w_pos": 0.5, "w_rot": 0.3, "w_vel": 0.1, "w_ang_vel": 0.1}  # humanoid_im.py:55
 

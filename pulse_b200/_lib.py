@@ -176,6 +176,27 @@ class LoaderArgs(C.Structure):
     ]
 
 
+class TaskObsArgs(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("body_env_stride", C.c_int64), ("track_ids", C.c_void_p),
+        ("num_track", C.c_int32), ("time_steps", C.c_int32), ("version", C.c_int32), ("upright", C.c_int32),
+        ("ref_pos", C.c_void_p), ("ref_rot", C.c_void_p), ("ref_vel", C.c_void_p), ("ref_ang_vel", C.c_void_p),
+        ("dof_pos", C.c_void_p), ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64), ("ref_dof_pos", C.c_void_p),
+        ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("num_envs", C.c_int64),
+    ]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [
+        ("body_pos", C.c_void_p), ("pos_env_stride", C.c_int64), ("pos_body_stride", C.c_int64),
+        ("body_pos_gt", C.c_void_p), ("gt_env_stride", C.c_int64), ("gt_body_stride", C.c_int64),
+        ("terminate", C.c_void_p), ("num_steps", C.c_void_p),
+        ("num_envs", C.c_int32), ("bound", C.c_int32), ("max_steps_all", C.c_int32), ("reserved", C.c_int32),
+        ("ctrl", C.c_void_p), ("terminate_state", C.c_void_p), ("hist", C.c_void_p), ("sums", C.c_void_p), ("counts", C.c_void_p),
+        ("mpjpe_out", C.c_void_p),
+    ]
+
+
 PEER_MAX, PEER_MAX_GRID, PEER_SIGNAL_BYTES = 8, 256, 3 * 8 * 4 + 8 * 8
 
 
@@ -262,6 +283,9 @@ SIGNATURES = {
     "pulse_reach_update_task": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                           C.c_int64, C.c_void_p]),
     "pulse_reach_step": (C.c_int, [C.POINTER(ReachStepArgs), C.c_int64, C.c_void_p]),
+    "pulse_task_obs_size": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "pulse_im_task_obs": (C.c_int, [C.POINTER(TaskObsArgs), C.c_void_p]),
+    "pulse_eval_step": (C.c_int, [C.POINTER(EvalArgs), C.c_void_p]),
     "pulse_motionlib_load_clips": (C.c_int, [C.POINTER(LoaderArgs), C.c_void_p]),
 }
 

@@ -301,6 +301,53 @@ class HumanoidImCompute:
                       env_ids=ws["env_list"][:n_list], env_count=ws["count"], flags=_lib.STEP_OBS)
         return ws
 
+    def task_obs(self, *, version: int, body_state: torch.Tensor, progress_buf: torch.Tensor, motion_ids: torch.Tensor,
+                 motion_start_times: torch.Tensor, motion_start_offset: torch.Tensor, global_offset: torch.Tensor,
+                 track_ids: torch.Tensor, obs_buf: torch.Tensor, time_steps: int = 1, sample_dt: float = 0.0, upright: bool = True,
+                 dof_pos: Optional[torch.Tensor] = None, env_ids: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """`HumanoidIm._compute_task_obs` (humanoid_im.py:708-851) for ANY observation version (1, 2, 3, 4/6, 7, 8, 9), tracked-body
+        subset and number of future samples (`_fut_tracks`: `time_steps = _num_traj_samples`, `sample_dt = _traj_sample_timestep`,
+        :723-729): the MotionLib query of the N * time_steps sample times (one `pulse_motion_state` launch) + one `pulse_im_task_obs`
+        launch writing `obs_buf[:, :size]`.  Returns the query (for the `ref_body_*` side buffers, :835-848).
+        `track_ids`: int32 device tensor (`_track_bodies_id`).  The fused step kernel remains the path of the default configuration."""
+        N = int(body_state.shape[0]) if env_ids is None else int(env_ids.shape[0])
+        if env_ids is not None:      # subset call (reset path): gather the rows, the kernel is per env
+            body_state, progress_buf, motion_ids = body_state[env_ids], progress_buf[env_ids], motion_ids[env_ids]
+            motion_start_times, motion_start_offset, global_offset = motion_start_times[env_ids], motion_start_offset[env_ids], global_offset[env_ids]
+            if dof_pos is not None:
+                dof_pos = dof_pos[env_ids]
+        T = int(time_steps)
+        size = int(self.lib.pulse_task_obs_size(int(version), int(track_ids.shape[0]), T))
+        if size <= 0:
+            raise _lib.PulseError(f"observation version {version} is not built (have 1, 2, 3, 6, 7, 8, 9)")
+        if obs_buf.shape[0] != N or obs_buf.shape[1] < size or obs_buf.stride(1) != 1 or obs_buf.dtype != torch.float32:
+            raise _lib.PulseError(f"obs_buf must be float32 [{N}, >= {size}] with unit inner stride")
+        if track_ids.dtype != torch.int32 or not track_ids.is_contiguous():
+            raise _lib.PulseError("track_ids must be a contiguous int32 device tensor")
+        if body_state.dim() != 3 or body_state.shape[1] < NUM_BODIES or body_state.shape[2] != 13 or body_state.stride(2) != 1 or body_state.stride(1) != 13:
+            raise _lib.PulseError("body_state must be a [N, B>=24, 13] view with row stride 13")
+        # motion times of the samples: (progress + 1) * dt + k * sample_dt + start + offset, the reference's operation order (:726 / :732)
+        t0 = (progress_buf + 1) * self.cfg.dt
+        if T > 1:
+            k = torch.arange(T, device=self.device) * sample_dt
+            times = (t0[:, None] + k[None, :] + motion_start_times[:, None] + motion_start_offset[:, None]).reshape(-1)
+            ids = motion_ids.repeat_interleave(T)
+            off = global_offset.repeat_interleave(T, dim=0)
+        else:
+            times, ids, off = t0 + motion_start_times + motion_start_offset, motion_ids, global_offset
+        res = self.motion_lib.get_motion_state(ids, times.to(torch.float32), offset=off.contiguous())
+        a = _lib.TaskObsArgs(body_state=body_state.data_ptr(), body_env_stride=body_state.stride(0), track_ids=track_ids.data_ptr(),
+                             num_track=int(track_ids.shape[0]), time_steps=T, version=int(version), upright=int(bool(upright)),
+                             ref_pos=res["rg_pos"].data_ptr(), ref_rot=res["rb_rot"].data_ptr(), ref_vel=res["body_vel"].data_ptr(),
+                             ref_ang_vel=res["body_ang_vel"].data_ptr(), obs=obs_buf.data_ptr(), obs_stride=obs_buf.stride(0), num_envs=N)
+        if int(version) == 2:
+            if dof_pos is None:
+                raise _lib.PulseError("observation version 2 needs dof_pos")
+            a.dof_pos, a.dof_env_stride, a.dof_elem_stride, a.ref_dof_pos = dof_pos.data_ptr(), dof_pos.stride(0), dof_pos.stride(1), res["dof_pos"].data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pulse_im_task_obs(C.byref(a), _lib.current_stream(self.device)), "pulse_im_task_obs")
+        return res
+
     def fetch_amp_obs_demo(self, num_samples: int) -> torch.Tensor:
         """HumanoidAMP.fetch_amp_obs_demo (humanoid_amp.py:215-230) with HumanoidIm's `_sample_time` = sample_time_interval."""
         ids = self.motion_lib.sample_motions(num_samples)

@@ -274,7 +274,10 @@ class PPOPolicy:
         if self._side is None:
             self._side = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         s_critic, s_disc, s_pref = self._side
-        pref_at = os.environ.get("PULSE_PREFETCH_AT", "reduce" if world_size > 1 else "start") if prefetch is not None else None
+        # where the next minibatch's input preparation is forked: under the NCCL all-reduce when there is one (it leaves most SMs idle);
+        # at the start, under the GEMMs, on one GPU and with the peer-memory optimizer kernel (which occupies every SM while it runs)
+        peer_step = self.flat.peer is not None and world_size > 1 and not keep_grads
+        pref_at = os.environ.get("PULSE_PREFETCH_AT", "reduce" if (world_size > 1 and not peer_step) else "start") if prefetch is not None else None
 
         def fork_prefetch():
             s_pref.wait_stream(main)
@@ -345,7 +348,7 @@ class PPOPolicy:
             main.wait_stream(s_disc)
         if pref_at == "reduce":
             fork_prefetch()
-        if self.flat.peer is not None and world_size > 1 and not keep_grads:
+        if peer_step:
             # one kernel per rank over NVLink peer memory: reduce-scatter of the gradients, norm clip, Adam on the rank's slice, push of
             # the new masters / bf16 operands to every rank (csrc/peer_adam.cu) -- no NCCL call on the data path
             self.flat.peer_adam_step(self.lr, max_norm=self.grad_norm)
