@@ -119,7 +119,7 @@ class AMPAgentB200Mixin:
                     if f"{sec}.{k}" in sd and k in st:
                         st[k].copy_(sd[f"{sec}.{k}"].to(st[k].device, st[k].dtype).reshape(st[k].shape))
             if isinstance(pol, PPOPolicy) and getattr(self, "optimizer", None) is not None:
-                opt_state = pol.optimizer_state()
+                opt_state = pol.optimizer_state(gather=False)   # this may run on rank 0 only (rl_games saves there): train_epoch gathered
                 for n, p in self.model.named_parameters():
                     if n in opt_state:
                         tgt = self.optimizer.state[p]
@@ -171,6 +171,8 @@ class AMPAgentB200Mixin:
             pol = self._pulse_policy()
             if isinstance(pol, PPOPolicy):
                 pol.sync_stats(torch.distributed.get_world_size())
+                pol.flat.gather_moments()     # peer-memory optimizer: the Adam moments are sharded; every rank re-assembles them here (once
+                                              # per epoch, two all-reduces) so that a rank-0-only checkpoint write needs no collective
         return info
 
     # ------------------------------------------------------------------ rollout side

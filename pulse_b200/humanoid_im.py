@@ -381,13 +381,25 @@ class HumanoidImB200Mixin:
         self._pulse.termination_distances = self._termination_distances.reshape(-1)[:NUM_BODIES].to(self.device, torch.float32).contiguous()
         self._pulse_fused_pending = False
         self._pulse_pass_time = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
-        unsupported = (getattr(self, "obs_v", 6) != 6 or getattr(self, "self_obs_v", 1) != 1 or getattr(self, "_fut_tracks", False)
-                       or getattr(self, "zero_out_far", False) or getattr(self, "_occl_training", False)
-                       or not getattr(self, "_full_body_reward", True) or len(self._track_bodies_id) != NUM_BODIES
-                       or getattr(self, "add_obs_noise", False))
+        unsupported = (getattr(self, "self_obs_v", 1) != 1 or getattr(self, "zero_out_far", False) or getattr(self, "_occl_training", False)
+                       or not getattr(self, "_full_body_reward", True) or getattr(self, "add_obs_noise", False))
+        obs_v = 6 if int(getattr(self, "obs_v", 6)) == 4 else int(getattr(self, "obs_v", 6))     # obs_v 4 and 6 share a function (:786-787)
+        fut = bool(getattr(self, "_fut_tracks", False))
+        # the fused step kernel is specialised for the default observation; every other version / tracked-body subset / fut_tracks window
+        # goes through the general task-observation kernel with the self observation still taken from the fused kernel
+        self._pulse_general_obs = obs_v != 6 or fut or len(self._track_bodies_id) != NUM_BODIES
+        if self._pulse_general_obs:
+            T = int(getattr(self, "_num_traj_samples", 1)) if fut else 1
+            size = int(self._pulse.lib.pulse_task_obs_size(obs_v, len(self._track_bodies_id), T))
+            unsupported = unsupported or size <= 0 or (T > 1 and obs_v in (2, 8)) or bool(getattr(self, "_fut_tracks_dropout", False))
+            if not unsupported:
+                self._pulse_obs_v, self._pulse_T, self._pulse_task_size = obs_v, T, size
+                self._pulse_track = self._track_bodies_id.to(self.device, torch.int32).contiguous()
+                self._pulse_scratch_obs = torch.zeros(self.num_envs, IM_OBS, device=self.device)
+                self._pulse_task_obs = torch.zeros(self.num_envs, size, device=self.device)
         if unsupported:
-            raise _lib.PulseError("HumanoidImB200Mixin covers the default HumanoidIm configuration only "
-                                  "(obs_v 6, self_obs_v 1, 24 tracked bodies, full-body reward, no fut_tracks / zero_out_far / occlusion)")
+            raise _lib.PulseError("HumanoidImB200Mixin: unsupported task configuration (needs self_obs_v 1, full-body reward, no zero_out_far / "
+                                  "occlusion / observation noise / fut_tracks dropout; obs_v in 1, 2, 3, 4, 6, 7, 8, 9; v2 / v8 without fut_tracks)")
         self._pulse_ready = True
 
     def resample_motions(self):
@@ -414,9 +426,41 @@ class HumanoidImB200Mixin:
         args = self._pulse_args()
         if self.cycle_motion:
             self._pulse.step(flags=_lib.STEP_REWARD, **args)
+        elif self._pulse_general_obs:      # reward + reset fused; the observation takes the general path in _compute_observations
+            self._pulse.step(flags=_lib.STEP_REWARD | _lib.STEP_RESET, **self._pulse_no_obs(args))
+            self._pulse_fused_pending = True
         else:
             self._pulse.step(flags=_lib.STEP_ALL, **args)
             self._pulse_fused_pending = True
+
+    @staticmethod
+    def _pulse_no_obs(args):
+        return {k: v for k, v in args.items() if k not in ("obs_buf", "self_obs_buf", "ref_body_pos", "ref_body_vel", "ref_body_rot", "ref_dof_pos")}
+
+    def _compute_task_obs(self, env_ids=None, save_buffer=True):
+        """humanoid_im.py:708-851 for the non-default observation configurations: MotionLib query of the sample times + one
+        pulse_im_task_obs launch; returns the [n, task_obs_size] block the reference's _compute_observations concatenates."""
+        if not self._pulse_ready:
+            self._pulse_setup()
+        if not self._pulse_general_obs:
+            return super()._compute_task_obs(env_ids, save_buffer)
+        n = self.num_envs if env_ids is None else len(env_ids)
+        out = self._pulse_task_obs[:n]
+        ids = None if env_ids is None else env_ids.to(torch.int64).contiguous()
+        res = self._pulse.task_obs(version=self._pulse_obs_v, body_state=self._rigid_body_state_reshaped, progress_buf=self.progress_buf,
+                                   motion_ids=self._sampled_motion_ids, motion_start_times=self._motion_start_times,
+                                   motion_start_offset=self._motion_start_times_offset, global_offset=self._global_offset,
+                                   track_ids=self._pulse_track, obs_buf=out, time_steps=self._pulse_T,
+                                   sample_dt=float(getattr(self, "_traj_sample_timestep", 0.0)), upright=bool(getattr(self, "_has_upright_start", True)),
+                                   dof_pos=self._dof_pos, env_ids=ids)
+        if save_buffer:                    # :835-848 (sample 0 of a fut_tracks window)
+            sel = slice(None) if env_ids is None else env_ids
+            first = lambda x: x.view(n, self._pulse_T, *x.shape[1:])[:, 0]
+            self.ref_body_pos[sel], self.ref_body_vel[sel] = first(res["rg_pos"]), first(res["body_vel"])
+            self.ref_body_rot[sel], self.ref_dof_pos[sel] = first(res["rb_rot"]), first(res["dof_pos"])
+            if hasattr(self, "ref_body_pos_subset"):
+                self.ref_body_pos_subset[sel] = first(res["rg_pos"])[:, self._track_bodies_id]
+        return out
 
     def _compute_reset(self):
         if self._pulse_fused_pending:
@@ -434,6 +478,22 @@ class HumanoidImB200Mixin:
         self._pulse_fused_pending = True
 
     def _compute_observations(self, env_ids=None):
+        if getattr(self, "_pulse_general_obs", False) or not self._pulse_ready:
+            args = self._pulse_args()
+            if self._pulse_general_obs:
+                # humanoid_im.py:677-706: obs = [self obs (fused kernel, observation mode, into a scratch row) | task obs (general kernel)]
+                self._pulse_fused_pending = False
+                if env_ids is not None and len(env_ids) == 0:
+                    return
+                a = self._pulse_no_obs(args)
+                if env_ids is not None:
+                    a["env_ids"] = env_ids.to(torch.int64).contiguous()
+                self._pulse.step(flags=_lib.STEP_OBS, obs_buf=self._pulse_scratch_obs, self_obs_buf=self.self_obs_buf, **a)
+                task = self._compute_task_obs(env_ids)
+                sel = slice(None) if env_ids is None else env_ids
+                self.obs_buf[sel, :SELF_OBS] = self.self_obs_buf[sel]
+                self.obs_buf[sel, SELF_OBS:SELF_OBS + task.shape[1]] = task
+                return
         if env_ids is None and self._pulse_fused_pending:
             self._pulse_fused_pending = False
             return

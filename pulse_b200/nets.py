@@ -126,7 +126,10 @@ class FlatParams:
             a.grads[p], a.params[p], a.params_bf16[p], a.signals[p] = int(hg.buffer_ptrs[p]), int(hp.buffer_ptrs[p]), int(hb.buffer_ptrs[p]), int(hs.buffer_ptrs[p])
         if int(a.grads[rank]) != grads.data_ptr() or int(a.params[rank]) != params.data_ptr():
             raise RuntimeError("symmetric-memory handle does not describe the local tensors")
-        use_mc = os.environ.get("PULSE_PEER_MC", "0") == "1"
+        # multimem (NVLS) variant: measured 107 vs 112 us per step at 8 GPUs but 112 vs 75 us at 2 (profiles/r02_peer_adam_probe_n*.json):
+        # the switch-side reduction pays once the peer count makes the pull / push fan-out the bound
+        mc_env = os.environ.get("PULSE_PEER_MC", "auto")
+        use_mc = mc_env == "1" or (mc_env == "auto" and world >= 8)
         mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (hg, hp, hb)]
         if use_mc and all(mc):
             a.mc_grads, a.mc_params, a.mc_params_bf16 = mc

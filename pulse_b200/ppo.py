@@ -410,10 +410,12 @@ class PPOPolicy:
                     rms.count.copy_(torch.as_tensor(sd[f"{sec}.count"]).to(self.device).double().reshape(()))
                 rms._refresh()
 
-    def optimizer_state(self) -> Dict[str, Dict[str, torch.Tensor]]:
+    def optimizer_state(self, gather: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
         """torch.optim.Adam state per reference parameter name: {'exp_avg', 'exp_avg_sq'} in the parameter's shape, plus 'step'."""
         out = {}
-        self.flat.gather_moments()      # peer mode keeps the moments sharded over the ranks (collective; no-op otherwise)
+        if gather:
+            self.flat.gather_moments()  # peer mode keeps the moments sharded over the ranks (COLLECTIVE; no-op otherwise).  A caller that runs on
+                                        # one rank only (rank-0 checkpointing) gathers at a point every rank reaches and passes gather=False
         step = self.flat.step.clone().float().reshape(())
         for name, l in self._named_layers():
             m, v = self.flat.view(l.w_idx, "exp_avg"), self.flat.view(l.w_idx, "exp_avg_sq")

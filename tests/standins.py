@@ -17,12 +17,13 @@ CONTRACT = {
                                          "_motion_start_times_offset", "_global_offset", "_cycle_counter", "reward_specs", "power_reward",
                                          "power_coefficient", "_reset_bodies_id", "_termination_distances", "ref_body_pos", "ref_body_vel",
                                          "ref_body_rot", "ref_dof_pos", "reward_raw", "obs_v", "_fut_tracks", "zero_out_far", "_occl_training",
-                                         "_full_body_reward", "_track_bodies_id", "cycle_motion", "resample_motions", "_sample_time"],
+                                         "_full_body_reward", "_track_bodies_id", "cycle_motion", "resample_motions", "_sample_time", "_compute_task_obs",
+                                         "_num_traj_samples", "_traj_sample_timestep", "_fut_tracks_dropout", "ref_body_pos_subset"],
         "phc/env/tasks/humanoid.py": ["_rigid_body_state_reshaped", "_dof_vel", "_dof_pos", "dof_force_tensor", "progress_buf", "obs_buf",
                                       "self_obs_buf", "rew_buf", "reset_buf", "_terminate_buf", "max_episode_length", "_enable_early_termination",
                                       "self_obs_v", "_humanoid_root_states", "post_physics_step", "_has_dof_subset", "_reset_envs",
                                       "_reset_env_tensors", "_rigid_body_pos", "_rigid_body_rot", "_rigid_body_vel", "_rigid_body_ang_vel",
-                                      "_contact_forces", "_humanoid_actor_ids"],
+                                      "_contact_forces", "_humanoid_actor_ids", "_has_upright_start"],
         "phc/env/tasks/humanoid_amp.py": ["_update_hist_amp_obs", "_compute_amp_observations", "_amp_obs_buf", "_num_amp_obs_steps", "_motion_lib",
                                           "amp_obs_v", "_state_init", "_reset_default_env_ids", "_reset_ref_env_ids", "_reset_ref_motion_ids",
                                           "_reset_ref_motion_times", "_state_reset_happened", "_reset_rb_pos", "_reset_rb_rot", "_reset_rb_vel",

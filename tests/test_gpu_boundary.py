@@ -67,6 +67,51 @@ def test_task_mixin_post_physics_step_matches_oracle(getup):
         torch.testing.assert_close(task.obs_buf, before, atol=1e-6, rtol=0)
 
 
+@pytest.mark.parametrize("obs_v,track,fut", [(7, [13, 18, 23], True), (9, [0, 4, 8, 13, 18, 23], False), (3, list(range(24)), True)])
+def test_task_mixin_general_observation_configurations(obs_v, track, fut):
+    """SURVEY 8f-4 through the drop-in layer: a task configured with another observation version / a tracked-body subset / a fut_tracks
+    window (env_pulse_im.yaml-style 3-point tracking, humanoid_im.py:708-851) -- reward and reset still come from the fused kernel, the
+    observation is [self obs | general task-observation kernel]."""
+    from oracle import pulse_oracle as po
+    from pulse_b200.humanoid_im import HumanoidImB200Mixin
+
+    class HumanoidImB200(HumanoidImB200Mixin, StandInHumanoidIm):
+        pass
+
+    n = 389
+    tb = exact_tables(41, seed=8)
+    z, _ = exact_step_inputs(tb, n, seed=9)
+    task = HumanoidImB200(_mlib(tb), z, DEV)
+    task.obs_v, task._track_bodies_id, task._fut_tracks = obs_v, torch.tensor(track, device=DEV), fut
+    task._num_traj_samples, task._traj_sample_timestep, task._has_upright_start = 3, 0.5, True
+    task.post_physics_step = lambda: (task.progress_buf.add_(1), task._compute_reward(None), task._compute_reset(), task._compute_observations())
+    task.post_physics_step()
+    torch.cuda.synchronize()
+    ref = po.humanoid_im_step(tb, po.ImStepConfig(), z["body_state"], z["dof_vel"], z["dof_force"], z["progress_buf"], z["motion_ids"], z["start_times"],
+                              z["start_offset"], z["global_offset"], z["cycle_counter"], z["reset_buf_in"])
+    assert torch.equal(task.reset_buf.cpu(), ref["reset_buf"]) and torch.equal(task._terminate_buf.cpu(), ref["terminate_buf"])
+    torch.testing.assert_close(task.rew_buf.cpu(), ref["rew_buf"], atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.obs_buf[:, :358].cpu(), ref["obs_buf"][:, :358], atol=1e-4, rtol=0)
+    T = 3 if fut else 1
+    dt = po.STEP_DT
+    t0 = (z["progress_buf"] + 1) * dt
+    times = (t0[:, None] + (torch.arange(T) * 0.5)[None, :] + z["start_times"][:, None] + z["start_offset"][:, None]).reshape(-1) if T > 1 \
+        else t0 + z["start_times"] + z["start_offset"]
+    q = po.motion_state(tb, z["motion_ids"].repeat_interleave(T), times.float(), z["global_offset"].repeat_interleave(T, dim=0))
+    bs, tr = z["body_state"], torch.tensor(track)
+    want = po.imitation_obs(obs_v, bs[:, 0, 0:3], bs[:, 0, 3:7], bs[:, tr, 0:3], bs[:, tr, 3:7], bs[:, tr, 7:10], bs[:, tr, 10:13],
+                            q["rg_pos"][:, tr], q["rb_rot"][:, tr], q["body_vel"][:, tr], q["body_ang_vel"][:, tr], T, True)
+    torch.testing.assert_close(task.obs_buf[:, 358:358 + want.shape[1]].cpu(), want, atol=1e-4, rtol=0)
+    torch.testing.assert_close(task.ref_body_pos.cpu(), q["rg_pos"].view(n, T, 24, 3)[:, 0], atol=1e-5, rtol=0)
+    # reset-time observation of a subset through the same override
+    ids = torch.tensor([3, 77, 388], device=DEV)
+    before = task.obs_buf.clone()
+    task.obs_buf[ids] = -7.0
+    task._compute_observations(ids)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(task.obs_buf[:, :358 + want.shape[1]], before[:, :358 + want.shape[1]], atol=1e-6, rtol=0)
+
+
 def test_task_mixin_reset_envs_matches_oracle():
     """`_reset_envs(env_ids)` through the mixin (one fused launch + the reference's own gym setters / refresh / observation call) against
     the oracle's restatement of the reference's reset chain, with the start-time draws taken from torch's generator exactly as
