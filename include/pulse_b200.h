@@ -610,6 +610,39 @@ typedef struct {
 int pulse_reach_step(const pulse_reach_step_args_t* args, int64_t num_envs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Post-physics step of the downstream latent-space tasks HumanoidSpeedZ / HumanoidStrikeZ, siblings of pulse_reach_step:
+ * self observation (humanoid.py:1675-1731) + task observation + reward + reset in one launch.
+ *   PULSE_ZTASK_SPEED   compute_speed_observations / compute_speed_reward (phc/env/tasks/humanoid_speed.py:310-343), power term
+ *                       (:215-222; dof_force NULL = off), compute_humanoid_reset (humanoid.py:1573-1608).  obs 358 + 3.
+ *   PULSE_ZTASK_STRIKE  compute_strike_observations / compute_strike_reward (humanoid_strike.py:270-328), the strike variant of
+ *                       compute_humanoid_reset (:330-375).  obs 358 + 15.
+ * prev_root_pos [N,3] = root position before the physics step (pre_physics_step, humanoid_speed.py:73-76).  Not covered: the
+ * power_usage_reward terms (:224-240, humanoid_strike.py:186-198), the input-noise suffix (humanoid_speed.py:194-195).
+ * ---------------------------------------------------------------------------------------------- */
+#define PULSE_ZTASK_SPEED 1
+#define PULSE_ZTASK_STRIKE 2
+#define PULSE_SPEED_OBS 361
+#define PULSE_STRIKE_OBS 373
+typedef struct {
+  int32_t kind, enable_early_termination;
+  const float* body_state; int64_t body_env_stride;
+  const float* contact_forces; int64_t contact_env_stride;      /* [N, B, 3] view or NULL */
+  const float* termination_heights;                              /* [24] */
+  uint32_t contact_body_mask;                                    /* bodies allowed to touch the ground (_contact_body_ids) */
+  uint32_t strike_body_mask;                                     /* strike: bodies allowed to hit the target (_strike_body_ids) */
+  const int64_t* progress_buf; int64_t max_episode_length;
+  const float* prev_root_pos; float dt; float power_coefficient;
+  const float* tar_speed;                                        /* speed: [N] */
+  const float* target_states; int64_t target_env_stride;         /* strike: [N, 13] view of the target actor's root state */
+  const float* tar_contact_forces; int64_t tar_contact_env_stride;   /* strike: [N, 3] view */
+  const float* dof_force; int64_t dof_force_stride;              /* speed power term: [N, 69] */
+  const float* dof_vel; int64_t dof_env_stride, dof_elem_stride;
+  float* obs_buf; int64_t obs_stride; float* rew_buf; float* reward_raw; int64_t raw_stride;
+  int64_t* reset_buf; int64_t* terminate_buf;
+} pulse_ztask_step_args_t;
+int pulse_ztask_step(const pulse_ztask_step_args_t* args, int64_t num_envs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Task observation for every observation version / tracked-body subset / number of future samples: replaces the
  * dispatch of HumanoidIm._compute_task_obs (phc/env/tasks/humanoid_im.py:757-833) over compute_imitation_observations (:1222-1258,
  * obs_v 1), _v2 (:1261-1301), _v3 (:1304-1326), _v6 (:1328-1378, obs_v 4 / 6), _v7 (:1381-1413), _v8 (:1415-1479, time_steps 1) and

@@ -890,6 +890,74 @@ def humanoid_reset(progress_buf, contact_buf, contact_body_ids, rigid_body_pos, 
     return reset, terminated
 
 
+def speed_obs(root_states: torch.Tensor, tar_speed: torch.Tensor) -> torch.Tensor:
+    """compute_speed_observations (humanoid_speed.py:310-325): heading-frame x axis (2) + target speed."""
+    x = torch.zeros_like(root_states[:, 0:3])
+    x[:, 0] = 1
+    d = quat_rotate(heading_quat(root_states[:, 3:7], inverse=True), x)
+    return torch.cat([d[:, 0:2], tar_speed[:, None]], dim=-1)
+
+
+def speed_reward(root_pos, prev_root_pos, tar_speed, dt: float) -> torch.Tensor:
+    """compute_speed_reward (humanoid_speed.py:327-343)."""
+    v = (root_pos - prev_root_pos) / dt
+    err = tar_speed - v[:, 0]
+    return torch.exp(-0.25 * (err * err + 0.1 * v[:, 1] * v[:, 1]))
+
+
+def power_reward(dof_force, dof_vel, progress_buf, coefficient: float) -> torch.Tensor:
+    """humanoid_speed.py:215-222 (same expression as humanoid_im.py:910-917)."""
+    p = -coefficient * torch.abs(dof_force * dof_vel).sum(dim=-1)
+    p[progress_buf <= 3] = 0
+    return p
+
+
+def strike_obs(root_states: torch.Tensor, tar_states: torch.Tensor) -> torch.Tensor:
+    """compute_strike_observations (humanoid_strike.py:270-293)."""
+    hinv = heading_quat(root_states[:, 3:7], inverse=True)
+    lp = tar_states[:, 0:3] - root_states[:, 0:3]
+    lp[:, 2] = tar_states[:, 2]
+    return torch.cat([quat_rotate(hinv, lp), quat_to_six(quat_mul(hinv, tar_states[:, 3:7])), quat_rotate(hinv, tar_states[:, 7:10]),
+                      quat_rotate(hinv, tar_states[:, 10:13])], dim=-1)
+
+
+def strike_reward(tar_pos, tar_rot, root_pos, prev_root_pos, dt: float) -> torch.Tensor:
+    """compute_strike_reward (humanoid_strike.py:295-328)."""
+    up = torch.zeros_like(tar_pos)
+    up[:, 2] = 1
+    rot_err = torch.sum(up * quat_rotate(tar_rot, up), dim=-1)
+    rot_r = torch.clamp_min(1.0 - rot_err, 0.0)
+    d = torch.nn.functional.normalize(tar_pos[:, 0:2] - root_pos[:, 0:2], dim=-1)
+    v = (root_pos - prev_root_pos) / dt
+    dir_speed = torch.sum(d * v[:, :2], dim=-1)
+    verr = torch.clamp_min(1.0 - dir_speed, 0.0)
+    vel_r = torch.exp(-4.0 * verr * verr)
+    vel_r[dir_speed <= 0] = 0
+    r = 0.6 * rot_r + 0.4 * vel_r
+    return torch.where(rot_err < 0.2, torch.ones_like(r), r)
+
+
+def strike_reset(progress_buf, contact_buf, contact_body_ids, rigid_body_pos, tar_contact_forces, strike_body_ids, max_episode_length: int,
+                 enable_early_termination: bool, termination_heights) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The strike task's compute_humanoid_reset (humanoid_strike.py:330-375): fall as in humanoid_reset, OR the target pushed with more
+    than 50 N (x / y) while a body that is neither a ground-contact nor a strike body carries more than 50 N."""
+    terminated = torch.zeros_like(progress_buf)
+    if enable_early_termination:
+        masked = contact_buf.clone()
+        masked[:, contact_body_ids, :] = 0
+        fall_contact = torch.any(torch.any(torch.abs(masked) > 0.1, dim=-1), dim=-1)
+        fall_height = rigid_body_pos[..., 2] < termination_heights
+        fall_height[:, contact_body_ids] = False
+        has_fallen = fall_contact & torch.any(fall_height, dim=-1)
+        tar_contact = torch.any(torch.abs(tar_contact_forces[..., 0:2]) > 50.0, dim=-1)
+        masked[:, strike_body_ids, :] = 0
+        nonstrike = torch.any(torch.any(torch.abs(masked) > 50.0, dim=-1), dim=-1)
+        failed = (has_fallen | (tar_contact & nonstrike)) & (progress_buf > 1)
+        terminated = torch.where(failed, torch.ones_like(progress_buf), terminated)
+    reset = torch.where(progress_buf >= max_episode_length - 1, torch.ones_like(progress_buf), terminated)
+    return reset, terminated
+
+
 # ------------------------------------------------------------------------------------------------
 # MotionLib loader (SURVEY 8f-1): what `load_motions` computes per clip before concatenating the tables
 # ------------------------------------------------------------------------------------------------

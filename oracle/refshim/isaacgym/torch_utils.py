@@ -81,3 +81,15 @@ def quat_from_euler_xyz(roll, pitch, yaw):
     qy = cy * cr * sp + sy * sr * cp
     qz = sy * cr * cp - cy * sr * sp
     return torch.stack([qx, qy, qz, qw], dim=-1)
+
+
+@torch.jit.script
+def quat_rotate(q, v):
+    """isaacgym.torch_utils.quat_rotate [3P-memory]: v (2 w^2 - 1) + 2 w (q_vec x v) + 2 q_vec (q_vec . v); used by the strike task."""
+    shape = q.shape
+    q_w = q[:, -1]
+    q_vec = q[:, :3]
+    a = v * (2.0 * q_w ** 2 - 1.0).unsqueeze(-1)
+    b = torch.cross(q_vec, v, dim=-1) * q_w.unsqueeze(-1) * 2.0
+    c = q_vec * torch.bmm(q_vec.view(shape[0], 1, 3), v.view(shape[0], 3, 1)).squeeze(-1) * 2.0
+    return a + b + c

@@ -176,6 +176,22 @@ class LoaderArgs(C.Structure):
     ]
 
 
+class ZTaskStepArgs(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("enable_early_termination", C.c_int32), ("body_state", C.c_void_p), ("body_env_stride", C.c_int64),
+        ("contact_forces", C.c_void_p), ("contact_env_stride", C.c_int64), ("termination_heights", C.c_void_p),
+        ("contact_body_mask", C.c_uint32), ("strike_body_mask", C.c_uint32), ("progress_buf", C.c_void_p), ("max_episode_length", C.c_int64),
+        ("prev_root_pos", C.c_void_p), ("dt", C.c_float), ("power_coefficient", C.c_float), ("tar_speed", C.c_void_p),
+        ("target_states", C.c_void_p), ("target_env_stride", C.c_int64), ("tar_contact_forces", C.c_void_p), ("tar_contact_env_stride", C.c_int64),
+        ("dof_force", C.c_void_p), ("dof_force_stride", C.c_int64), ("dof_vel", C.c_void_p), ("dof_env_stride", C.c_int64), ("dof_elem_stride", C.c_int64),
+        ("obs_buf", C.c_void_p), ("obs_stride", C.c_int64), ("rew_buf", C.c_void_p), ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64),
+        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+    ]
+
+
+ZTASK_SPEED, ZTASK_STRIKE = 1, 2
+
+
 class TaskObsArgs(C.Structure):
     _fields_ = [
         ("body_state", C.c_void_p), ("body_env_stride", C.c_int64), ("track_ids", C.c_void_p),
@@ -283,6 +299,7 @@ SIGNATURES = {
     "pulse_reach_update_task": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                           C.c_int64, C.c_void_p]),
     "pulse_reach_step": (C.c_int, [C.POINTER(ReachStepArgs), C.c_int64, C.c_void_p]),
+    "pulse_ztask_step": (C.c_int, [C.POINTER(ZTaskStepArgs), C.c_int64, C.c_void_p]),
     "pulse_task_obs_size": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "pulse_im_task_obs": (C.c_int, [C.POINTER(TaskObsArgs), C.c_void_p]),
     "pulse_eval_step": (C.c_int, [C.POINTER(EvalArgs), C.c_void_p]),

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(lib):
     import subprocess
     import tempfile
     from pulse_b200 import _lib
-    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t), sizeof(pulse_reset_args_t), sizeof(pulse_policy_post_args_t), sizeof(pulse_amp_row_args_t), sizeof(pulse_peer_adam_args_t), sizeof(pulse_eval_args_t), sizeof(pulse_task_obs_args_t));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pulse_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pulse_motionlib_desc_t), sizeof(pulse_motion_query_t), sizeof(pulse_im_step_args_t), sizeof(pulse_amp_obs_args_t), sizeof(pulse_gae_args_t), sizeof(pulse_gemm_epilogue_t), sizeof(pulse_ppo_loss_args_t), sizeof(pulse_vae_latent_args_t), sizeof(pulse_reach_step_args_t), sizeof(pulse_loader_args_t), sizeof(pulse_gemm_problem_t), sizeof(pulse_reset_args_t), sizeof(pulse_policy_post_args_t), sizeof(pulse_amp_row_args_t), sizeof(pulse_peer_adam_args_t), sizeof(pulse_eval_args_t), sizeof(pulse_task_obs_args_t), sizeof(pulse_ztask_step_args_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
@@ -46,7 +46,7 @@ def test_struct_sizes_match_header(lib):
     assert sizes == [C.sizeof(_lib.MotionLibDesc), C.sizeof(_lib.MotionQuery), C.sizeof(_lib.ImStepArgs), C.sizeof(_lib.AmpObsArgs),
                      C.sizeof(_lib.GaeArgs), C.sizeof(_lib.GemmEpilogue), C.sizeof(_lib.PpoLossArgs), C.sizeof(_lib.VaeLatentArgs),
                      C.sizeof(_lib.ReachStepArgs), C.sizeof(_lib.LoaderArgs), C.sizeof(_lib.GemmProblem), C.sizeof(_lib.ResetArgs), C.sizeof(_lib.PolicyPostArgs),
-                     C.sizeof(_lib.AmpRowArgs), C.sizeof(_lib.PeerAdamArgs), C.sizeof(_lib.EvalArgs), C.sizeof(_lib.TaskObsArgs)]
+                     C.sizeof(_lib.AmpRowArgs), C.sizeof(_lib.PeerAdamArgs), C.sizeof(_lib.EvalArgs), C.sizeof(_lib.TaskObsArgs), C.sizeof(_lib.ZTaskStepArgs)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -60,6 +60,8 @@ def test_argument_validation_without_gpu(lib):
     assert [lib.pulse_task_obs_size(v, 24, 1) for v in (1, 2, 3, 6, 7, 8, 9, 4)] == [360, 429, 216, 576, 216, 720, 438, -1]
     ta.version, ta.time_steps, ta.num_envs = 8, 3, 4
     assert lib.pulse_im_task_obs(C.byref(ta), None) == -1 and b"time_steps = 1" in lib.pulse_last_error()
+    za = _lib.ZTaskStepArgs(kind=7)
+    assert lib.pulse_ztask_step(C.byref(za), 4, None) == -1 and b"unknown task kind" in lib.pulse_last_error()
     ea = _lib.EvalArgs()
     assert lib.pulse_eval_step(C.byref(ea), None) == -1 and b"num_envs" in lib.pulse_last_error()
     pa = _lib.PeerAdamArgs()

@@ -67,7 +67,7 @@ def test_task_mixin_post_physics_step_matches_oracle(getup):
         torch.testing.assert_close(task.obs_buf, before, atol=1e-6, rtol=0)
 
 
-@pytest.mark.parametrize("obs_v,track,fut", [(7, [13, 18, 23], True), (9, [0, 4, 8, 13, 18, 23], False), (3, list(range(24)), True)])
+@pytest.mark.parametrize("obs_v,track,fut", [(7, [13, 18, 23], True), (9, [0, 4, 8, 13, 18, 23], False), (1, [0, 4, 8, 13, 18, 23], True), (3, list(range(24)), False)])
 def test_task_mixin_general_observation_configurations(obs_v, track, fut):
     """SURVEY 8f-4 through the drop-in layer: a task configured with another observation version / a tracked-body subset / a fut_tracks
     window (env_pulse_im.yaml-style 3-point tracking, humanoid_im.py:708-851) -- reward and reset still come from the fused kernel, the
