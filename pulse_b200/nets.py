@@ -333,8 +333,8 @@ class MLP:
         for l in self.layers:
             l.refresh()
 
-    def _workspace(self, M: int, train: bool):
-        key = (M, train)
+    def _workspace(self, M: int, train: bool, slot: int = 0):
+        key = (M, train) if slot == 0 else (M, train, slot)      # slot > 0: a second evaluation workspace for a concurrent forward pass
         if key not in self._ws:
             dev = self.flat.device
             bf = lambda r, c: torch.zeros(r, c, device=dev, dtype=torch.bfloat16)
@@ -398,11 +398,11 @@ class MLP:
         return dy[:, :l.N], w, kw
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, train: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, train: bool = False, out: Optional[torch.Tensor] = None, slot: int = 0) -> torch.Tensor:
         """x: bf16 [M, Kp0] (normalised, zero padded; column `in_features` = 1.0 for augmented nets).  Returns fp32 [M, head] (view of a
         reused workspace buffer, or `out`).  With train=True the activations / ReLU masks / SiLU pre-activations backward() needs are kept."""
         M = x.shape[0]
-        ws = self._workspace(M, train)
+        ws = self._workspace(M, train, slot)
         if out is not None:
             ws = dict(ws, out=out)
         h = x

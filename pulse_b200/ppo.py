@@ -190,12 +190,22 @@ class PPOPolicy:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_policy_post(C.byref(a), M, _lib.current_stream(self.device)), "pulse_policy_post")
 
-    def critic_values_into(self, obs: torch.Tensor, out: torch.Tensor, terminate: Optional[torch.Tensor] = None) -> None:
-        """`next_vals = self._eval_critic(self.obs); next_vals *= (1.0 - terminated)` (amp_agent.py:396-398) into `out` ([M] / [M,1] view)."""
+    def critic_values_into(self, obs: torch.Tensor, out: torch.Tensor, terminate: Optional[torch.Tensor] = None, slot: int = 0,
+                           after_normalize=None) -> None:
+        """`next_vals = self._eval_critic(self.obs); next_vals *= (1.0 - terminated)` (amp_agent.py:396-398) into `out` ([M] / [M,1] view).
+        `slot` 1: a second operand buffer / critic workspace, so that this evaluation may run on another stream beside `act_into`;
+        `after_normalize()` is called once `obs` has been read (the caller records an event there: `obs` may be overwritten after it)."""
         M = obs.shape[0]
         b = self._buf(M, False)
-        self.obs_rms.normalize_into(obs, b["x"])
-        value = self.critic.forward(b["x"])
+        x = b["x"]
+        if slot:
+            if "x_next" not in b:
+                b["x_next"] = torch.zeros_like(b["x"])
+            x = b["x_next"]
+        self.obs_rms.normalize_into(obs, x)
+        if after_normalize is not None:
+            after_normalize()
+        value = self.critic.forward(x, slot=slot)
         rms = self.value_rms
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pulse_value_post(value.data_ptr(), value.stride(0), rms.running_mean.data_ptr() if rms is not None else None,

@@ -84,7 +84,9 @@ class PlayStepsB200:
         # next-value critic, the critic beside the actor.  At 2048 envs per rank (8 GPUs) every kernel of the step is latency-bound
         # (7-17 us each, profiles/r02_rollout_step_2048envs_launches.txt), so the step time is the length of the dependency chain.
         self.fork = os.environ.get("PULSE_ROLLOUT_FORK", "1") != "0"
+        self.overlap = os.environ.get("PULSE_ROLLOUT_OVERLAP", "1") != "0"   # next values of step t beside reset / actor of step t+1 (_whole_overlapped)
         self._side = None
+        self._side_b = None
 
     # ------------------------------------------------------------------ the pieces of one step
     def _step_kw(self):
@@ -172,7 +174,59 @@ class PlayStepsB200:
             self._graphs[key] = g
         g.replay()
 
+    def _whole_overlapped(self) -> None:
+        """The horizon with the independent pieces of consecutive steps overlapped on three streams (single-graph mode, no host I/O):
+             main    reset(t) -> obs of the reset envs -> normalise -> actor -> policy_post -> fused step kernel(t)
+             side A  critic(obs t) beside the actor;  AMP row(t) beside the step kernel
+             side B  next values of step t (normalise -> critic -> value_post) beside reset(t+1) / actor(t+1)
+           Hazards, all expressed as stream dependencies inside the captured graph: reset(t+1) rewrites the body state and the AMP
+           `fresh` flags the AMP row(t) reads (main waits for A); the observation of the reset envs overwrites rows of obses[:, t+1]
+           that B's normalise reads (main waits for the event B records after it); the step kernel(t+1) rewrites `terminate_buf` that
+           B's value_post reads (main waits for B).  The reset does not clear `terminate_buf` here (the step kernel rewrites it for
+           every env each step; nothing else reads it in between).  At 2048 envs per rank the step is a chain of latency-bound
+           launches: 142 -> ~110 us per step."""
+        s, pol, T = self.sim, self.policy, self.T
+        main = torch.cuda.current_stream(self.dev)
+        A = self._side_stream()
+        if self._side_b is None:
+            self._side_b = torch.cuda.Stream(self.dev)
+        B = self._side_b
+        norm_done = None
+        for t in range(T):
+            if t > 0:
+                main.wait_stream(A)                                  # AMP row(t-1) has read the pre-reset state
+            ws = self.comp.reset_envs(motion_ids=s["motion_ids"], motion_start_times=s["motion_start_times"], motion_start_offset=s["motion_start_offset"],
+                                      global_offset=s["global_offset"], progress_buf=s["progress_buf"], root_states=s["root_states"], dof_pos=s["dof_pos"],
+                                      dof_vel=s["dof_vel"], rigid_body_state=s["body_state"], reset_buf=self.reset_buf, terminate_buf=None,
+                                      cycle_counter=s.get("cycle_counter"), contact_forces=s.get("contact_forces"), amp_obs_buf=self.amp_init,
+                                      actor_ids=s.get("actor_ids"), seed=self.reset_seed, offset=t, offset_dev=pol.rng_offset, obs_buf=None,
+                                      amp_fresh=self.amp_fresh)
+            if norm_done is not None:
+                main.wait_event(norm_done)                           # B has read obses[:, t]
+            self.comp.step(body_state=s["body_state"], progress_buf=s["progress_buf"], motion_ids=s["motion_ids"],
+                           motion_start_times=s["motion_start_times"], motion_start_offset=s["motion_start_offset"], global_offset=s["global_offset"],
+                           obs_buf=self.obses[:, t], env_ids=ws["env_list"][:self.n], env_count=ws["count"], flags=_lib.STEP_OBS)
+            pol.act_into(self.obses[:, t], actions=self.actions[:, t], neglogp=self.neglogp[:, t], mus=self.mus[:, t], values=self.values[t],
+                         pd=(self.pd[0], self.pd[1], self.pd_tar), rng_step=t, side=A)
+            A.wait_stream(main)
+            with torch.cuda.stream(A):
+                prev = self.amp_obs[:, t - 1] if t > 0 else self.amp_obs[:, T - 1]
+                self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
+                                      fresh=self.amp_fresh, fresh_rows=self.amp_init)
+            if t > 0:
+                main.wait_stream(B)                                  # value_post(t-1) has read terminate_buf
+            self._env_step(t)
+            B.wait_stream(main)
+            with torch.cuda.stream(B):
+                norm_done = torch.cuda.Event()
+                self.policy.critic_values_into(self._next_obs(t), self.next_values[t].view(-1), terminate=self.terminate_buf, slot=1,
+                                               after_normalize=lambda ev=norm_done: ev.record(B))
+        main.wait_stream(A)
+        main.wait_stream(B)
+
     def _whole(self) -> None:
+        if self.fork and self.overlap and self.host_io is None and self.physics is None:
+            return self._whole_overlapped()
         for t in range(self.T):
             self._segment(t)
             if self.physics is not None:

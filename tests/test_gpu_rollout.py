@@ -168,3 +168,29 @@ def test_play_steps_graph_replay_equals_eager_and_last_step_matches_oracle(singl
     torch.testing.assert_close(ps.next_values[T - 1], nv, atol=1e-5, rtol=1e-5)     # on the PRE-reset observation
     # envs reset before step t start it with progress 1 after the step's own increment
     assert bool((sim["progress_buf"] >= 1).all())
+
+
+def test_overlapped_schedule_equals_the_sequential_one():
+    """_whole_overlapped (next values of step t beside reset / actor of step t+1, AMP row beside the step kernel; three streams inside one
+    graph) produces bit for bit the experience of the sequential schedule, eagerly and replayed, over several iterations."""
+    from pulse_b200.rollout import PlayStepsB200
+    n, T = 1024, 8
+    runs = {}
+    for overlap, graphs in ((False, True), (True, False), (True, True)):
+        tb, comp, sim = _sim(n, clips=64)
+        pol = _policy(with_disc=True)
+        ps = PlayStepsB200(comp, pol, sim, horizon=T, use_graphs=graphs, single_graph=True, reset_seed=9)
+        ps.overlap = overlap
+        ps.first_observation()
+        for it in range(4):
+            ps.play_steps()
+            ps.finish()
+        torch.cuda.synchronize()
+        runs[(overlap, graphs)] = (ps, sim)
+    ref, ref_sim = runs[(False, True)]
+    for key in ((True, False), (True, True)):
+        ps, sim = runs[key]
+        for name in ("obses", "actions", "mus", "neglogp", "amp_obs", "values", "next_values", "rewards", "dones", "obs_carry", "adv", "ret"):
+            assert torch.equal(getattr(ref, name), getattr(ps, name)), (key, name)
+        for k in ("progress_buf", "motion_start_times", "body_state"):
+            assert torch.equal(ref_sim[k], sim[k]), (key, k)
