@@ -87,6 +87,7 @@ class PlayStepsB200:
         self.overlap = os.environ.get("PULSE_ROLLOUT_OVERLAP", "1") != "0"   # next values of step t beside reset / actor of step t+1 (_whole_overlapped)
         self._side = None
         self._side_b = None
+        self.amp_with_step = n <= 4096      # _whole_overlapped: AMP row concurrently with the fused step kernel only where both are latency-bound
 
     # ------------------------------------------------------------------ the pieces of one step
     def _step_kw(self):
@@ -208,14 +209,19 @@ class PlayStepsB200:
                            obs_buf=self.obses[:, t], env_ids=ws["env_list"][:self.n], env_count=ws["count"], flags=_lib.STEP_OBS)
             pol.act_into(self.obses[:, t], actions=self.actions[:, t], neglogp=self.neglogp[:, t], mus=self.mus[:, t], values=self.values[t],
                          pd=(self.pd[0], self.pd[1], self.pd_tar), rng_step=t, side=A)
-            A.wait_stream(main)
-            with torch.cuda.stream(A):
-                prev = self.amp_obs[:, t - 1] if t > 0 else self.amp_obs[:, T - 1]
-                self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
-                                      fresh=self.amp_fresh, fresh_rows=self.amp_init)
+            def amp_row():
+                A.wait_stream(main)
+                with torch.cuda.stream(A):
+                    prev = self.amp_obs[:, t - 1] if t > 0 else self.amp_obs[:, T - 1]
+                    self.comp.amp_obs_row(body_state=s["body_state"], dof_pos=s["dof_pos"], dof_vel=s["dof_vel"], prev=prev, out=self.amp_obs[:, t],
+                                          fresh=self.amp_fresh, fresh_rows=self.amp_init)
+            if self.amp_with_step:
+                amp_row()                                            # beside the step kernel: both are latency-bound at small env counts
             if t > 0:
                 main.wait_stream(B)                                  # value_post(t-1) has read terminate_buf
             self._env_step(t)
+            if not self.amp_with_step:
+                amp_row()                                            # large env counts: two HBM-bound kernels gain nothing from sharing the GPU
             B.wait_stream(main)
             with torch.cuda.stream(B):
                 norm_done = torch.cuda.Event()

@@ -176,11 +176,13 @@ def test_overlapped_schedule_equals_the_sequential_one():
     from pulse_b200.rollout import PlayStepsB200
     n, T = 1024, 8
     runs = {}
-    for overlap, graphs in ((False, True), (True, False), (True, True)):
+    for overlap, graphs in ((False, True), (True, False), (True, True), ("amp_after_step", True)):
         tb, comp, sim = _sim(n, clips=64)
         pol = _policy(with_disc=True)
         ps = PlayStepsB200(comp, pol, sim, horizon=T, use_graphs=graphs, single_graph=True, reset_seed=9)
-        ps.overlap = overlap
+        ps.overlap = bool(overlap)
+        if overlap == "amp_after_step":
+            ps.amp_with_step = False        # the ordering used above 4096 envs
         ps.first_observation()
         for it in range(4):
             ps.play_steps()
@@ -188,7 +190,7 @@ def test_overlapped_schedule_equals_the_sequential_one():
         torch.cuda.synchronize()
         runs[(overlap, graphs)] = (ps, sim)
     ref, ref_sim = runs[(False, True)]
-    for key in ((True, False), (True, True)):
+    for key in ((True, False), (True, True), ("amp_after_step", True)):
         ps, sim = runs[key]
         for name in ("obses", "actions", "mus", "neglogp", "amp_obs", "values", "next_values", "rewards", "dones", "obs_carry", "adv", "ret"):
             assert torch.equal(getattr(ref, name), getattr(ps, name)), (key, name)
