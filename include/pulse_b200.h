@@ -9,7 +9,10 @@
  *   - every entry point returns 0 on success or a negative pulse_status; the message is available
  *     from pulse_last_error() (thread-local).  No exceptions cross the boundary;
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
- *     PULSE_ERR_CUDA.
+ *     PULSE_ERR_CUDA;
+ *   - ONE device per process (the reference's model: one Isaac Gym sim per process, run_hydra.py:117-131): launch attributes,
+ *     the SM count and the persistent-grid sizes are cached per process on first use, so a process must not drive two
+ *     different devices through this library; calls are made from one host thread per process, on the caller's stream.
  *
  * Each entry point cites the reference interface (file:line under the PULSE tree) it replaces.
  */
