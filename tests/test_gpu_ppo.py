@@ -289,5 +289,7 @@ def test_prefetched_minibatch_sequence_equals_inline_sequence():
                 assert d.mean().item() < 1e-6 and d.max().item() < 5e-4, (mode, d.mean().item(), d.max().item())
             elif k in (4, 5):        # loss sums
                 torch.testing.assert_close(a, b, atol=1e-6, rtol=2e-4, msg=lambda m: f"{mode} item {k}: {m}")
-            else:                    # running statistics: the same kernels on the same data in the same order (fp64 atomics: last bits)
-                torch.testing.assert_close(a, b, atol=0.0, rtol=1e-11, msg=lambda m: f"{mode} item {k}: {m}")
+            else:                    # running statistics: the same kernels on the same data in the same order.  The fp64 atomics add in a
+                # run-dependent order (last bits of sums of O(1) values: ~1e-16 absolute), so an element that happens to lie near zero has
+                # no meaningful RELATIVE error: the absolute floor covers it (seen once in ~8 full-suite runs with atol = 0)
+                torch.testing.assert_close(a, b, atol=1e-12, rtol=1e-11, msg=lambda m: f"{mode} item {k}: {m}")
