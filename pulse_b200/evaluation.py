@@ -104,10 +104,12 @@ class EvalLoopB200:
     """
 
     def __init__(self, num_envs: int, num_unique: int, keys: Sequence[str], load_chunk: Callable, reset_all: Callable, step: Callable,
-                 device="cuda:0", poll_every: int = 8):
+                 device="cuda:0", poll_every: int = 8, metrics=None):
         self.N, self.num_unique, self.keys = int(num_envs), int(num_unique), np.asarray(keys)
         self.load_chunk, self.reset_all, self.step_fn = load_chunk, reset_all, step
-        self.metrics = EvalMetricsB200(num_envs, device)
+        # `metrics`: an object with the EvalMetricsB200 interface (begin_chunk / step / finished / read); the CPU suite injects a numpy
+        # model of the device state machine to exercise this host loop without a GPU (tests/test_eval_host_cpu.py)
+        self.metrics = metrics if metrics is not None else EvalMetricsB200(num_envs, device)
         self.poll_every = max(1, int(poll_every))
 
     def run(self) -> Dict:

@@ -90,3 +90,51 @@ def test_chain_reducer_averages_every_slice_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # no NCCL / no CUDA here: the flat buffers must fall back to plain memory (peer = None), the moments stay whole, and the
+        # documented fallback sequence -- average_gradients on the flat gradient buffer -- is what every rank then runs
+        from pulse_b200.nets import FlatParams
+        f = FlatParams("cpu")
+        f.reserve(100, 7)
+        f.reserve(33)
+        f.finalize()                                       # default: peer mode wanted, unavailable -> silent plain allocation on CPU
+        ok = f.peer is None and f.shard_span() == (0, f.numel) and f.numel % 64 == 0
+        f.grads.fill_(float(rank + 1))
+        average_gradients(f.grads, world)
+        ok = ok and torch.allclose(f.grads, torch.full_like(f.grads, (world + 1) / 2))
+        f.gather_moments()                                 # no-op outside peer mode (must not issue a collective on one rank only)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_params_fall_back_to_plain_buffers_without_nccl_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30700 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_peer_shard_spans_cover_the_flat_buffer():
+    """The slice arithmetic of csrc/peer_adam.cu (per = ceil(n4 / world) float4s per rank) as FlatParams.shard_span states it."""
+    from pulse_b200.nets import FlatParams
+    for numel, world in ((5529600, 8), (5529600, 2), (64 * 7, 8), (64, 8), (31700032, 4)):
+        f = FlatParams("cpu")
+        f._numel = numel
+        spans = []
+        for r in range(world):
+            f.peer = {"world": world, "rank": r}
+            spans.append(f.shard_span())
+        assert spans[0][0] == 0 and spans[-1][1] == numel
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1)) and all(a % 4 == 0 and b % 4 == 0 for a, b in spans)
