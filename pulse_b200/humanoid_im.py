@@ -515,7 +515,9 @@ class HumanoidImB200Mixin:
         `_refresh_sim_tensors` with its `_reset_rb_*` restore (humanoid_amp.py:598-620) and `_compute_observations(env_ids)`.
         Default / Hybrid state initialisation is handed back to the reference."""
         name = getattr(getattr(self, "_state_init", None), "name", None)
-        if len(env_ids) == 0 or name not in ("Random", "Start"):
+        # HumanoidImGetup splits the reset envs into recovery / fall-state / reference-state episodes inside its own `_reset_actors`
+        # (humanoid_im_getup.py:135-182: Bernoulli draws, a pool of simulated fall states): that control flow stays the reference's.
+        if len(env_ids) == 0 or name not in ("Random", "Start") or hasattr(self, "_recovery_counter"):
             return super()._reset_envs(env_ids)
         if not self._pulse_ready:
             self._pulse_setup()
