@@ -433,6 +433,7 @@ def main():
     del tabs
     z = device_step_inputs(ml, n, seed=200 + rank)
     comp = HumanoidImCompute(ml)
+    os.environ.setdefault("PULSE_PEER_TIMEOUT_MS", "120000")  # ranks of a bench run stay in lock step: a peer missing for 2 min is a failure
     policy = PPOPolicy(device=dev, seed=0, with_disc=True)   # replicated: same seed on every rank (Horovod broadcast equivalent)
     disc = policy.disc
     AMP_MB = 4096                                        # amp_minibatch_size (im.yaml:81)

@@ -503,7 +503,7 @@ typedef struct {
   int64_t count;
   float max_norm, lr, beta1, beta2, eps;
   int32_t grid;
-  uint32_t timeout_ms;                     /* bound of every wait on a peer (0 = 20000) */
+  uint32_t timeout_ms;                     /* bound of every wait on a peer (0 = 30 min: ranks drift apart around rank-0-only work) */
   uint32_t reserved;
   int32_t* step;
   uint32_t* epoch;

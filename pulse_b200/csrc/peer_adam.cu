@@ -14,7 +14,7 @@
 //   phase 3  a last flag round: a rank's kernel ends only when all slices of ITS operand copy have landed.
 //
 // Each byte crosses NVLink once per direction; nothing is staged, no second kernel reads the reduced gradients back.  All waits are
-// bounded (a lost peer surfaces as a launch failure, never as a hung GPU).  Flags are monotonic epoch numbers kept on the device, so
+// bounded (timeout_ms, default 30 min: a lost peer surfaces as a launch failure, never as a GPU hung for good).  Flags are monotonic epoch numbers kept on the device, so
 // the launch is CUDA-graph replayable.
 #include <cuda_bf16.h>
 
@@ -24,7 +24,10 @@ namespace pulse {
 namespace {
 
 constexpr int kPeerThreads = 512;
-constexpr unsigned kDefaultTimeoutMs = 20000u;   // far beyond any legitimate wait
+// Default bound of a wait on a peer.  Ranks legitimately drift far apart in a training run -- rl_games checkpoints, logs and runs the
+// minutes-long evaluation pass on rank 0 only while the other ranks already sit in their next optimizer step -- so the default is the
+// order of a collective-library watchdog, not of a kernel; tests and probes pass seconds.
+constexpr unsigned kDefaultTimeoutMs = 30u * 60u * 1000u;
 
 __device__ __forceinline__ unsigned long long now_ns() {
   unsigned long long t;

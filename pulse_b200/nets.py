@@ -139,6 +139,7 @@ class FlatParams:
                        bar=torch.zeros(1, dtype=torch.int64, device=dev))
         a.epoch, a.cta_partials, a.grid_bar = scratch["epoch"].data_ptr(), scratch["partials"].data_ptr(), scratch["bar"].data_ptr()
         a.grid = int(os.environ.get("PULSE_PEER_GRID", "0"))
+        a.timeout_ms = int(os.environ.get("PULSE_PEER_TIMEOUT_MS", "0"))     # 0 = the library default (30 min, see csrc/peer_adam.cu)
         self.peer = dict(args=a, handles=(hg, hp, hb, hs), signals=sig, scratch=scratch, world=world, rank=rank, multicast=bool(a.mc_grads))
 
     def shard_span(self):

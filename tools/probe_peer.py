@@ -68,6 +68,7 @@ def main():
     ap.add_argument("--numel", type=int, default=5529600)      # the PPO + discriminator flat buffer of im.yaml (22 MB fp32)
     ap.add_argument("--iters", type=int, default=50)
     args = ap.parse_args()
+    os.environ.setdefault("PULSE_PEER_TIMEOUT_MS", "20000")
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
