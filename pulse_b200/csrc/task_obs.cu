@@ -11,7 +11,6 @@
 namespace pulse {
 namespace {
 
-
 __device__ __forceinline__ Quat ldq(const float* p) { return {p[0], p[1], p[2], p[3]}; }
 __device__ __forceinline__ Vec3 ldv(const float* p) { return {p[0], p[1], p[2]}; }
 __device__ __forceinline__ void stv(float* o, Vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
